@@ -1,0 +1,195 @@
+/*
+ * vgt_b200.h -- C-ABI of the B200 (sm_100a) backend for the occupancy -> SDF hot path of
+ * calderpg/voxelized_geometry_tools. Plain C: raw pointers, sizes, no C++/Eigen/torch types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference checkout). Grids use the reference's storage convention
+ * (common_robotics_utilities VoxelGrid; mirrored at
+ * src/voxelized_geometry_tools/cuda_voxelization_helpers.cu:281-282):
+ *     linear index = x * (ny * nz) + y * nz + z        (x slowest, z contiguous)
+ * OccupancyMap raw data is a packed float[nx*ny*nz] (include/.../occupancy_map.hpp:28-58).
+ *
+ * Conventions
+ *   - every function returns VGT_B200_OK (0) or an error code; vgt_b200_last_error() returns a
+ *     thread-local message for the last failing call on the calling thread.
+ *   - "host" entry points take HOST pointers and do their own H2D/D2H; "_dev" entry points take
+ *     DEVICE pointers on `device` plus a cudaStream_t (passed as void*; NULL = legacy default
+ *     stream) and never synchronise the host unless stated.
+ *   - all functions may be called concurrently from several host threads (each call sets the
+ *     device it needs; there is no global mutable state besides the thread-local error string).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails with
+ *     VGT_B200_ERR_DEVICE.
+ */
+#ifndef VGT_B200_H_
+#define VGT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGT_B200_API __attribute__((visibility("default")))
+
+enum
+{
+  VGT_B200_OK = 0,
+  /* maps to std::invalid_argument in the C++ adapter (sdfgen.hpp:123-126, pcv_if.hpp:30-41,267-288) */
+  VGT_B200_ERR_INVALID_ARGUMENT = 1,
+  /* maps to std::runtime_error (cuda.cu:26-33 "[msg] Cuda error [str]", dev_pcv.hpp:34-46) */
+  VGT_B200_ERR_DEVICE = 2,
+  VGT_B200_ERR_UNSUPPORTED = 3
+};
+
+/* "no opposite-class voxel anywhere": the reference's +inf squared distance. */
+#define VGT_B200_SQ_INF INT32_MAX
+
+/* Largest supported voxel count per axis (squared distances must stay below 2^31). */
+#define VGT_B200_MAX_AXIS 8192
+
+VGT_B200_API const char* vgt_b200_last_error(void);
+VGT_B200_API const char* vgt_b200_version(void);
+
+/* Replaces cuda_helpers::GetAvailableDevices() / IsAvailable()
+ * (src/.../cuda_voxelization_helpers.cu:562-637, 769-822). Returns the number of usable
+ * sm_100 devices (0 when there is none or the driver is missing; never an error). */
+VGT_B200_API int vgt_b200_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Signed distance field generation
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces OccupancyMap::ExtractSignedDistanceField<float> -> internal::ExtractSignedDistanceField
+ * (include/.../occupancy_map.hpp:174-210, include/.../signed_distance_field_generation.hpp:39-113
+ * and :115-285 for add_virtual_border) followed by SignedDistanceField::Lock()
+ * (include/.../signed_distance_field.hpp:765-787).
+ *   occupancy          host float[nx*ny*nz]; filled iff occ > 0.5 or (unknown_is_filled and occ == 0.5)
+ *   resolution         voxel edge length (> 0, finite); the grid must be uniform (sdfgen.hpp:123-126)
+ *   sdf_out            host float[nx*ny*nz]: +d outside, -d inside, +/-inf when a class is absent
+ *   out_min, out_max   may be NULL; the values Lock() would cache
+ */
+VGT_B200_API int vgt_b200_sdf_f32(
+    const float* occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, float* sdf_out, float* out_min,
+    float* out_max);
+
+/* Same for SignedDistanceField<double> (ExtractSignedDistanceFieldDouble, occupancy_map.cpp:250-254). */
+VGT_B200_API int vgt_b200_sdf_f64(
+    const float* occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, double* sdf_out, double* out_min,
+    double* out_max);
+
+/* For grids whose filled predicate is an opaque std::function (the other map types,
+ * include/.../signed_distance_field_generation.hpp:115-121): the adapter evaluates the predicate
+ * on the host into filled_mask (uint8, non-zero = filled) and calls this. */
+VGT_B200_API int vgt_b200_sdf_from_mask_f32(
+    const uint8_t* filled_mask, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int add_virtual_border, int device, float* sdf_out, float* out_min, float* out_max);
+
+/* Parity hook for internal::ComputeDistanceFieldTransformInPlace on the two 0/inf fields
+ * (include/.../signed_distance_field_generation.hpp:34-37, 47-80): both squared fields in voxel
+ * units as int32, VGT_B200_SQ_INF where the reference holds +inf. Host pointers. */
+VGT_B200_API int vgt_b200_edt_sq_i32(
+    const float* occupancy, int64_t nx, int64_t ny, int64_t nz, int unknown_is_filled, int device,
+    int32_t* dist_to_filled_sq, int32_t* dist_to_free_sq);
+
+/* Device-resident variants (no host copies, asynchronous on `stream`).
+ *   d_occupancy   device float[nx*ny*nz]
+ *   d_sdf_out     device float[nx*ny*nz]; also used as the scratch for the integer passes
+ *   d_min_max     device float[2] (min, max) or NULL; written by the last kernel on `stream`
+ */
+VGT_B200_API int vgt_b200_sdf_f32_dev(
+    const float* d_occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, float* d_sdf_out, float* d_min_max,
+    void* stream);
+
+/* d_scratch: device int32[nx*ny*nz] work buffer (the f64 output cannot double as scratch). */
+VGT_B200_API int vgt_b200_sdf_f64_dev(
+    const float* d_occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, int32_t* d_scratch,
+    double* d_sdf_out, double* d_min_max, void* stream);
+
+VGT_B200_API int vgt_b200_sdf_from_mask_f32_dev(
+    const uint8_t* d_filled_mask, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int add_virtual_border, int device, float* d_sdf_out, float* d_min_max, void* stream);
+
+/* ---- staged passes, for the slab-sharded multi-GPU path ----
+ * The sign-fused intermediate is one int32 per voxel: bit 31 = class (1 = filled), bits 0..30 =
+ * partial squared distance to the opposite class (0x7fffffff = none yet).
+ *
+ * vgt_b200_edt_local_passes_dev: passes along z (contiguous) and y on an x-slab
+ *   [nx_local, ny, nz]; both are independent per x, so a slab needs no neighbours.
+ *   Replaces the Y and Z loops of ComputeDistanceFieldTransformInPlace (sdfgen.cpp:315-390) for
+ *   both fields at once plus the marking loop (sdfgen.hpp:57-74).
+ * vgt_b200_edt_final_pass_f32_dev: the pass along x on a y-slab laid out [nx, ny_local, nz]
+ *   (after the all-to-all), fused with the sqrt*resolution combine (sdfgen.hpp:85-108) and the
+ *   min/max of Lock(). y_offset / ny_total / (x,z are whole) locate the slab inside the full grid
+ *   for the virtual border. d_in and d_sdf_out may alias (in-place).
+ */
+VGT_B200_API int vgt_b200_edt_local_passes_dev(
+    const float* d_occupancy, int64_t nx_local, int64_t ny, int64_t nz, int unknown_is_filled,
+    int device, int32_t* d_out, void* stream);
+
+VGT_B200_API int vgt_b200_edt_final_pass_f32_dev(
+    const int32_t* d_in, int64_t nx, int64_t ny_local, int64_t nz, int64_t y_offset,
+    int64_t ny_total, double resolution, int add_virtual_border, int device, float* d_sdf_out,
+    float* d_min_max, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Point cloud voxelization
+ * ------------------------------------------------------------------------------------------- */
+
+/* One cloud, as the adapter extracts it from a PointCloudWrapper
+ * (include/.../pointcloud_voxelization_interface.hpp:94-202). */
+typedef struct vgt_b200_cloud
+{
+  const double* points_xyz; /* num_points * 3 doubles, cloud frame (CopyPointLocationIntoDoublePtr) */
+  int64_t num_points;       /* PointCloudWrapper::Size() */
+  double x_gc[16];          /* X_GC = X_GW * X_WC, column-major 4x4 (Eigen .data(); cpu_pcv.cpp:176) */
+  double max_range;         /* PointCloudWrapper::MaxRange(), may be +inf */
+} vgt_b200_cloud;
+
+/* PointCloudVoxelizationFilterOptions (pointcloud_voxelization_interface.hpp:20-92). */
+typedef struct vgt_b200_filter_options
+{
+  double percent_seen_free;         /* (0, 1] */
+  int32_t outlier_points_threshold; /* > 0 */
+  int32_t num_cameras_seen_free;    /* > 0 */
+} vgt_b200_filter_options;
+
+/* Replaces <Backend>PointCloudVoxelizer::DoVoxelizePointClouds
+ * (src/.../cpu_pointcloud_voxelization.cpp:133-165 for semantics -- double-precision DDA,
+ * src/.../device_pointcloud_voxelization.cpp:65-181 for the call position). Host pointers.
+ *   static_occupancy   host float[V], copied to out_occupancy first (pcv_if.hpp:252)
+ *   out_occupancy      host float[V]
+ *   out_counts         optional host int32[num_clouds][V][2] = {seen_free, seen_filled} per cloud
+ *                      (the CpuVoxelizationTrackingCell layout, cpu_pcv.hpp:24-32); NULL to skip
+ *   out_seconds        optional double[2] = {raycasting, filtering} (VoxelizerRuntime, pcv_if.hpp:206-229)
+ */
+VGT_B200_API int vgt_b200_voxelize_f64(
+    const float* static_occupancy, int64_t nx, int64_t ny, int64_t nz, double voxel_size,
+    const vgt_b200_cloud* clouds, int32_t num_clouds, const vgt_b200_filter_options* filter,
+    int device, float* out_occupancy, int32_t* out_counts, double* out_seconds);
+
+/* Device-resident pieces (asynchronous on `stream`).
+ * vgt_b200_raycast_f64_dev accumulates one cloud into d_counts (int32[V][2], caller zeroes it).
+ *   Replaces CpuPointCloudVoxelizer::DoRaycastPointCloud (cpu_pcv.cpp:167-206) and, positionally,
+ *   DeviceVoxelizationHelperInterface::RaycastPoints (device_voxelization_interface.hpp:149-156).
+ * vgt_b200_filter_dev applies the per-camera rule and the combine to d_occupancy in place.
+ *   Replaces DoCombineAndFilterGrids (cpu_pcv.cpp:438-497) / FilterTrackingGrids
+ *   (device_voxelization_interface.hpp:162-167). d_counts is int32[num_grids][V][2].
+ */
+VGT_B200_API int vgt_b200_raycast_f64_dev(
+    const double* d_points_xyz, int64_t num_points, const double* x_gc /* host, 16 */,
+    double max_range, int64_t nx, int64_t ny, int64_t nz, double voxel_size, int device,
+    int32_t* d_counts, void* stream);
+
+VGT_B200_API int vgt_b200_filter_dev(
+    const int32_t* d_counts, int32_t num_grids, int64_t num_voxels,
+    const vgt_b200_filter_options* filter, int device, float* d_occupancy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VGT_B200_H_ */

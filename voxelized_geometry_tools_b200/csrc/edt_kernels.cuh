@@ -1,0 +1,57 @@
+// Exact signed squared Euclidean distance transform for sm_100a, as three line passes.
+//
+// Representation between passes ("sign-fused", one int32 per voxel for BOTH reference fields):
+//   bit 31      class of the voxel (1 = filled, 0 = free)
+//   bits 0..30  partial squared distance (voxel units) to the nearest voxel of the OPPOSITE class
+//               over the axes processed so far; kNone (0x7fffffff) = none found yet.
+// The reference keeps two VoxelGrid<double> fields (sdfgen.hpp:47-55); at every voxel exactly one
+// of them is 0, so the non-zero one plus the class bit carries the same information.
+//
+// Why one sweep per line serves both fields: a voxel of the opposite class is a zero-height site,
+// and a zero-height site hides every site behind it. So a line splits into maximal same-class
+// runs; inside a run [a, b] the answer for q is
+//     min( lower envelope of the run's own parabolas at q, (q-(a-1))^2, ((b+1)-q)^2 )
+// with the two boundary terms present only when a-1 / b+1 are inside the line.
+//
+// The 1-D transform is exact (squared distances are integers; the pop test is a cross-multiplied
+// integer comparison), so the result equals the reference's F-H/brute-force output
+// (sdfgen.cpp:85-226) independent of pass order.
+#pragma once
+
+#include <cstdint>
+
+namespace vgt_b200
+{
+namespace edt
+{
+constexpr uint32_t kNone = 0x7fffffffu;      // "+inf" in bits 0..30
+constexpr uint32_t kClassBit = 0x80000000u;  // filled
+constexpr int kWarp = 32;
+
+// Geometry of one family of parallel lines. Column c in [0, inner_count) of outer block o starts
+// at element o * outer_stride + c; consecutive elements of a line are line_stride apart.
+struct LineFamily
+{
+  int64_t num_outer;
+  int64_t outer_stride;
+  int64_t inner_count;
+  int64_t line_stride;
+  int32_t length;
+};
+
+// What the last pass needs to turn squared voxel distances into the SDF.
+struct FinalizeParams
+{
+  double resolution;
+  int32_t add_virtual_border;
+  // Full-grid extents and the position of this (slab) family inside the full grid, used only by
+  // the virtual border: voxel (line index q, column c) is at
+  //   x = q, y = y_offset + c / nz, z = c % nz.
+  int32_t nx_total;
+  int32_t ny_total;
+  int32_t nz_total;
+  int32_t y_offset;
+  int32_t nz;  // columns per y row of this family
+};
+}  // namespace edt
+}  // namespace vgt_b200

@@ -1,0 +1,145 @@
+"""Device-resident entry points: torch CUDA tensors in, torch CUDA tensors out.
+
+torch is only the owner of device memory and streams here; every kernel is launched by
+libvgt_b200.so through the ``*_dev`` C-ABI functions on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+from .pointcloud_voxelization import PointCloudVoxelizationFilterOptions
+
+
+def _stream_handle(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(tensor: torch.Tensor, dtype: torch.dtype, what: str) -> None:
+    if not tensor.is_cuda:
+        raise _capi.BackendUnavailable(f"{what} must live on a CUDA device (no CPU fallback)")
+    if tensor.dtype != dtype or not tensor.is_contiguous():
+        raise ValueError(f"{what} must be a contiguous {dtype} tensor")
+
+
+def signed_distance_field(occupancy: torch.Tensor, resolution: float,
+                          unknown_is_filled: bool = True, add_virtual_border: bool = False,
+                          out: torch.Tensor | None = None, min_max: torch.Tensor | None = None,
+                          compute_min_max: bool = True):
+    """ExtractSignedDistanceField<float> on a device-resident occupancy grid [nx, ny, nz].
+
+    Returns (sdf float32 [nx, ny, nz], min_max float32 [2] or None). Asynchronous."""
+    _require_cuda(occupancy, torch.float32, "occupancy")
+    if occupancy.dim() != 3:
+        raise ValueError("occupancy must be indexed [x, y, z]")
+    device = occupancy.device
+    if out is None:
+        out = torch.empty_like(occupancy)
+    _require_cuda(out, torch.float32, "out")
+    if compute_min_max and min_max is None:
+        min_max = torch.empty(2, dtype=torch.float32, device=device)
+    nx, ny, nz = occupancy.shape
+    code = _capi.library().vgt_b200_sdf_f32_dev(
+        occupancy.data_ptr(), nx, ny, nz, float(resolution), int(unknown_is_filled),
+        int(add_virtual_border), device.index or 0, out.data_ptr(),
+        min_max.data_ptr() if compute_min_max else None, _stream_handle(device))
+    _capi.check(code)
+    return out, (min_max if compute_min_max else None)
+
+
+def signed_distance_field_f64(occupancy: torch.Tensor, resolution: float,
+                              unknown_is_filled: bool = True, add_virtual_border: bool = False):
+    _require_cuda(occupancy, torch.float32, "occupancy")
+    device = occupancy.device
+    out = torch.empty(occupancy.shape, dtype=torch.float64, device=device)
+    scratch = torch.empty(occupancy.shape, dtype=torch.int32, device=device)
+    min_max = torch.empty(2, dtype=torch.float64, device=device)
+    nx, ny, nz = occupancy.shape
+    code = _capi.library().vgt_b200_sdf_f64_dev(
+        occupancy.data_ptr(), nx, ny, nz, float(resolution), int(unknown_is_filled),
+        int(add_virtual_border), device.index or 0, scratch.data_ptr(), out.data_ptr(),
+        min_max.data_ptr(), _stream_handle(device))
+    _capi.check(code)
+    return out, min_max
+
+
+def signed_distance_field_from_mask(mask: torch.Tensor, resolution: float,
+                                    add_virtual_border: bool = False):
+    _require_cuda(mask, torch.uint8, "mask")
+    device = mask.device
+    out = torch.empty(mask.shape, dtype=torch.float32, device=device)
+    min_max = torch.empty(2, dtype=torch.float32, device=device)
+    nx, ny, nz = mask.shape
+    code = _capi.library().vgt_b200_sdf_from_mask_f32_dev(
+        mask.data_ptr(), nx, ny, nz, float(resolution), int(add_virtual_border),
+        device.index or 0, out.data_ptr(), min_max.data_ptr(), _stream_handle(device))
+    _capi.check(code)
+    return out, min_max
+
+
+def edt_local_passes(occupancy_slab: torch.Tensor, unknown_is_filled: bool = True,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
+    """z and y passes on an x-slab [nx_local, ny, nz] -> sign-fused int32 words."""
+    _require_cuda(occupancy_slab, torch.float32, "occupancy_slab")
+    device = occupancy_slab.device
+    if out is None:
+        out = torch.empty(occupancy_slab.shape, dtype=torch.int32, device=device)
+    _require_cuda(out, torch.int32, "out")
+    nx, ny, nz = occupancy_slab.shape
+    code = _capi.library().vgt_b200_edt_local_passes_dev(
+        occupancy_slab.data_ptr(), nx, ny, nz, int(unknown_is_filled), device.index or 0,
+        out.data_ptr(), _stream_handle(device))
+    _capi.check(code)
+    return out
+
+
+def edt_final_pass(packed: torch.Tensor, y_offset: int, ny_total: int, resolution: float,
+                   add_virtual_border: bool = False, compute_min_max: bool = True):
+    """x pass + finalize on a y-slab [nx, ny_local, nz] of sign-fused words (in place: the
+    returned float32 tensor shares storage with ``packed``)."""
+    _require_cuda(packed, torch.int32, "packed")
+    device = packed.device
+    nx, ny_local, nz = packed.shape
+    out = packed.view(torch.float32)
+    min_max = torch.empty(2, dtype=torch.float32, device=device) if compute_min_max else None
+    code = _capi.library().vgt_b200_edt_final_pass_f32_dev(
+        packed.data_ptr(), nx, ny_local, nz, int(y_offset), int(ny_total), float(resolution),
+        int(add_virtual_border), device.index or 0, out.data_ptr(),
+        min_max.data_ptr() if compute_min_max else None, _stream_handle(device))
+    _capi.check(code)
+    return out, min_max
+
+
+def raycast_cloud(points_xyz: torch.Tensor, x_gc, max_range: float, counts: torch.Tensor,
+                  voxel_size: float) -> torch.Tensor:
+    """Accumulates one cloud (float64 [N, 3], cloud frame) into counts int32 [nx, ny, nz, 2]."""
+    _require_cuda(points_xyz, torch.float64, "points_xyz")
+    _require_cuda(counts, torch.int32, "counts")
+    if counts.dim() != 4 or counts.shape[3] != 2:
+        raise ValueError("counts must be [nx, ny, nz, 2]")
+    device = counts.device
+    column_major = np.ascontiguousarray(np.asarray(x_gc, dtype=np.float64).reshape(4, 4).T)
+    nx, ny, nz, _ = counts.shape
+    code = _capi.library().vgt_b200_raycast_f64_dev(
+        points_xyz.data_ptr(), points_xyz.shape[0],
+        column_major.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), float(max_range), nx, ny,
+        nz, float(voxel_size), device.index or 0, counts.data_ptr(), _stream_handle(device))
+    _capi.check(code)
+    return counts
+
+
+def filter_grids(counts: torch.Tensor, occupancy: torch.Tensor,
+                 filter_options: PointCloudVoxelizationFilterOptions) -> torch.Tensor:
+    """counts int32 [num_grids, nx, ny, nz, 2]; occupancy float32 [nx, ny, nz] updated in place."""
+    _require_cuda(counts, torch.int32, "counts")
+    _require_cuda(occupancy, torch.float32, "occupancy")
+    device = occupancy.device
+    options = filter_options.as_struct()
+    code = _capi.library().vgt_b200_filter_dev(
+        counts.data_ptr(), counts.shape[0], occupancy.numel(), ctypes.byref(options),
+        device.index or 0, occupancy.data_ptr(), _stream_handle(device))
+    _capi.check(code)
+    return occupancy

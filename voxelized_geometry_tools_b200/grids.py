@@ -1,0 +1,293 @@
+"""Host-side mirror of the grid value types on the hot path.
+
+Names, argument meaning and error behaviour follow the reference so parity tests read like the
+reference's own (paths relative to the reference checkout):
+
+* ``OccupancyMap``                      include/voxelized_geometry_tools/occupancy_map.hpp:65-216
+* ``SignedDistanceField``               include/voxelized_geometry_tools/signed_distance_field.hpp:193-211, 724-795
+* ``SignedDistanceFieldGenerationParameters``  signed_distance_field.hpp:1234-1264
+* ``VoxelGridSizes``                    common_robotics_utilities voxel_grid.hpp (FromGridSizes /
+  FromVoxelCounts; cell count = ceil(size / voxel_size), consistent with
+  test/sdf_generation_test.cpp:267-272 -> 4 x 8 x 12)
+
+Only what the occupancy -> SDF path needs is here: storage, the filled predicate's inputs, the
+Extract entry points and Lock()/min-max. Queries, gradients and serialization are out of scope.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+
+
+@dataclass(frozen=True)
+class VoxelGridSizes:
+    voxel_size: float
+    num_x_voxels: int
+    num_y_voxels: int
+    num_z_voxels: int
+
+    @staticmethod
+    def FromGridSizes(voxel_size: float, sizes) -> "VoxelGridSizes":
+        if not (voxel_size > 0.0 and math.isfinite(voxel_size)):
+            raise ValueError("voxel_size must be positive and finite")
+        counts = [int(math.ceil(float(s) / voxel_size)) for s in sizes]
+        if min(counts) < 1:
+            raise ValueError("all grid sizes must be positive")
+        return VoxelGridSizes(float(voxel_size), *counts)
+
+    @staticmethod
+    def FromVoxelCounts(voxel_size: float, counts) -> "VoxelGridSizes":
+        if not (voxel_size > 0.0 and math.isfinite(voxel_size)):
+            raise ValueError("voxel_size must be positive and finite")
+        counts = [int(c) for c in counts]
+        if min(counts) < 1:
+            raise ValueError("all voxel counts must be positive")
+        return VoxelGridSizes(float(voxel_size), *counts)
+
+    @property
+    def shape(self):
+        return (self.num_x_voxels, self.num_y_voxels, self.num_z_voxels)
+
+    def sizes(self):
+        return tuple(c * self.voxel_size for c in self.shape)
+
+
+class SignedDistanceFieldGenerationParameters:
+    """signed_distance_field.hpp:1234-1264. ``parallelism`` is accepted and ignored on device."""
+
+    def __init__(self, oob_value=float("inf"), parallelism=None, unknown_is_filled: bool = True,
+                 add_virtual_border: bool = False):
+        self._oob_value = oob_value
+        self._parallelism = parallelism
+        self._unknown_is_filled = bool(unknown_is_filled)
+        self._add_virtual_border = bool(add_virtual_border)
+
+    def OOBValue(self):
+        return self._oob_value
+
+    def Parallelism(self):
+        return self._parallelism
+
+    def UnknownIsFilled(self) -> bool:
+        return self._unknown_is_filled
+
+    def AddVirtualBorder(self) -> bool:
+        return self._add_virtual_border
+
+
+class SignedDistanceField:
+    """Result container: raw [x, y, z] data, frame, lock flag and cached min/max."""
+
+    def __init__(self, origin_transform, frame: str, sizes: VoxelGridSizes, data: np.ndarray,
+                 oob_value, minimum_maximum=None):
+        self._origin_transform = np.array(origin_transform, dtype=np.float64).reshape(4, 4)
+        self._frame = frame
+        self._sizes = sizes
+        self._data = data
+        self._oob_value = oob_value
+        self._locked = False
+        self._minimum_maximum = minimum_maximum
+
+    # --- VoxelGridBase-like accessors -------------------------------------------------------
+    def NumXVoxels(self):
+        return self._sizes.num_x_voxels
+
+    def NumYVoxels(self):
+        return self._sizes.num_y_voxels
+
+    def NumZVoxels(self):
+        return self._sizes.num_z_voxels
+
+    def Resolution(self):
+        return self._sizes.voxel_size
+
+    def Frame(self):
+        return self._frame
+
+    def ControlSizes(self):
+        return self._sizes
+
+    def OriginTransform(self):
+        return self._origin_transform
+
+    def GetImmutableRawData(self) -> np.ndarray:
+        return self._data
+
+    def GetIndexImmutable(self, x: int, y: int, z: int):
+        """Value at an index; out of bounds returns the OOB value like a failed query would."""
+        if (0 <= x < self.NumXVoxels() and 0 <= y < self.NumYVoxels()
+                and 0 <= z < self.NumZVoxels()):
+            return self._data[x, y, z]
+        return self._data.dtype.type(self._oob_value)
+
+    # --- locking + min/max (signed_distance_field.hpp:765-789) ----------------------------
+    def IsLocked(self) -> bool:
+        return self._locked
+
+    def Lock(self) -> None:
+        if self._minimum_maximum is None:
+            self._minimum_maximum = (self._data.min(), self._data.max())
+        self._locked = True
+        self._data.setflags(write=False)
+
+    def Unlock(self) -> None:
+        self._locked = False
+        self._data = np.array(self._data)  # writable copy
+        self._minimum_maximum = None
+
+    def GetMinimumMaximum(self):
+        if not self._locked:
+            raise RuntimeError("Cannot get min/max of an unlocked SDF")
+        return self._minimum_maximum
+
+
+class OccupancyMap:
+    """Dense occupancy grid: one float per cell, <0.5 free, 0.5 unknown, >0.5 filled
+    (occupancy_map.hpp:28-58). Data is indexed [x, y, z], z contiguous."""
+
+    def __init__(self, origin_transform, frame: str, sizes: VoxelGridSizes,
+                 default_occupancy: float = 0.0, data: np.ndarray | None = None):
+        self._origin_transform = np.array(origin_transform, dtype=np.float64).reshape(4, 4)
+        self._frame = frame
+        self._sizes = sizes
+        if data is None:
+            self._data = np.full(sizes.shape, default_occupancy, dtype=np.float32)
+        else:
+            data = np.ascontiguousarray(data, dtype=np.float32)
+            if data.shape != sizes.shape:
+                raise ValueError("data shape does not match the grid sizes")
+            self._data = data
+
+    def IsInitialized(self) -> bool:
+        return True
+
+    def HasUniformVoxelSize(self) -> bool:
+        return True  # VoxelGridSizes here only models cubic voxels
+
+    def NumXVoxels(self):
+        return self._sizes.num_x_voxels
+
+    def NumYVoxels(self):
+        return self._sizes.num_y_voxels
+
+    def NumZVoxels(self):
+        return self._sizes.num_z_voxels
+
+    def NumTotalVoxels(self):
+        return self._data.size
+
+    def VoxelXSize(self):
+        return self._sizes.voxel_size
+
+    def ControlSizes(self):
+        return self._sizes
+
+    def Frame(self):
+        return self._frame
+
+    def OriginTransform(self):
+        return self._origin_transform
+
+    def InverseOriginTransform(self):
+        rotation = self._origin_transform[:3, :3]
+        translation = self._origin_transform[:3, 3]
+        inverse = np.eye(4)
+        inverse[:3, :3] = rotation.T
+        inverse[:3, 3] = -(rotation.T @ translation)
+        return inverse
+
+    def GetMutableRawData(self) -> np.ndarray:
+        return self._data
+
+    def GetImmutableRawData(self) -> np.ndarray:
+        return self._data
+
+    def SetIndex(self, x: int, y: int, z: int, occupancy: float) -> bool:
+        if (0 <= x < self.NumXVoxels() and 0 <= y < self.NumYVoxels()
+                and 0 <= z < self.NumZVoxels()):
+            self._data[x, y, z] = occupancy
+            return True
+        return False
+
+    def copy(self) -> "OccupancyMap":
+        return OccupancyMap(self._origin_transform, self._frame, self._sizes,
+                            data=self._data.copy())
+
+    # --- the path's entry points (occupancy_map.hpp:174-216, occupancy_map.cpp:250-260) ----
+    def ExtractSignedDistanceField(self, parameters: SignedDistanceFieldGenerationParameters,
+                                   dtype=np.float32, device: int = 0) -> SignedDistanceField:
+        _capi.require_device(device)
+        lib = _capi.library()
+        occupancy = self._data
+        nx, ny, nz = self._sizes.shape
+        out = np.empty(self._sizes.shape, dtype=dtype)
+        if np.dtype(dtype) == np.float32:
+            lo, hi = ctypes.c_float(), ctypes.c_float()
+            code = lib.vgt_b200_sdf_f32(
+                occupancy.ctypes.data, nx, ny, nz, self._sizes.voxel_size,
+                int(parameters.UnknownIsFilled()), int(parameters.AddVirtualBorder()), device,
+                out.ctypes.data, ctypes.byref(lo), ctypes.byref(hi))
+        elif np.dtype(dtype) == np.float64:
+            lo, hi = ctypes.c_double(), ctypes.c_double()
+            code = lib.vgt_b200_sdf_f64(
+                occupancy.ctypes.data, nx, ny, nz, self._sizes.voxel_size,
+                int(parameters.UnknownIsFilled()), int(parameters.AddVirtualBorder()), device,
+                out.ctypes.data, ctypes.byref(lo), ctypes.byref(hi))
+        else:
+            raise ValueError("SDF scalar type must be float32 or float64")
+        _capi.check(code)
+        sdf = SignedDistanceField(
+            self._origin_transform, self._frame, self._sizes, out, parameters.OOBValue(),
+            minimum_maximum=(out.dtype.type(lo.value), out.dtype.type(hi.value)))
+        sdf.Lock()
+        return sdf
+
+    def ExtractSignedDistanceFieldFloat(self, parameters, device: int = 0):
+        return self.ExtractSignedDistanceField(parameters, np.float32, device)
+
+    def ExtractSignedDistanceFieldDouble(self, parameters, device: int = 0):
+        return self.ExtractSignedDistanceField(parameters, np.float64, device)
+
+
+def ExtractSignedDistanceFieldFromMask(filled_mask: np.ndarray, origin_transform, frame: str,
+                                       sizes: VoxelGridSizes,
+                                       parameters: SignedDistanceFieldGenerationParameters,
+                                       device: int = 0) -> SignedDistanceField:
+    """internal::ExtractSignedDistanceField for an opaque predicate
+    (signed_distance_field_generation.hpp:115-121): the caller evaluates it into a mask."""
+    _capi.require_device(device)
+    mask = np.ascontiguousarray(filled_mask, dtype=np.uint8)
+    if mask.shape != sizes.shape:
+        raise ValueError("mask shape does not match the grid sizes")
+    out = np.empty(sizes.shape, dtype=np.float32)
+    lo, hi = ctypes.c_float(), ctypes.c_float()
+    code = _capi.library().vgt_b200_sdf_from_mask_f32(
+        mask.ctypes.data, *sizes.shape, sizes.voxel_size, int(parameters.AddVirtualBorder()),
+        device, out.ctypes.data, ctypes.byref(lo), ctypes.byref(hi))
+    _capi.check(code)
+    sdf = SignedDistanceField(origin_transform, frame, sizes, out, parameters.OOBValue(),
+                              minimum_maximum=(np.float32(lo.value), np.float32(hi.value)))
+    sdf.Lock()
+    return sdf
+
+
+def ComputeSquaredDistanceFields(occupancy: np.ndarray, unknown_is_filled: bool = True,
+                                 device: int = 0):
+    """Parity hook: (dist_to_filled_sq, dist_to_free_sq) int32, _capi.SQ_INF = the reference's +inf.
+    Mirrors the two ComputeDistanceFieldTransformInPlace calls (sdfgen.hpp:76-80)."""
+    _capi.require_device(device)
+    occ = np.ascontiguousarray(occupancy, dtype=np.float32)
+    if occ.ndim != 3:
+        raise ValueError("occupancy must be indexed [x, y, z]")
+    to_filled = np.empty(occ.shape, dtype=np.int32)
+    to_free = np.empty(occ.shape, dtype=np.int32)
+    code = _capi.library().vgt_b200_edt_sq_i32(
+        occ.ctypes.data, *occ.shape, int(unknown_is_filled), device, to_filled.ctypes.data,
+        to_free.ctypes.data)
+    _capi.check(code)
+    return to_filled, to_free
