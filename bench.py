@@ -1,0 +1,409 @@
+#!/usr/bin/env python3
+"""Benchmark of the occupancy -> SDF hot path on B200 (BASELINE.json metric: SDF Gvoxels/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one ExtractSignedDistanceField<float> over one synthetic occupancy grid.
+Workload (weak scaling, 512^3 voxels per GPU, x-slab sharded):
+    N=1  512 x 512 x 512      (BASELINE config 2: clustered spheres ~10 % filled, 1 % unknown)
+    N=2  1024 x 512 x 512
+    N=4  1024 x 1024 x 512
+    N=8  1024 x 1024 x 1024   (BASELINE config 4)
+Every grid is far larger than the 126 MB L2 (>= 512 MiB in, >= 512 MiB out), so no L2 flush is
+needed between iterations.
+
+value  = voxels / s with the occupancy already resident in HBM (CUDA events, max over ranks).
+e2e    = the same through the drop-in host entry point vgt_b200_sdf_f32 (host buffers in, host
+         buffers out; H2D + D2H inside the timed region), per rank on its slab at N>1.
+roofline: the dominant kernel (x pass + finalize), algorithmic 8 B/voxel, timed with CUDA events
+         between the kernels on the launching stream (vgt_b200_sdf_f32_dev_profile).
+cpu_baseline / --impl reference: the CPU oracle (our restatement of the reference CPU path, or
+         the reference's own EDT source when oracle/_ref was built) on a bounded 256^3 sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+RESOLUTION = 0.02
+SDF_BYTES_PER_VOXEL = 24           # 3 passes x (4 B in + 4 B out), SURVEY.md section 8d
+PASS_BYTES_PER_VOXEL = 8
+KERNELS_PER_STEP = 5               # scan, y envelope, key reset, x envelope + finalize, key decode
+CPU_SAMPLE_DIMS = (256, 256, 256)
+
+
+def workload_dims(n_gpus: int):
+    return {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512),
+            8: (1024, 1024, 1024)}.get(n_gpus, (512 * n_gpus, 512, 512))
+
+
+def measured_peaks():
+    path = REPO / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={self.QUERY}",
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                fields = [f.strip() for f in out.stdout.strip().split(",")]
+                if len(fields) >= 6:
+                    self.samples.append(fields)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [name for i, name in enumerate(names)
+                   if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_arm(steps: int, warmup: int):
+    """Times the CPU path on the host cores: kind 'reference' when oracle/_ref exists (the
+    reference's own signed_distance_field_generation.cpp), else 'port' (our restatement)."""
+    import numpy as np
+    from oracle import oracle
+    from voxelized_geometry_tools_b200 import synthetic
+    occupancy = synthetic.clustered_spheres_occupancy(CPU_SAMPLE_DIMS)
+    kind = "port"
+    runner = lambda: oracle.sdf(occupancy, RESOLUTION, threads=0)  # noqa: E731
+    try:
+        from oracle import reference_oracle
+        if reference_oracle.available():
+            kind = "reference"
+            runner = lambda: reference_oracle.sdf(occupancy, RESOLUTION, threads=0)  # noqa: E731
+    except Exception:
+        pass
+    cores = oracle.max_threads()
+    for _ in range(warmup):
+        runner()
+    times = []
+    for _ in range(steps):
+        begin = time.perf_counter()
+        runner()
+        times.append(time.perf_counter() - begin)
+    seconds = sum(times) / len(times)
+    voxels = float(np.prod(CPU_SAMPLE_DIMS))
+    return {"value": voxels / seconds / 1e9, "unit": "Gvoxels/s", "cores": cores, "kind": kind,
+            "sample": f"{'x'.join(map(str, CPU_SAMPLE_DIMS))} clustered-spheres grid (1/8 of the "
+                      f"512^3 workload), ExtractSignedDistanceField<float>, {steps} run(s), "
+                      f"{seconds:.3f} s each",
+            "seconds_per_sample": seconds}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warmup = min(args.warmup, 1)
+    baseline = cpu_reference_arm(steps, warmup)
+    dims = workload_dims(args.gpus)
+    line = {
+        "impl": "reference", "metric": "sdf_gvoxels_per_s", "value": baseline["value"],
+        "unit": "Gvoxels/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": baseline["seconds_per_sample"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{'x'.join(map(str, dims))} occupancy -> SDF<float> "
+                               "(clustered spheres ~10% filled, 1% unknown)",
+                   "sample": baseline["sample"]},
+        "cpu_baseline": {k: baseline[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": baseline["value"], "unit": "Gvoxels/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from voxelized_geometry_tools_b200 import _capi, device as vdev, sharded, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise _capi.BackendUnavailable("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world if distributed else 1
+    dims = workload_dims(n_gpus)
+    voxels = float(np.prod(dims))
+
+    plan = sharded.ShardedSignedDistanceField(dims, rank=rank, world_size=n_gpus) \
+        if distributed else None
+    x_range = plan.x_range if distributed else (0, dims[0])
+    occupancy = synthetic.clustered_spheres_occupancy_torch(dims, dev, x_range=x_range)
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    out = None if distributed else torch.empty_like(occupancy)
+    min_max = torch.empty(2, dtype=torch.float32, device=dev)
+
+    def step():
+        if distributed:
+            return plan.extract(occupancy, RESOLUTION)
+        return vdev.signed_distance_field(occupancy, RESOLUTION, out=out, min_max=min_max)
+
+    for _ in range(max(3, args.warmup)):
+        result = step()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as sampler:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            result = step()
+        stop.record()
+        barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    if distributed:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = voxels / (ms_per_step * 1e-3) / 1e9
+    sdf_min_max = [float(v) for v in result[1].tolist()]
+
+    # ---- per-kernel timing for the roofline (rank-local grid, events between the kernels) ----
+    pass_ms = None
+    if not distributed:
+        samples = [vdev.signed_distance_field_profile(occupancy, RESOLUTION, out, min_max)
+                   for _ in range(max(3, args.steps))]
+        pass_ms = [statistics.mean(s[i] for s in samples) for i in range(3)]
+    peak, peak_kind = measured_peaks()
+    roofline = None
+    if pass_ms is not None:
+        dominant = max(range(3), key=lambda i: pass_ms[i])
+        names = ["ScanContiguousAxisKernel (z)", "EnvelopeAxisKernel (y)",
+                 "EnvelopeAxisKernel (x + finalize)"]
+        achieved = PASS_BYTES_PER_VOXEL * voxels / (pass_ms[dominant] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": names[dominant], "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_kind": peak_kind,
+                    "algorithmic_bytes_per_launch": PASS_BYTES_PER_VOXEL * voxels,
+                    "pass_ms": {"z_scan": pass_ms[0], "y_envelope": pass_ms[1],
+                                "x_envelope_finalize": pass_ms[2]},
+                    "whole_sdf": {"achieved": SDF_BYTES_PER_VOXEL * voxels / (ms_per_step * 1e-3) / 1e9,
+                                  "frac": SDF_BYTES_PER_VOXEL * voxels / (ms_per_step * 1e-3) / 1e9
+                                  / (peak * n_gpus),
+                                  "bytes_per_voxel": SDF_BYTES_PER_VOXEL}}
+    else:
+        whole = SDF_BYTES_PER_VOXEL * voxels / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "whole SDF (3 passes + all-to-all)",
+                    "achieved": whole, "peak": peak * n_gpus, "unit": "GB/s",
+                    "frac": whole / (peak * n_gpus), "traffic": None, "peak_kind": peak_kind}
+
+    # ---- end to end through the host C-ABI (pinned host buffers, H2D + D2H timed) ----
+    lib = _capi.library()
+    local_shape = tuple(occupancy.shape)
+    host_in = torch.empty(local_shape, dtype=torch.float32).pin_memory()
+    host_in.copy_(occupancy)
+    host_out = torch.empty(local_shape, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize(dev)
+    e2e = None
+    if not distributed:
+        lo, hi = ctypes.c_float(), ctypes.c_float()
+
+        def host_step():
+            code = lib.vgt_b200_sdf_f32(host_in.data_ptr(), *local_shape, RESOLUTION, 1, 0,
+                                        local_rank, host_out.data_ptr(), ctypes.byref(lo),
+                                        ctypes.byref(hi))
+            _capi.check(code)
+
+        for _ in range(2):
+            host_step()
+        begin = time.perf_counter()
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            host_step()
+        e2e_seconds = (time.perf_counter() - begin) / e2e_steps
+        e2e = {"value": voxels / e2e_seconds / 1e9, "unit": "Gvoxels/s",
+               "h2d_bytes_per_step": int(4 * voxels), "d2h_bytes_per_step": int(4 * voxels + 8),
+               "ms_per_step": e2e_seconds * 1e3,
+               "api": "vgt_b200_sdf_f32 (host pointers, pinned)"}
+    else:
+        # Per-rank host slabs in, y-slabs out, through the sharded public API.
+        def host_step():
+            slab = host_in.to(dev, non_blocking=True)
+            sdf, mm = plan.extract(slab, RESOLUTION)
+            host_sdf = sdf.to("cpu", non_blocking=True)
+            mm.tolist()
+            torch.cuda.synchronize(dev)
+            return host_sdf
+
+        for _ in range(2):
+            host_step()
+        barrier()
+        begin = time.perf_counter()
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            host_step()
+        barrier()
+        e2e_seconds = (time.perf_counter() - begin) / e2e_steps
+        t = torch.tensor([e2e_seconds], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_seconds = float(t.item())
+        e2e = {"value": voxels / e2e_seconds / 1e9, "unit": "Gvoxels/s",
+               "h2d_bytes_per_step": int(4 * voxels), "d2h_bytes_per_step": int(4 * voxels + 8),
+               "ms_per_step": e2e_seconds * 1e3,
+               "api": "ShardedSignedDistanceField.extract (host slabs in/out per rank)"}
+
+    # ---- voxelizer (config 3) on rank 0 at N=1: Mrays/s beside the main metric ----
+    voxelizer = None
+    if not distributed and not args.skip_voxelizer:
+        voxelizer = bench_voxelizer(dev, peak)
+
+    cpu_baseline = None
+    if rank == 0 and not distributed and not args.skip_cpu:
+        full = cpu_reference_arm(1, 0)
+        cpu_baseline = {k: full[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "sdf_gvoxels_per_s", "value": value, "unit": "Gvoxels/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": f"{'x'.join(map(str, dims))} occupancy -> SDF<float> "
+                                   "(clustered spheres ~10% filled, 1% unknown), "
+                                   f"{'x-slab sharded, NCCL all-to-all' if distributed else 'one GPU'}",
+                       "voxels": int(voxels), "resolution": RESOLUTION,
+                       "l2_policy": "inputs larger than L2 (>= 512 MiB per pass), no flush",
+                       "sdf_min_max": sdf_min_max},
+            "clocks": sampler.summary(), "e2e": e2e,
+            "gpu_launches": KERNELS_PER_STEP * args.steps, "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        if voxelizer is not None:
+            line["voxelizer"] = voxelizer
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def bench_voxelizer(dev, peak):
+    """BASELINE config 3: 4 cameras x 640x480 rays into 256^3, filter (0.9, 2, 2)."""
+    import numpy as np
+    import torch
+    from voxelized_geometry_tools_b200 import device as vdev, synthetic
+    from voxelized_geometry_tools_b200.pointcloud_voxelization import (
+        PointCloudVoxelizationFilterOptions)
+    scene = synthetic.depth_camera_scene()
+    n = scene["static_occupancy"].shape[0]
+    x_gw = np.eye(4)
+    x_gw[:3, 3] = -scene["origin_transform"][:3, 3]
+    clouds = [(torch.from_numpy(points).to(dev), x_gw @ x_wc, max_range)
+              for points, x_wc, max_range in scene["clouds"]]
+    finite_rays = int(sum(np.isfinite(points).all(axis=1).sum() for points, _, _ in scene["clouds"]))
+    counts = torch.zeros((len(clouds), n, n, n, 2), dtype=torch.int32, device=dev)
+    static = torch.from_numpy(scene["static_occupancy"]).to(dev)
+    occupancy = static.clone()
+    options = PointCloudVoxelizationFilterOptions(0.9, 2, 2)
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    raycast_ms, filter_ms, zero_ms = [], [], []
+    increments = 0
+    for iteration in range(6):
+        occupancy.copy_(static)
+        events[0].record()
+        counts.zero_()
+        events[1].record()
+        for index, (points, x_gc, max_range) in enumerate(clouds):
+            vdev.raycast_cloud(points, x_gc, max_range, counts[index], scene["voxel_size"])
+        events[2].record()
+        vdev.filter_grids(counts, occupancy, options)
+        events[3].record()
+        torch.cuda.synchronize(dev)
+        if iteration >= 2:
+            zero_ms.append(events[0].elapsed_time(events[1]))
+            raycast_ms.append(events[1].elapsed_time(events[2]))
+            filter_ms.append(events[2].elapsed_time(events[3]))
+        increments = int(counts.sum(dtype=torch.int64).item())
+    raycast = statistics.mean(raycast_ms)
+    filt = statistics.mean(filter_ms)
+    voxels = n ** 3
+    filter_bytes = (8 * len(clouds) + 8) * voxels
+    return {"metric": "voxelization_mrays_per_s", "value": finite_rays / (raycast * 1e-3) / 1e6,
+            "unit": "Mrays/s", "rays": finite_rays, "grid": f"{n}^3", "cameras": len(clouds),
+            "raycast_ms": raycast, "filter_ms": filt, "zero_ms": statistics.mean(zero_ms),
+            "atomic_increments": increments,
+            "raycast_gatomics_per_s": increments / (raycast * 1e-3) / 1e9,
+            "filter_roofline": {"bound": "hbm", "achieved": filter_bytes / (filt * 1e-3) / 1e9,
+                                "peak": peak, "unit": "GB/s",
+                                "frac": filter_bytes / (filt * 1e-3) / 1e9 / peak}}
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=10)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    parser.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    parser.add_argument("--skip-voxelizer", action="store_true")
+    args = parser.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,14 @@ VGT_B200_API int vgt_b200_sdf_f32_dev(
     int unknown_is_filled, int add_virtual_border, int device, float* d_sdf_out, float* d_min_max,
     void* stream);
 
+/* Measurement aid for bench.py / profiles: the same three kernels as vgt_b200_sdf_f32_dev with
+ * CUDA events between them on `stream`. Synchronises the stream. out_pass_ms[3] receives the
+ * duration of the z scan, the y envelope pass and the x envelope pass + finalize. */
+VGT_B200_API int vgt_b200_sdf_f32_dev_profile(
+    const float* d_occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, float* d_sdf_out, float* d_min_max,
+    void* stream, float* out_pass_ms);
+
 /* d_scratch: device int32[nx*ny*nz] work buffer (the f64 output cannot double as scratch). */
 VGT_B200_API int vgt_b200_sdf_f64_dev(
     const float* d_occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,

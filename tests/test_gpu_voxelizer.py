@@ -1,0 +1,119 @@
+"""GPU: the CUDA voxelizer through the C-ABI against the oracle: counts bit-exact, occupancy exact."""
+import numpy as np
+import pytest
+
+import voxelized_geometry_tools_b200 as vgt
+from voxelized_geometry_tools_b200 import _capi, synthetic
+
+from . import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def build(scene, clouds):
+    sizes = vgt.VoxelGridSizes.FromVoxelCounts(scene["voxel_size"], scene["static"].shape)
+    static = vgt.OccupancyMap(scene["x_wg"], "world", sizes, data=scene["static"].copy())
+    wrappers = [vgt.VectorPointCloudWrapper(points, x_wc, max_range)
+                for points, x_wc, max_range in clouds]
+    return static, wrappers
+
+
+def oracle_voxelize(oracle, scene, clouds, filter_options):
+    x_gw = scenes.inverse_rigid(scene["x_wg"])
+    prepared = [(points, x_gw @ x_wc, max_range) for points, x_wc, max_range in clouds]
+    return oracle.voxelize(scene["static"], prepared, scene["voxel_size"], *filter_options)
+
+
+def test_reference_scene(shared_library, oracle):
+    # test/pointcloud_voxelization_test.cpp:269-295 for this backend.
+    scene = scenes.reference_voxelization_scene()
+    options = vgt.PointCloudVoxelizationFilterOptions(*scene["filter"])
+    for backend in vgt.GetAvailableBackends():
+        messages = []
+        voxelizer = vgt.MakePointCloudVoxelizer(backend["options"], messages.append)
+        static, wrappers = build(scene, scene["clouds"])
+        runtimes = []
+        empty = voxelizer.VoxelizePointClouds(static, options, [], runtimes.append)
+        scenes.check_empty_voxelization(empty.GetImmutableRawData())
+        voxelized = voxelizer.VoxelizePointClouds(static, options, wrappers, runtimes.append)
+        scenes.check_voxelization(voxelized.GetImmutableRawData())
+        assert len(runtimes) == 2 and runtimes[1].RaycastingTime() >= 0.0
+        assert messages
+        # and exactly the oracle's answer, counts included
+        got, counts = voxelizer.VoxelizePointCloudsWithCounts(static, options, wrappers)
+        want, want_counts = oracle_voxelize(oracle, scene, scene["clouds"], scene["filter"])
+        np.testing.assert_array_equal(counts, want_counts)
+        np.testing.assert_array_equal(got.GetImmutableRawData(), want)
+    # null logging function must be accepted (:297-311)
+    vgt.MakePointCloudVoxelizer({}, None)
+
+
+def test_random_rays_counts_bit_exact(shared_library, oracle):
+    # The 1000 seeded rays of test/voxel_raycasting_test.cpp, each as a one-point cloud whose
+    # origin is the cloud pose; plus the at-most-once property on the GPU result.
+    g, pairs = scenes.random_ray_pairs()
+    dims = tuple(g["voxel_counts"])
+    sizes = vgt.VoxelGridSizes.FromVoxelCounts(g["resolution"], dims)
+    static = vgt.OccupancyMap(np.eye(4), "world", sizes)
+    voxelizer = vgt.B200PointCloudVoxelizer()
+    options = vgt.PointCloudVoxelizationFilterOptions()
+    batch = 50
+    for start in range(0, len(pairs), batch):
+        wrappers, expected = [], []
+        for origin, point in pairs[start:start + batch]:
+            pose = scenes.translation(*origin)
+            local = np.asarray(point) - np.asarray(origin)
+            wrappers.append(vgt.VectorPointCloudWrapper(local[None, :], pose, g["max_range"]))
+            expected.append(oracle.raycast_cloud(local[None, :], pose, g["max_range"], dims,
+                                                 g["resolution"]))
+        _, counts = voxelizer.VoxelizePointCloudsWithCounts(static, options, wrappers)
+        np.testing.assert_array_equal(counts, np.stack(expected))
+        assert counts.max() <= 1
+        assert not np.any((counts[..., 0] > 0) & (counts[..., 1] > 0))
+
+
+@pytest.mark.parametrize("filter_options", [(1.0, 1, 1), (0.9, 2, 2)])
+def test_camera_scene_counts_and_occupancy(shared_library, oracle, filter_options):
+    # BASELINE config 3 at reduced size: clipped rays, NaN pixels, cameras outside the grid.
+    scene = synthetic.depth_camera_scene(96, 0.04, 160, 120, max_range=3.0)
+    packed = {"static": scene["static_occupancy"], "x_wg": scene["origin_transform"],
+              "voxel_size": scene["voxel_size"]}
+    static, wrappers = build(packed, scene["clouds"])
+    options = vgt.PointCloudVoxelizationFilterOptions(*filter_options)
+    got, counts = vgt.B200PointCloudVoxelizer().VoxelizePointCloudsWithCounts(
+        static, options, wrappers)
+    want, want_counts = oracle_voxelize(oracle, packed, scene["clouds"], filter_options)
+    assert want_counts[..., 0].sum() > 100000 and want_counts[..., 1].sum() > 1000
+    np.testing.assert_array_equal(counts, want_counts)
+    np.testing.assert_array_equal(got.GetImmutableRawData(), want)
+    # then the SDF of the voxelized map, end to end
+    sdf = got.ExtractSignedDistanceFieldFloat(vgt.SignedDistanceFieldGenerationParameters())
+    want_sdf, _ = oracle.sdf(want, scene["voxel_size"])
+    np.testing.assert_array_equal(sdf.GetImmutableRawData(), want_sdf)
+
+
+def test_full_config3_counts(shared_library, oracle):
+    # BASELINE config 3 at full size: 4 x 640x480 rays into 256^3.
+    scene = synthetic.depth_camera_scene()
+    packed = {"static": scene["static_occupancy"], "x_wg": scene["origin_transform"],
+              "voxel_size": scene["voxel_size"]}
+    static, wrappers = build(packed, scene["clouds"])
+    options = vgt.PointCloudVoxelizationFilterOptions(0.9, 2, 2)
+    got, counts = vgt.B200PointCloudVoxelizer().VoxelizePointCloudsWithCounts(
+        static, options, wrappers)
+    want, want_counts = oracle_voxelize(oracle, packed, scene["clouds"], (0.9, 2, 2))
+    np.testing.assert_array_equal(counts, want_counts)
+    np.testing.assert_array_equal(got.GetImmutableRawData(), want)
+
+
+def test_argument_errors(shared_library):
+    scene = scenes.reference_voxelization_scene()
+    static, wrappers = build(scene, scene["clouds"])
+    voxelizer = vgt.B200PointCloudVoxelizer()
+    options = vgt.PointCloudVoxelizationFilterOptions()
+    with pytest.raises(ValueError):       # pcv_if.hpp:281-289
+        voxelizer.VoxelizePointClouds(static, options, [wrappers[0], None])
+    with pytest.raises(ValueError):       # pcv_if.hpp:30-41
+        vgt.PointCloudVoxelizationFilterOptions(0.0, 1, 1)
+    with pytest.raises(_capi.BackendUnavailable):   # dev_pcv.hpp:34-46
+        vgt.B200PointCloudVoxelizer({"CUDA_DEVICE": 77})

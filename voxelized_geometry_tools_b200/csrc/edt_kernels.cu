@@ -910,6 +910,71 @@ int vgt_b200_sdf_f32_dev(
                                  static_cast<cudaStream_t>(stream));
 }
 
+int vgt_b200_sdf_f32_dev_profile(
+    const float* d_occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, float* d_sdf_out, float* d_min_max,
+    void* stream, float* out_pass_ms)
+{
+  const int check = CheckSdfArguments(d_occupancy, d_sdf_out, nx, ny, nz, resolution);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  if (out_pass_ms == nullptr)
+  {
+    return FailInvalid("null out_pass_ms");
+  }
+  ScopedDevice scoped(device);
+  VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaEvent_t marks[4];
+  for (auto& mark : marks)
+  {
+    VGT_CUDA_TRY(cudaEventCreate(&mark), "cudaEventCreate");
+  }
+  uint32_t* d_packed = reinterpret_cast<uint32_t*>(d_sdf_out);
+  KeyScratch<uint32_t> keys;
+  if (d_min_max != nullptr)
+  {
+    VGT_CUDA_TRY(keys.Allocate(s), "min/max scratch");
+  }
+  cudaEventRecord(marks[0], s);
+  int status = LaunchScan<float>(d_occupancy, d_packed, nx * ny, static_cast<int32_t>(nz),
+                                 unknown_is_filled, s);
+  cudaEventRecord(marks[1], s);
+  if (status == VGT_B200_OK && ny > 1)
+  {
+    const LineFamily along_y{nx, ny * nz, nz, nz, static_cast<int32_t>(ny)};
+    status = LaunchEnvelope<kEmitPacked>(d_packed, d_packed, along_y, Square(nz - 1),
+                                         FinalizeParams{}, nullptr, s);
+  }
+  cudaEventRecord(marks[2], s);
+  if (status == VGT_B200_OK)
+  {
+    status = RunFinalPass<kEmitFloat>(d_packed, nx, ny, nz, 0, ny, resolution,
+                                      add_virtual_border, d_sdf_out, d_min_max, keys.ptr, s);
+  }
+  cudaEventRecord(marks[3], s);
+  const cudaError_t sync = cudaStreamSynchronize(s);
+  if (status == VGT_B200_OK && sync == cudaSuccess)
+  {
+    for (int i = 0; i < 3; i++)
+    {
+      cudaEventElapsedTime(out_pass_ms + i, marks[i], marks[i + 1]);
+    }
+  }
+  for (auto& mark : marks)
+  {
+    cudaEventDestroy(mark);
+  }
+  if (status != VGT_B200_OK)
+  {
+    return status;
+  }
+  VGT_CUDA_TRY(sync, "profiled SDF generation");
+  return VGT_B200_OK;
+}
+
 int vgt_b200_sdf_from_mask_f32_dev(
     const uint8_t* d_filled_mask, int64_t nx, int64_t ny, int64_t nz, double resolution,
     int add_virtual_border, int device, float* d_sdf_out, float* d_min_max, void* stream)

@@ -50,6 +50,23 @@ def signed_distance_field(occupancy: torch.Tensor, resolution: float,
     return out, (min_max if compute_min_max else None)
 
 
+def signed_distance_field_profile(occupancy: torch.Tensor, resolution: float,
+                                  out: torch.Tensor, min_max: torch.Tensor | None = None):
+    """Same kernels as signed_distance_field with CUDA events between them; synchronises.
+    Returns [ms z-scan, ms y-pass, ms x-pass + finalize]."""
+    _require_cuda(occupancy, torch.float32, "occupancy")
+    _require_cuda(out, torch.float32, "out")
+    device = occupancy.device
+    nx, ny, nz = occupancy.shape
+    pass_ms = (ctypes.c_float * 3)()
+    code = _capi.library().vgt_b200_sdf_f32_dev_profile(
+        occupancy.data_ptr(), nx, ny, nz, float(resolution), 1, 0, device.index or 0,
+        out.data_ptr(), None if min_max is None else min_max.data_ptr(), _stream_handle(device),
+        pass_ms)
+    _capi.check(code)
+    return [float(v) for v in pass_ms]
+
+
 def signed_distance_field_f64(occupancy: torch.Tensor, resolution: float,
                               unknown_is_filled: bool = True, add_virtual_border: bool = False):
     _require_cuda(occupancy, torch.float32, "occupancy")
