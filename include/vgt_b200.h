@@ -95,7 +95,8 @@ VGT_B200_API int vgt_b200_edt_sq_i32(
 
 /* Device-resident variants (no host copies, asynchronous on `stream`).
  *   d_occupancy   device float[nx*ny*nz]
- *   d_sdf_out     device float[nx*ny*nz]; also used as the scratch for the integer passes
+ *   d_sdf_out     device float[nx*ny*nz]; also used as the first intermediate of the integer
+ *                 passes (a second, 4 bytes per voxel, comes from the device's stream-ordered pool)
  *   d_min_max     device float[2] (min, max) or NULL; written by the last kernel on `stream`
  */
 VGT_B200_API int vgt_b200_sdf_f32_dev(
@@ -111,11 +112,10 @@ VGT_B200_API int vgt_b200_sdf_f32_dev_profile(
     int unknown_is_filled, int add_virtual_border, int device, float* d_sdf_out, float* d_min_max,
     void* stream, float* out_pass_ms);
 
-/* d_scratch: device int32[nx*ny*nz] work buffer (the f64 output cannot double as scratch). */
 VGT_B200_API int vgt_b200_sdf_f64_dev(
     const float* d_occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
-    int unknown_is_filled, int add_virtual_border, int device, int32_t* d_scratch,
-    double* d_sdf_out, double* d_min_max, void* stream);
+    int unknown_is_filled, int add_virtual_border, int device, double* d_sdf_out,
+    double* d_min_max, void* stream);
 
 VGT_B200_API int vgt_b200_sdf_from_mask_f32_dev(
     const uint8_t* d_filled_mask, int64_t nx, int64_t ny, int64_t nz, double resolution,
@@ -132,14 +132,15 @@ VGT_B200_API int vgt_b200_sdf_from_mask_f32_dev(
  * vgt_b200_edt_final_pass_f32_dev: the pass along x on a y-slab laid out [nx, ny_local, nz]
  *   (after the all-to-all), fused with the sqrt*resolution combine (sdfgen.hpp:85-108) and the
  *   min/max of Lock(). y_offset / ny_total / (x,z are whole) locate the slab inside the full grid
- *   for the virtual border. d_in and d_sdf_out may alias (in-place).
+ *   for the virtual border. d_in is DESTROYED (the envelope stacks are built in place in it) and
+ *   must not alias d_sdf_out.
  */
 VGT_B200_API int vgt_b200_edt_local_passes_dev(
     const float* d_occupancy, int64_t nx_local, int64_t ny, int64_t nz, int unknown_is_filled,
     int device, int32_t* d_out, void* stream);
 
 VGT_B200_API int vgt_b200_edt_final_pass_f32_dev(
-    const int32_t* d_in, int64_t nx, int64_t ny_local, int64_t nz, int64_t y_offset,
+    int32_t* d_in, int64_t nx, int64_t ny_local, int64_t nz, int64_t y_offset,
     int64_t ny_total, double resolution, int add_virtual_border, int device, float* d_sdf_out,
     float* d_min_max, void* stream);
 

@@ -75,7 +75,7 @@ def test_random_rays_counts_bit_exact(shared_library, oracle):
 @pytest.mark.parametrize("filter_options", [(1.0, 1, 1), (0.9, 2, 2)])
 def test_camera_scene_counts_and_occupancy(shared_library, oracle, filter_options):
     # BASELINE config 3 at reduced size: clipped rays, NaN pixels, cameras outside the grid.
-    scene = synthetic.depth_camera_scene(96, 0.04, 160, 120, max_range=3.0)
+    scene = synthetic.depth_camera_scene(96, 0.04, 160, 120, max_range=5.0)
     packed = {"static": scene["static_occupancy"], "x_wg": scene["origin_transform"],
               "voxel_size": scene["voxel_size"]}
     static, wrappers = build(packed, scene["clouds"])

@@ -72,13 +72,12 @@ def signed_distance_field_f64(occupancy: torch.Tensor, resolution: float,
     _require_cuda(occupancy, torch.float32, "occupancy")
     device = occupancy.device
     out = torch.empty(occupancy.shape, dtype=torch.float64, device=device)
-    scratch = torch.empty(occupancy.shape, dtype=torch.int32, device=device)
     min_max = torch.empty(2, dtype=torch.float64, device=device)
     nx, ny, nz = occupancy.shape
     code = _capi.library().vgt_b200_sdf_f64_dev(
         occupancy.data_ptr(), nx, ny, nz, float(resolution), int(unknown_is_filled),
-        int(add_virtual_border), device.index or 0, scratch.data_ptr(), out.data_ptr(),
-        min_max.data_ptr(), _stream_handle(device))
+        int(add_virtual_border), device.index or 0, out.data_ptr(), min_max.data_ptr(),
+        _stream_handle(device))
     _capi.check(code)
     return out, min_max
 
@@ -115,12 +114,12 @@ def edt_local_passes(occupancy_slab: torch.Tensor, unknown_is_filled: bool = Tru
 
 def edt_final_pass(packed: torch.Tensor, y_offset: int, ny_total: int, resolution: float,
                    add_virtual_border: bool = False, compute_min_max: bool = True):
-    """x pass + finalize on a y-slab [nx, ny_local, nz] of sign-fused words (in place: the
-    returned float32 tensor shares storage with ``packed``)."""
+    """x pass + finalize on a y-slab [nx, ny_local, nz] of sign-fused words. ``packed`` is
+    destroyed (the envelope stacks are built in place in it); the SDF is a new tensor."""
     _require_cuda(packed, torch.int32, "packed")
     device = packed.device
     nx, ny_local, nz = packed.shape
-    out = packed.view(torch.float32)
+    out = torch.empty(packed.shape, dtype=torch.float32, device=device)
     min_max = torch.empty(2, dtype=torch.float32, device=device) if compute_min_max else None
     code = _capi.library().vgt_b200_edt_final_pass_f32_dev(
         packed.data_ptr(), nx, ny_local, nz, int(y_offset), int(ny_total), float(resolution),
