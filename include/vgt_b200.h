@@ -93,7 +93,9 @@ VGT_B200_API int vgt_b200_edt_sq_i32(
     const float* occupancy, int64_t nx, int64_t ny, int64_t nz, int unknown_is_filled, int device,
     int32_t* dist_to_filled_sq, int32_t* dist_to_free_sq);
 
-/* Device-resident variants (no host copies, asynchronous on `stream`).
+/* Device-resident variants of the entry points above (no host copies, asynchronous on `stream`);
+ * they replace the same reference code (include/.../occupancy_map.hpp:174-210,
+ * include/.../signed_distance_field_generation.hpp:39-113, :115-285).
  *   d_occupancy   device float[nx*ny*nz]
  *   d_sdf_out     device float[nx*ny*nz]; also used as the first intermediate of the integer
  *                 passes (a second, 4 bytes per voxel, comes from the device's stream-ordered pool)

@@ -1,0 +1,156 @@
+"""CPU: a pure-Python model of the line algorithm the CUDA envelope kernel runs
+(voxelized_geometry_tools_b200/csrc/edt_envelope_inplace.cuh), checked against brute force.
+
+The kernel cannot run without a GPU, but its algorithm can: this model mirrors the kernel's two
+phases statement by statement (same stack discipline, same integer pop test, same class-bit run
+tracking), so a logic error shows up here on CPU before any GPU time is spent.
+
+Line semantics: each voxel has a class bit and a partial squared distance to the opposite class
+(NONE = none yet). The transform of the line gives, for voxel q,
+    min( min over same-run voxels v with a value of (q-v)^2 + value(v),
+         (q-(a-1))^2 if the run starts at a > 0, ((b+1)-q)^2 if it ends at b < n-1 ).
+"""
+import random
+
+NONE = 0x7FFFFFFF
+NO_HEIGHT = 0x3FFFFFFF
+
+
+def hidden(below, top, incoming):
+    # MiddleIsHidden: crossing(below, top) >= crossing(top, incoming), cross-multiplied.
+    return (top[1] - below[1]) * (incoming[0] - top[0]) >= (incoming[1] - top[1]) * (top[0] - below[0])
+
+
+def kernel_line(classes, values):
+    n = len(classes)
+    num_words = (n + 31) // 32
+    rows = [None] * n                 # the line's own storage, reused as the stack
+    class_words = [0] * num_words
+    # ---- phase 1: per run, stack = [implicit zero site left of the run] + stored own sites;
+    #      the zero site right of the run pops what it hides when the run ends.
+    slot = depth = 0
+    has_left = False
+    left_zero = top = below = (0, 0)
+    previous = 0
+
+    def pop_hidden(incoming):
+        nonlocal slot, depth, top, below
+        while (depth >= 2 or (depth == 1 and has_left)) and hidden(below, top, incoming):
+            depth -= 1
+            slot -= 1
+            top = below
+            below = rows[slot - 2] if depth >= 2 else left_zero
+
+    for q in range(n):
+        filled, value = classes[q], values[q]
+        class_words[q >> 5] |= filled << (q & 31)
+        if q > 0 and filled != previous:
+            pop_hidden((q, q * q))
+            depth = 0
+            has_left = True
+            left_zero = top = (q - 1, (q - 1) ** 2)
+        previous = filled
+        if value != NONE:
+            incoming = (q, value + q * q)
+            pop_hidden(incoming)
+            assert slot <= q          # the in-place invariant: a slot never passes the read row
+            rows[slot] = incoming
+            below, top = top, incoming
+            depth += 1
+            slot += 1
+    stored_total = slot
+
+    # ---- phase 2: lockstep sweep; candidates of a run = left zero, stored sites, right zero
+    def load(index):
+        return rows[index] if index < stored_total else (NONE, NO_HEIGHT)
+
+    cursor = 0
+    pending = load(0)
+    winner = right_zero = (0, NO_HEIGHT)
+    run_end = 0
+    previous = 0
+    out = [0] * n
+    for q in range(n):
+        word = class_words[q >> 5]
+        filled = (word >> (q & 31)) & 1
+        if q == 0 or filled != previous:
+            w = q >> 5
+            different = ((~word if filled else word) & 0xFFFFFFFF) & ((0xFFFFFFFF << (q & 31)) & 0xFFFFFFFF)
+            while different == 0 and w + 1 < num_words:
+                w += 1
+                different = (~class_words[w] if filled else class_words[w]) & 0xFFFFFFFF
+            run_end = min(n, 32 * w + (different & -different).bit_length() - 1) if different else n
+            while pending[0] < q:
+                cursor += 1
+                pending = load(cursor)
+            right_zero = (run_end, run_end ** 2) if run_end < n else (0, NO_HEIGHT)
+            winner = (q - 1, (q - 1) ** 2) if q > 0 else (0, NO_HEIGHT)
+        previous = filled
+        while True:
+            from_stack = pending[0] < run_end
+            candidate = pending if from_stack else right_zero
+            if not (candidate[1] - 2 * candidate[0] * q < winner[1] - 2 * winner[0] * q):
+                break
+            winner = candidate
+            if from_stack:
+                cursor += 1
+                pending = load(cursor)
+            else:
+                right_zero = (0, NO_HEIGHT)
+        out[q] = NONE if winner[1] == NO_HEIGHT else winner[1] - 2 * winner[0] * q + q * q
+    return out
+
+
+def brute_line(classes, values):
+    n = len(classes)
+    out = []
+    for q in range(n):
+        best = NONE
+        # the run containing q
+        a = q
+        while a > 0 and classes[a - 1] == classes[q]:
+            a -= 1
+        b = q
+        while b < n - 1 and classes[b + 1] == classes[q]:
+            b += 1
+        for v in range(a, b + 1):
+            if values[v] != NONE:
+                best = min(best, (q - v) ** 2 + values[v])
+        if a > 0:
+            best = min(best, (q - a + 1) ** 2)
+        if b < n - 1:
+            best = min(best, (b + 1 - q) ** 2)
+        out.append(best)
+    return out
+
+
+def random_line(rng, n):
+    flip = rng.choice([0.02, 0.1, 0.5])
+    classes, c = [], rng.randint(0, 1)
+    for _ in range(n):
+        if rng.random() < flip:
+            c ^= 1
+        classes.append(c)
+    scale = rng.choice([3, 30, 400, 5000, 200000])
+    none_rate = rng.choice([0.0, 0.2, 0.9])
+    values = [NONE if rng.random() < none_rate else rng.randint(1, scale) for _ in range(n)]
+    return classes, values
+
+
+def test_kernel_line_model_matches_brute_force():
+    rng = random.Random(1)
+    for _ in range(6000):
+        n = rng.choice([1, 2, 3, 31, 32, 33, 40, 64, 65, 97])
+        classes, values = random_line(rng, n)
+        assert kernel_line(classes, values) == brute_line(classes, values), (classes, values)
+
+
+def test_smooth_distance_like_lines():
+    # values shaped like real partial distances (smooth bowls), the deep-stack case
+    rng = random.Random(2)
+    for _ in range(300):
+        n = rng.choice([64, 100, 130])
+        centre, offset = rng.uniform(0, n), rng.randint(1, 50)
+        classes = [1 if abs(i - n / 3) < 4 else 0 for i in range(n)]
+        values = [int((i - centre) ** 2) + offset for i in range(n)]
+        assert kernel_line(classes, values) == brute_line(classes, values)
