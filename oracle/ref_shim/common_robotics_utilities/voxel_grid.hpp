@@ -1,0 +1,164 @@
+// TEST INFRASTRUCTURE ONLY -- stand-in for common_robotics_utilities/voxel_grid.hpp with just the
+// surface signed_distance_field_generation.{hpp,cpp} use. Storage convention as in the real
+// library (mirrored in-tree at cuda_voxelization_helpers.cu:281-282): x slowest, z contiguous.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <vector>
+
+#include <Eigen/Geometry>
+
+namespace common_robotics_utilities
+{
+namespace voxel_grid
+{
+struct Vector3i64
+{
+  int64_t x = 0, y = 0, z = 0;
+  Vector3i64() = default;
+  Vector3i64(int64_t xi, int64_t yi, int64_t zi) : x(xi), y(yi), z(zi) {}
+};
+
+class GridIndex
+{
+public:
+  GridIndex() = default;
+  GridIndex(int64_t x, int64_t y, int64_t z) : x_(x), y_(y), z_(z) {}
+  const int64_t& X() const { return x_; }
+  const int64_t& Y() const { return y_; }
+  const int64_t& Z() const { return z_; }
+  int64_t& X() { return x_; }
+  int64_t& Y() { return y_; }
+  int64_t& Z() { return z_; }
+  bool operator==(const GridIndex& o) const { return x_ == o.x_ && y_ == o.y_ && z_ == o.z_; }
+  bool operator!=(const GridIndex& o) const { return !(*this == o); }
+
+private:
+  int64_t x_ = -1, y_ = -1, z_ = -1;
+};
+
+class VoxelGridSizes
+{
+public:
+  VoxelGridSizes() = default;
+  static VoxelGridSizes FromVoxelCounts(double voxel_size, const Vector3i64& counts)
+  {
+    if (!(voxel_size > 0.0) || counts.x < 1 || counts.y < 1 || counts.z < 1)
+    {
+      throw std::invalid_argument("invalid voxel grid sizes");
+    }
+    VoxelGridSizes sizes;
+    sizes.voxel_size_ = voxel_size;
+    sizes.counts_ = counts;
+    return sizes;
+  }
+  static VoxelGridSizes FromGridSizes(double voxel_size, const Eigen::Vector3d& grid_sizes)
+  {
+    return FromVoxelCounts(
+        voxel_size,
+        Vector3i64(static_cast<int64_t>(std::ceil(grid_sizes(0) / voxel_size)),
+                   static_cast<int64_t>(std::ceil(grid_sizes(1) / voxel_size)),
+                   static_cast<int64_t>(std::ceil(grid_sizes(2) / voxel_size))));
+  }
+  int64_t NumXVoxels() const { return counts_.x; }
+  int64_t NumYVoxels() const { return counts_.y; }
+  int64_t NumZVoxels() const { return counts_.z; }
+  int64_t TotalVoxels() const { return counts_.x * counts_.y * counts_.z; }
+  double VoxelXSize() const { return voxel_size_; }
+  bool UniformVoxelSize() const { return true; }
+  bool operator==(const VoxelGridSizes& o) const
+  {
+    return voxel_size_ == o.voxel_size_ && counts_.x == o.counts_.x && counts_.y == o.counts_.y
+        && counts_.z == o.counts_.z;
+  }
+  bool operator!=(const VoxelGridSizes& o) const { return !(*this == o); }
+
+private:
+  double voxel_size_ = 0.0;
+  Vector3i64 counts_;
+};
+
+template <typename T>
+class GridQuery
+{
+public:
+  GridQuery() = default;
+  explicit GridQuery(T* item) : item_(item) {}
+  T& Value() const
+  {
+    if (item_ == nullptr) { throw std::runtime_error("grid query has no value"); }
+    return *item_;
+  }
+  explicit operator bool() const { return item_ != nullptr; }
+
+private:
+  T* item_ = nullptr;
+};
+
+template <typename T, typename BackingStore = std::vector<T>>
+class VoxelGridBase
+{
+public:
+  VoxelGridBase() = default;
+  VoxelGridBase(const Eigen::Isometry3d& origin_transform, const VoxelGridSizes& sizes,
+                const T& default_value)
+      : origin_transform_(origin_transform), sizes_(sizes),
+        data_(static_cast<size_t>(sizes.TotalVoxels()), default_value), initialized_(true) {}
+  virtual ~VoxelGridBase() {}
+
+  bool IsInitialized() const { return initialized_; }
+  bool HasUniformVoxelSize() const { return sizes_.UniformVoxelSize(); }
+  const Eigen::Isometry3d& OriginTransform() const { return origin_transform_; }
+  const VoxelGridSizes& ControlSizes() const { return sizes_; }
+  int64_t NumXVoxels() const { return sizes_.NumXVoxels(); }
+  int64_t NumYVoxels() const { return sizes_.NumYVoxels(); }
+  int64_t NumZVoxels() const { return sizes_.NumZVoxels(); }
+  int64_t NumTotalVoxels() const { return sizes_.TotalVoxels(); }
+  double VoxelXSize() const { return sizes_.VoxelXSize(); }
+
+  bool CheckGridIndexInBounds(int64_t x, int64_t y, int64_t z) const
+  {
+    return x >= 0 && x < NumXVoxels() && y >= 0 && y < NumYVoxels() && z >= 0 && z < NumZVoxels();
+  }
+  int64_t GetDataIndex(int64_t x, int64_t y, int64_t z) const
+  {
+    return (x * NumYVoxels() + y) * NumZVoxels() + z;
+  }
+  GridQuery<const T> GetIndexImmutable(int64_t x, int64_t y, int64_t z) const
+  {
+    if (!CheckGridIndexInBounds(x, y, z)) { return GridQuery<const T>(); }
+    return GridQuery<const T>(&data_[static_cast<size_t>(GetDataIndex(x, y, z))]);
+  }
+  GridQuery<const T> GetIndexImmutable(const GridIndex& index) const
+  {
+    return GetIndexImmutable(index.X(), index.Y(), index.Z());
+  }
+  bool SetIndex(int64_t x, int64_t y, int64_t z, const T& value)
+  {
+    if (!CheckGridIndexInBounds(x, y, z) || !OnMutableAccess(x, y, z)) { return false; }
+    data_[static_cast<size_t>(GetDataIndex(x, y, z))] = value;
+    return true;
+  }
+  bool SetIndex(const GridIndex& index, const T& value)
+  {
+    return SetIndex(index.X(), index.Y(), index.Z(), value);
+  }
+  const BackingStore& GetImmutableRawData() const { return data_; }
+  BackingStore& GetMutableRawData() { return data_; }
+
+protected:
+  virtual bool OnMutableAccess(int64_t, int64_t, int64_t) { return true; }
+
+private:
+  Eigen::Isometry3d origin_transform_;
+  VoxelGridSizes sizes_;
+  BackingStore data_;
+  bool initialized_ = false;
+};
+
+template <typename T>
+using VoxelGrid = VoxelGridBase<T, std::vector<T>>;
+}  // namespace voxel_grid
+}  // namespace common_robotics_utilities
