@@ -86,6 +86,10 @@ VGT_B200_API int vgt_b200_sdf_from_mask_f32(
     const uint8_t* filled_mask, int64_t nx, int64_t ny, int64_t nz, double resolution,
     int add_virtual_border, int device, float* sdf_out, float* out_min, float* out_max);
 
+VGT_B200_API int vgt_b200_sdf_from_mask_f64(
+    const uint8_t* filled_mask, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int add_virtual_border, int device, double* sdf_out, double* out_min, double* out_max);
+
 /* Parity hook for internal::ComputeDistanceFieldTransformInPlace on the two 0/inf fields
  * (include/.../signed_distance_field_generation.hpp:34-37, 47-80): both squared fields in voxel
  * units as int32, VGT_B200_SQ_INF where the reference holds +inf. Host pointers. */

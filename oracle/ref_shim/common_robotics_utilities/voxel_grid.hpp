@@ -111,6 +111,7 @@ public:
   bool IsInitialized() const { return initialized_; }
   bool HasUniformVoxelSize() const { return sizes_.UniformVoxelSize(); }
   const Eigen::Isometry3d& OriginTransform() const { return origin_transform_; }
+  Eigen::Isometry3d InverseOriginTransform() const { return origin_transform_.inverse(); }
   const VoxelGridSizes& ControlSizes() const { return sizes_; }
   int64_t NumXVoxels() const { return sizes_.NumXVoxels(); }
   int64_t NumYVoxels() const { return sizes_.NumYVoxels(); }

@@ -566,6 +566,14 @@ int vgt_b200_sdf_from_mask_f32(
                                           add_virtual_border, device, sdf_out, out_min, out_max);
 }
 
+int vgt_b200_sdf_from_mask_f64(
+    const uint8_t* filled_mask, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int add_virtual_border, int device, double* sdf_out, double* out_min, double* out_max)
+{
+  return SdfFromHost<uint8_t, kEmitDouble>(filled_mask, nx, ny, nz, resolution, 0,
+                                           add_virtual_border, device, sdf_out, out_min, out_max);
+}
+
 int vgt_b200_edt_sq_i32(
     const float* occupancy, int64_t nx, int64_t ny, int64_t nz, int unknown_is_filled, int device,
     int32_t* dist_to_filled_sq, int32_t* dist_to_free_sq)
