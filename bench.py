@@ -183,7 +183,8 @@ def run_ours(args):
     dims = workload_dims(n_gpus)
     voxels = float(np.prod(dims))
 
-    plan = sharded.ShardedSignedDistanceField(dims, rank=rank, world_size=n_gpus) \
+    plan = sharded.ShardedSignedDistanceField(dims, rank=rank, world_size=n_gpus,
+                                              chunks=args.chunks, exchange=args.exchange) \
         if distributed else None
     x_range = plan.x_range if distributed else (0, dims[0])
     occupancy = synthetic.clustered_spheres_occupancy_torch(dims, dev, x_range=x_range)
@@ -222,6 +223,17 @@ def run_ours(args):
     value = voxels / (ms_per_step * 1e-3) / 1e9
     sdf_min_max = [float(v) for v in result[1].tolist()]
 
+    stage_ms = None
+    if distributed:
+        plan.profile = True
+        collected = []
+        for _ in range(3):
+            plan.extract(occupancy, RESOLUTION)
+            torch.cuda.synchronize(dev)
+            collected.append(plan.stage_ms())
+        plan.profile = False
+        stage_ms = {k: statistics.mean(c[k] for c in collected) for k in collected[0]}
+
     # ---- per-kernel timing for the roofline (rank-local grid, events between the kernels) ----
     pass_ms = None
     if not distributed:
@@ -247,9 +259,15 @@ def run_ours(args):
                                   "bytes_per_voxel": SDF_BYTES_PER_VOXEL}}
     else:
         whole = SDF_BYTES_PER_VOXEL * voxels / (ms_per_step * 1e-3) / 1e9
+        nvlink_bytes = 4.0 * (voxels / n_gpus) * (n_gpus - 1) / n_gpus   # per GPU, per direction
         roofline = {"bound": "hbm", "kernel": "whole SDF (3 passes + all-to-all)",
                     "achieved": whole, "peak": peak * n_gpus, "unit": "GB/s",
-                    "frac": whole / (peak * n_gpus), "traffic": None, "peak_kind": peak_kind}
+                    "frac": whole / (peak * n_gpus), "traffic": None, "peak_kind": peak_kind,
+                    "rank0_stage_ms": stage_ms, "exchange_chunks": args.chunks,
+                    "exchange": plan.exchange_used,
+                    "nvlink_bytes_per_gpu_per_direction": nvlink_bytes,
+                    "nvlink_floor_ms_at_770GBs": nvlink_bytes / 770e9 * 1e3,
+                    "hbm_floor_ms": SDF_BYTES_PER_VOXEL * (voxels / n_gpus) / (peak * 1e9) * 1e3}
 
     # ---- end to end through the host C-ABI (pinned host buffers, H2D + D2H timed) ----
     lib = _capi.library()
@@ -324,7 +342,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"{'x'.join(map(str, dims))} occupancy -> SDF<float> "
                                    "(clustered spheres ~10% filled, 1% unknown), "
-                                   f"{'x-slab sharded, NCCL all-to-all' if distributed else 'one GPU'}",
+                                   + ("x-slab sharded, exchange fused into the y pass as NVLink "
+                                      "peer stores" if distributed and plan.exchange_used ==
+                                      "peer_store" else "x-slab sharded, NCCL all-to-all"
+                                      if distributed else "one GPU"),
                        "voxels": int(voxels), "resolution": RESOLUTION,
                        "l2_policy": "inputs larger than L2 (>= 512 MiB per pass), no flush",
                        "sdf_min_max": sdf_min_max},
@@ -398,6 +419,9 @@ def main():
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
     parser.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     parser.add_argument("--skip-voxelizer", action="store_true")
+    parser.add_argument("--exchange", default="auto", choices=["auto", "peer_store", "nccl"])
+    parser.add_argument("--chunks", type=int, default=2,
+                        help="x-chunks per slab for overlapping the all-to-all (N > 1)")
     args = parser.parse_args()
     if args.impl == "reference":
         run_reference(args)

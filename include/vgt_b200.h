@@ -135,6 +135,11 @@ VGT_B200_API int vgt_b200_sdf_from_mask_f32_dev(
  *   [nx_local, ny, nz]; both are independent per x, so a slab needs no neighbours.
  *   Replaces the Y and Z loops of ComputeDistanceFieldTransformInPlace (sdfgen.cpp:315-390) for
  *   both fields at once plus the marking loop (sdfgen.hpp:57-74).
+ *   send_parts <= 1: d_out has the slab's own layout [nx_local][ny][nz].
+ *   send_parts = G > 1: d_out is written in SEND LAYOUT -- y is cut into G near-equal parts (the
+ *   first ny % G parts one row longer) and part h is stored as the block [nx_local][rows_h][nz],
+ *   blocks back to back: block h is exactly what the all-to-all sends to rank h, so no packing
+ *   pass is needed. Returns VGT_B200_ERR_UNSUPPORTED when ny > 1024 (caller packs instead).
  * vgt_b200_edt_final_pass_f32_dev: the pass along x on a y-slab laid out [nx, ny_local, nz]
  *   (after the all-to-all), fused with the sqrt*resolution combine (sdfgen.hpp:85-108) and the
  *   min/max of Lock(). y_offset / ny_total / (x,z are whole) locate the slab inside the full grid
@@ -143,7 +148,21 @@ VGT_B200_API int vgt_b200_sdf_from_mask_f32_dev(
  */
 VGT_B200_API int vgt_b200_edt_local_passes_dev(
     const float* d_occupancy, int64_t nx_local, int64_t ny, int64_t nz, int unknown_is_filled,
-    int device, int32_t* d_out, void* stream);
+    int send_parts, int device, int32_t* d_out, void* stream);
+
+/* Fused compute + exchange: the same two passes, but the y pass stores part h of every line
+ * straight into rank h's receive buffer through peer-mapped device pointers (NVLink stores), so
+ * the kernel IS the all-to-all (the reference has no counterpart: SURVEY.md section 2.2).
+ *   peer_receive_buffers  host array of num_ranks device addresses, entry h = base of rank h's
+ *                         receive buffer laid out [nx_total][rows_h][nz] (rows_h = rank h's share
+ *                         of ny), mapped into this process (CUDA IPC / symmetric memory);
+ *                         entry [own rank] is the local buffer.
+ *   x_offset              first x row of this rank's slab inside the full grid.
+ * The caller synchronises the ranks (a barrier on `stream`) before any rank reads its buffer. */
+VGT_B200_API int vgt_b200_edt_local_passes_scatter_dev(
+    const float* d_occupancy, int64_t nx_local, int64_t ny, int64_t nz, int unknown_is_filled,
+    int num_ranks, int64_t x_offset, const uint64_t* peer_receive_buffers, int device,
+    void* stream);
 
 VGT_B200_API int vgt_b200_edt_final_pass_f32_dev(
     int32_t* d_in, int64_t nx, int64_t ny_local, int64_t nz, int64_t y_offset,

@@ -19,10 +19,15 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
-    for dims, border in (((96, 80, 72), False), ((61, 45, 130), True), ((256, 256, 256), False)):
-        plan = ShardedSignedDistanceField(dims)
+    for dims, border, chunks, exchange in (
+            ((96, 80, 72), False, 1, "nccl"), ((61, 45, 130), True, 3, "nccl"),
+            ((256, 256, 256), False, 4, "nccl"), ((96, 80, 72), False, 1, "peer_store"),
+            ((61, 45, 130), True, 1, "peer_store"), ((256, 256, 256), False, 1, "peer_store")):
+        plan = ShardedSignedDistanceField(dims, chunks=chunks, exchange=exchange)
         slab = synthetic.clustered_spheres_occupancy_torch(dims, dev, x_range=plan.x_range)
-        sdf_slab, min_max = plan.extract(slab, 0.02, add_virtual_border=border)
+        for _ in range(3):      # several steps: exercises the double-buffered receive side
+            sdf_slab, min_max = plan.extract(slab, 0.02, add_virtual_border=border)
+        assert plan.exchange_used == exchange, (plan.exchange_used, exchange)
         full = plan.gather_to_host(sdf_slab)
         if rank == 0:
             whole = synthetic.clustered_spheres_occupancy_torch(dims, dev)
@@ -34,7 +39,7 @@ def main():
                 from oracle import oracle
                 want, _ = oracle.sdf(whole.cpu().numpy(), 0.02, add_virtual_border=border)
                 assert np.array_equal(full.numpy(), want), f"{dims}: sharded != oracle"
-            print(f"dims {dims} border {border}: world {world} ok", flush=True)
+            print(f"dims {dims} border {border} {exchange}: world {world} ok", flush=True)
         dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK_OK", flush=True)

@@ -23,12 +23,23 @@ def test_staged_passes_emulating_four_ranks_on_one_gpu(shared_library, oracle):
     rng = np.random.default_rng(41)
     occupancy = random_occupancy(rng, shape, 0.1, blobs=True)
     dev = torch.device("cuda", 0)
-    packed_slabs = []
+    packed_slabs, from_send_layout = [], []
     for rank in range(world):
         x0, x1 = split_range(shape[0], world, rank)
         slab = torch.from_numpy(occupancy[x0:x1].copy()).to(dev)
         packed_slabs.append(vdev.edt_local_passes(slab))
+        # the same passes writing send layout: block h = [nxl, rows_h, nz], back to back
+        send = vdev.edt_local_passes(slab, send_parts=world).view(-1)
+        blocks, offset = [], 0
+        for peer in range(world):
+            y0, y1 = split_range(shape[1], world, peer)
+            count = (x1 - x0) * (y1 - y0) * shape[2]
+            blocks.append(send[offset:offset + count].view(x1 - x0, y1 - y0, shape[2]))
+            offset += count
+        assert offset == send.numel()
+        from_send_layout.append(torch.cat(blocks, dim=1))
     packed = torch.cat(packed_slabs, dim=0)           # what the all-to-all reassembles
+    assert torch.equal(packed, torch.cat(from_send_layout, dim=0))
     for border in (False, True):
         pieces, extrema = [], []
         for rank in range(world):

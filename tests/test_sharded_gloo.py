@@ -63,10 +63,18 @@ def _cpu_stages(oracle):
         sdf = np.where(filled, -magnitude, magnitude).astype(np.float32)
         return torch.from_numpy(sdf), torch.tensor([sdf.min(), sdf.max()])
 
-    return Stages(local_passes, final_pass)
+    def local_passes_send(occupancy_slab, unknown_is_filled, parts):
+        # send layout: part h of every y-line as the block [nxl, rows_h, nz], blocks back to back
+        from voxelized_geometry_tools_b200.sharded import split_range
+        packed = local_passes(occupancy_slab, unknown_is_filled)
+        ny = packed.shape[1]
+        return torch.cat([packed[:, split_range(ny, parts, h)[0]:split_range(ny, parts, h)[1], :]
+                          .reshape(-1) for h in range(parts)])
+
+    return Stages(local_passes, final_pass, local_passes_send)
 
 
-def _worker(rank, world, port, shape, result_path):
+def _worker(rank, world, port, shape, result_path, chunks=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -76,7 +84,7 @@ def _worker(rank, world, port, shape, result_path):
         rng = np.random.default_rng(77)
         occupancy = (rng.random(shape) < 0.15).astype(np.float32)
         occupancy[rng.random(shape) < 0.05] = 0.5
-        plan = ShardedSignedDistanceField(shape, stages=_cpu_stages(oracle))
+        plan = ShardedSignedDistanceField(shape, stages=_cpu_stages(oracle), chunks=chunks)
         x0, x1 = plan.x_range
         sdf_slab, min_max = plan.extract(torch.from_numpy(occupancy[x0:x1].copy()), 0.25)
         assert tuple(sdf_slab.shape) == plan.y_slab_shape()
@@ -96,10 +104,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,shape", [(2, (10, 9, 7)), (3, (7, 8, 5)), (2, (5, 2, 11))])
-def test_sharded_matches_single_process(tmp_path, oracle, world, shape):
+@pytest.mark.parametrize("world,shape,chunks", [(2, (10, 9, 7), 1), (3, (7, 8, 5), 1),
+                                                (2, (5, 2, 11), 1), (2, (11, 6, 5), 3),
+                                                (3, (8, 7, 4), 4)])
+def test_sharded_matches_single_process(tmp_path, oracle, world, shape, chunks):
     result = tmp_path / "result.txt"
-    mp.spawn(_worker, args=(world, _free_port(), shape, str(result)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, str(result), chunks), nprocs=world,
+             join=True)
     assert result.read_text() == "ok"
 
 

@@ -59,7 +59,9 @@ SIGNATURES = {
     "vgt_b200_sdf_f64_dev": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _int, _vp, _vp, _vp]),
     "vgt_b200_sdf_from_mask_f32_dev": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _vp, _vp,
                                               _vp]),
-    "vgt_b200_edt_local_passes_dev": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
+    "vgt_b200_edt_local_passes_dev": (_int, [_vp, _i64, _i64, _i64, _int, _int, _int, _vp, _vp]),
+    "vgt_b200_edt_local_passes_scatter_dev": (_int, [_vp, _i64, _i64, _i64, _int, _int, _i64,
+                                                     ctypes.POINTER(ctypes.c_uint64), _int, _vp]),
     "vgt_b200_edt_final_pass_f32_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _dbl, _int, _int,
                                                _vp, _vp, _vp]),
     "vgt_b200_voxelize_f64": (_int, [_vp, _i64, _i64, _i64, _dbl, ctypes.POINTER(Cloud),

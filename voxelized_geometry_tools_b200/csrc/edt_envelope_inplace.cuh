@@ -185,9 +185,49 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp) EnvelopeAxisInPlace
       }
     }
 
-    Out* dst = out + first;
+    // Output row pointer. In send layout (family.out_parts > 0) it jumps at part boundaries,
+    // which are the same for every lane, so the check below is warp-uniform.
+    Out* write_at = out + first;
+    int next_part_start = length;
+    if (family.out_parts > 0)
+    {
+      next_part_start = 0;
+    }
     for (int q = 0; q < length; q++)
     {
+      if (q == next_part_start)
+      {
+        // Part h covers rows [y0, y0 + rows); its block starts at inner * num_outer * y0.
+        const int wide = family.out_base + 1;
+        const int wide_rows = family.out_extra * wide;
+        int y0;
+        int rows;
+        if (q < wide_rows)
+        {
+          y0 = (q / wide) * wide;
+          rows = wide;
+        }
+        else
+        {
+          y0 = wide_rows + ((q - wide_rows) / family.out_base) * family.out_base;
+          rows = family.out_base;
+        }
+        next_part_start = y0 + rows;
+        if (family.scatter_base[0] != nullptr)
+        {
+          // this part goes straight to its owner's receive buffer over NVLink
+          const int part = (q < wide_rows) ? (q / wide)
+                                           : (family.out_extra + (q - wide_rows) / family.out_base);
+          write_at = reinterpret_cast<Out*>(family.scatter_base[part])
+              + family.inner_count * ((family.scatter_row_offset + outer) * rows + (q - y0))
+              + column;
+        }
+        else
+        {
+          write_at = out + family.inner_count * (family.num_outer * y0 + outer * rows + (q - y0))
+              + column;
+        }
+      }
       if ((q & 31) == 0)
       {
         class_word = class_words[(q >> 5) * kWarp + lane];
@@ -248,7 +288,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp) EnvelopeAxisInPlace
 
       if constexpr (kMode == kEmitPacked)
       {
-        dst[static_cast<int64_t>(q) * stride] = (filled << 31) | squared;
+        *write_at = (filled << 31) | squared;
       }
       else
       {
@@ -265,10 +305,11 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp) EnvelopeAxisInPlace
           }
         }
         const Out value = SignedDistanceOf<Out>(filled, squared, finalize.resolution);
-        dst[static_cast<int64_t>(q) * stride] = value;
+        *write_at = value;
         lane_min = (value < lane_min) ? value : lane_min;
         lane_max = (value > lane_max) ? value : lane_max;
       }
+      write_at += stride;
     }
   }
 

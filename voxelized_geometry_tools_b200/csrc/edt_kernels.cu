@@ -175,8 +175,42 @@ LineFamily FamilyAlongX(int64_t nx, int64_t ny, int64_t nz)
 // second buffer of the same size that is used as the intermediate (contents destroyed).
 template <typename In>
 int RunLocalPasses(const In* d_in, int64_t nx, int64_t ny, int64_t nz, int unknown_is_filled,
-                   uint32_t* d_result, uint32_t* d_other, cudaStream_t stream)
+                   uint32_t* d_result, uint32_t* d_other, cudaStream_t stream, int send_parts = 0,
+                   const uint64_t* scatter_bases = nullptr, int64_t scatter_row_offset = 0)
 {
+  if (send_parts > 1)
+  {
+    // Send layout needs the in-place kernel (it owns the output addressing).
+    if (ny > kInPlaceMaxLength || Square(nz - 1) > kInPlaceMaxInput || send_parts > ny)
+    {
+      SetLastError("send layout needs 2 <= parts <= ny <= %d", kInPlaceMaxLength);
+      return VGT_B200_ERR_UNSUPPORTED;
+    }
+    const int status = LaunchScan<In>(d_in, d_other, nx * ny, static_cast<int32_t>(nz),
+                                      unknown_is_filled, stream);
+    if (status != VGT_B200_OK)
+    {
+      return status;
+    }
+    LineFamily family = FamilyAlongY(nx, ny, nz);
+    family.out_parts = send_parts;
+    family.out_base = static_cast<int32_t>(ny / send_parts);
+    family.out_extra = static_cast<int32_t>(ny % send_parts);
+    if (scatter_bases != nullptr)
+    {
+      if (send_parts > 8)
+      {
+        return FailInvalid("fused exchange supports at most 8 ranks");
+      }
+      family.scatter_row_offset = scatter_row_offset;
+      for (int part = 0; part < send_parts; part++)
+      {
+        family.scatter_base[part] = reinterpret_cast<uint32_t*>(scatter_bases[part]);
+      }
+    }
+    return LaunchEnvelope<kEmitPacked>(d_other, d_result, family, Square(nz - 1),
+                                       FinalizeParams{}, nullptr, stream);
+  }
   if (ny <= 1)
   {
     return LaunchScan<In>(d_in, d_result, nx * ny, static_cast<int32_t>(nz), unknown_is_filled,
@@ -490,7 +524,7 @@ int vgt_b200_sdf_f64_dev(
 
 int vgt_b200_edt_local_passes_dev(
     const float* d_occupancy, int64_t nx_local, int64_t ny, int64_t nz, int unknown_is_filled,
-    int device, int32_t* d_out, void* stream)
+    int send_parts, int device, int32_t* d_out, void* stream)
 {
   const int check = CheckSdfArguments(d_occupancy, d_out, nx_local, ny, nz, 1.0);
   if (check != VGT_B200_OK)
@@ -501,13 +535,49 @@ int vgt_b200_edt_local_passes_dev(
   VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
   KeepPoolMemory(device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (send_parts < 0)
+  {
+    return FailInvalid("send_parts must be >= 0");
+  }
   StreamScratch<uint32_t> scratch;
-  if (ny > 1)
+  if (ny > 1 || send_parts > 1)
   {
     VGT_CUDA_TRY(scratch.Allocate(nx_local * ny * nz, s), "local pass scratch allocation");
   }
   return RunLocalPasses<float>(d_occupancy, nx_local, ny, nz, unknown_is_filled,
-                               reinterpret_cast<uint32_t*>(d_out), scratch.get(), s);
+                               reinterpret_cast<uint32_t*>(d_out), scratch.get(), s, send_parts);
+}
+
+int vgt_b200_edt_local_passes_scatter_dev(
+    const float* d_occupancy, int64_t nx_local, int64_t ny, int64_t nz, int unknown_is_filled,
+    int num_ranks, int64_t x_offset, const uint64_t* peer_receive_buffers, int device,
+    void* stream)
+{
+  const int check = CheckSdfArguments(d_occupancy, peer_receive_buffers, nx_local, ny, nz, 1.0);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  if (num_ranks < 2 || num_ranks > 8 || x_offset < 0)
+  {
+    return FailInvalid("fused exchange needs 2..8 ranks and a non-negative x offset");
+  }
+  for (int rank = 0; rank < num_ranks; rank++)
+  {
+    if (peer_receive_buffers[rank] == 0)
+    {
+      return FailInvalid("null peer receive buffer %d", rank);
+    }
+  }
+  ScopedDevice scoped(device);
+  VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+  KeepPoolMemory(device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StreamScratch<uint32_t> scratch;
+  VGT_CUDA_TRY(scratch.Allocate(nx_local * ny * nz, s), "local pass scratch allocation");
+  // d_result is unused in scatter mode (every part has a remote or self-mapped destination).
+  return RunLocalPasses<float>(d_occupancy, nx_local, ny, nz, unknown_is_filled, scratch.get(),
+                               scratch.get(), s, num_ranks, peer_receive_buffers, x_offset);
 }
 
 int vgt_b200_edt_final_pass_f32_dev(

@@ -37,6 +37,20 @@ struct LineFamily
   int64_t inner_count;
   int64_t line_stride;
   int32_t length;
+  // Optional "send layout" for the output of the slab-local y pass (multi-GPU): the line axis is
+  // cut into out_parts near-equal parts (the first out_extra parts hold out_base + 1 rows, the
+  // rest out_base) and part h of every line is stored as the block [num_outer][rows_h][inner],
+  // blocks back to back. That is exactly what the all-to-all sends to rank h, so no packing copy
+  // is needed. out_parts == 0: the output has the input's layout.
+  int32_t out_parts;
+  int32_t out_base;
+  int32_t out_extra;
+  // Fused exchange (multi-GPU): when scatter_base[0] != nullptr, part h is not written into the
+  // local send buffer but straight into rank h's receive buffer [nx_total][rows_h][inner] through
+  // its peer-mapped pointer scatter_base[h] (NVLink stores), at rows scatter_row_offset + outer.
+  // The y pass then IS the all-to-all: no collective call, no intermediate copy.
+  int64_t scatter_row_offset;
+  uint32_t* scatter_base[8];
 };
 
 // What the last pass needs to turn squared voxel distances into the SDF.

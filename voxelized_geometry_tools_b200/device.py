@@ -97,8 +97,12 @@ def signed_distance_field_from_mask(mask: torch.Tensor, resolution: float,
 
 
 def edt_local_passes(occupancy_slab: torch.Tensor, unknown_is_filled: bool = True,
-                     out: torch.Tensor | None = None) -> torch.Tensor:
-    """z and y passes on an x-slab [nx_local, ny, nz] -> sign-fused int32 words."""
+                     out: torch.Tensor | None = None, send_parts: int = 0) -> torch.Tensor:
+    """z and y passes on an x-slab [nx_local, ny, nz] -> sign-fused int32 words.
+
+    send_parts = G > 1 writes the result in send layout (G blocks [nx_local, rows_h, nz] back to
+    back, block h = the part of every y-line that rank h owns); raises NotImplementedError when the
+    library cannot (ny > 1024), in which case the caller packs."""
     _require_cuda(occupancy_slab, torch.float32, "occupancy_slab")
     device = occupancy_slab.device
     if out is None:
@@ -106,10 +110,29 @@ def edt_local_passes(occupancy_slab: torch.Tensor, unknown_is_filled: bool = Tru
     _require_cuda(out, torch.int32, "out")
     nx, ny, nz = occupancy_slab.shape
     code = _capi.library().vgt_b200_edt_local_passes_dev(
-        occupancy_slab.data_ptr(), nx, ny, nz, int(unknown_is_filled), device.index or 0,
-        out.data_ptr(), _stream_handle(device))
+        occupancy_slab.data_ptr(), nx, ny, nz, int(unknown_is_filled), int(send_parts),
+        device.index or 0, out.data_ptr(), _stream_handle(device))
+    if code == _capi.ERR_UNSUPPORTED:
+        raise NotImplementedError(_capi.last_error())
     _capi.check(code)
     return out
+
+
+def edt_local_passes_scatter(occupancy_slab: torch.Tensor, x_offset: int, peer_buffer_ptrs,
+                             unknown_is_filled: bool = True) -> None:
+    """z and y passes on an x-slab with the exchange fused in: the y pass stores each rank's
+    part of every line straight into that rank's receive buffer (peer-mapped device pointers,
+    entry h = rank h's buffer laid out [nx_total, rows_h, nz])."""
+    _require_cuda(occupancy_slab, torch.float32, "occupancy_slab")
+    device = occupancy_slab.device
+    nx, ny, nz = occupancy_slab.shape
+    pointers = (ctypes.c_uint64 * len(peer_buffer_ptrs))(*[int(p) for p in peer_buffer_ptrs])
+    code = _capi.library().vgt_b200_edt_local_passes_scatter_dev(
+        occupancy_slab.data_ptr(), nx, ny, nz, int(unknown_is_filled), len(peer_buffer_ptrs),
+        int(x_offset), pointers, device.index or 0, _stream_handle(device))
+    if code == _capi.ERR_UNSUPPORTED:
+        raise NotImplementedError(_capi.last_error())
+    _capi.check(code)
 
 
 def edt_final_pass(packed: torch.Tensor, y_offset: int, ny_total: int, resolution: float,

@@ -34,9 +34,15 @@ def split_range(total: int, parts: int, index: int) -> tuple[int, int]:
 class Stages:
     """local_passes(occupancy_slab[nxl, ny, nz] f32, unknown_is_filled) -> int32 [nxl, ny, nz]
     final_pass(packed[nx, nyl, nz] int32, y_offset, ny_total, resolution, add_virtual_border)
-        -> (sdf f32 [nx, nyl, nz], min_max f32 [2])"""
+        -> (sdf f32 [nx, nyl, nz], min_max f32 [2])
+    local_passes_send (optional): (occupancy_slab, unknown_is_filled, parts) -> flat int32 in send
+        layout (parts blocks [nxl, rows_h, nz] back to back); may raise NotImplementedError."""
     local_passes: Callable
     final_pass: Callable
+    local_passes_send: Callable | None = None
+    # (occupancy_slab, x_offset, peer_buffer_ptrs, unknown_is_filled) -> None: passes with the
+    # exchange fused in (peer stores); CUDA only.
+    local_passes_scatter: Callable | None = None
 
 
 def cuda_stages() -> Stages:
@@ -45,17 +51,40 @@ def cuda_stages() -> Stages:
     def local_passes(occupancy_slab, unknown_is_filled):
         return device.edt_local_passes(occupancy_slab, unknown_is_filled)
 
+    def local_passes_send(occupancy_slab, unknown_is_filled, parts):
+        return device.edt_local_passes(occupancy_slab, unknown_is_filled,
+                                       send_parts=parts).view(-1)
+
     def final_pass(packed, y_offset, ny_total, resolution, add_virtual_border):
         return device.edt_final_pass(packed, y_offset, ny_total, resolution, add_virtual_border)
 
-    return Stages(local_passes, final_pass)
+    def local_passes_scatter(occupancy_slab, x_offset, peer_buffer_ptrs, unknown_is_filled):
+        device.edt_local_passes_scatter(occupancy_slab, x_offset, peer_buffer_ptrs,
+                                        unknown_is_filled)
+
+    return Stages(local_passes, final_pass, local_passes_send, local_passes_scatter)
 
 
 class ShardedSignedDistanceField:
     def __init__(self, dims, rank: int | None = None, world_size: int | None = None,
-                 group=None, stages: Stages | None = None):
+                 group=None, stages: Stages | None = None, chunks: int = 1,
+                 profile: bool = False, exchange: str = "auto"):
+        """chunks > 1 cuts the x-slab into that many x-chunks: the slab-local passes of chunk c+1
+        overlap the all-to-all of chunk c (NCCL runs on its own stream). profile=True records CUDA
+        events around the stages (``last_stage_ms`` after a synchronise)."""
+        # exchange: "peer_store" = the y pass stores straight into the peers' receive buffers over
+        # NVLink (symmetric memory, no collective call); "nccl" = all-to-all; "auto" = peer_store
+        # when the stages and the device support it, else nccl.
         self.dims = tuple(int(d) for d in dims)
         self.group = group
+        self.exchange = exchange
+        self.exchange_used = None
+        self._peer = None
+        self._step = 0
+        self.chunks = max(1, int(chunks))
+        self.profile = profile
+        self.last_stage_ms = None
+        self._events = None
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
         nx, ny, _ = self.dims
@@ -72,27 +101,33 @@ class ShardedSignedDistanceField:
     def y_slab_shape(self):
         return (self.dims[0], self.y_range[1] - self.y_range[0], self.dims[2])
 
-    def _exchange(self, packed: torch.Tensor) -> torch.Tensor:
-        """All-to-all transpose: x-slab [nxl, ny, nz] -> y-slab [nx, nyl, nz].
+    def pack_send_layout(self, packed: torch.Tensor) -> torch.Tensor:
+        """[nxl, ny, nz] -> send layout by a copy (fallback when the kernel cannot write it)."""
+        ny = self.dims[1]
+        chunks = []
+        for peer in range(self.world_size):
+            y0, y1 = split_range(ny, self.world_size, peer)
+            chunks.append(packed[:, y0:y1, :].reshape(-1))
+        return torch.cat(chunks)
+
+    def _exchange(self, send: torch.Tensor) -> torch.Tensor:
+        """All-to-all transpose: send layout of an x-slab -> y-slab [nx, nyl, nz].
 
         The block received from rank g is rows x in [x0_g, x1_g) of the y-slab, which is one
         contiguous range of the destination, so the collective writes straight into place."""
         nx, ny, nz = self.dims
         world = self.world_size
         nyl = self.y_range[1] - self.y_range[0]
-        if world == 1:
-            return packed
-        send_chunks = []
+        nxl = self.x_range[1] - self.x_range[0]
+        send_splits = []
         for peer in range(world):
             y0, y1 = split_range(ny, world, peer)
-            send_chunks.append(packed[:, y0:y1, :].reshape(-1))
-        send = torch.cat(send_chunks)
-        send_splits = [int(chunk.numel()) for chunk in send_chunks]
+            send_splits.append(nxl * (y1 - y0) * nz)
         recv_splits = []
         for peer in range(world):
             x0, x1 = split_range(nx, world, peer)
             recv_splits.append((x1 - x0) * nyl * nz)
-        received = torch.empty(nx * nyl * nz, dtype=packed.dtype, device=packed.device)
+        received = torch.empty(nx * nyl * nz, dtype=send.dtype, device=send.device)
         dist.all_to_all_single(received, send, recv_splits, send_splits, group=self.group)
         return received.view(nx, nyl, nz)
 
@@ -103,16 +138,153 @@ class ShardedSignedDistanceField:
         Returns (sdf y-slab [nx, nyl, nz] float32, global (min, max) tensor [2])."""
         if tuple(occupancy_slab.shape) != self.x_slab_shape():
             raise ValueError(f"expected an x-slab of shape {self.x_slab_shape()}")
-        packed = self.stages.local_passes(occupancy_slab, unknown_is_filled)
-        y_slab = self._exchange(packed)
+        self._mark("start", occupancy_slab)
+        if (self.world_size > 1 and self.exchange in ("auto", "peer_store")
+                and self.stages.local_passes_scatter is not None and occupancy_slab.is_cuda
+                and self._peer is None):
+            self._setup_peer_store(occupancy_slab.device)
+        if self.world_size > 1 and self._peer:
+            y_slab = self._peer_store_local_and_exchange(occupancy_slab, unknown_is_filled)
+            self.exchange_used = "peer_store"
+        elif self.world_size == 1:
+            y_slab = self.stages.local_passes(occupancy_slab, unknown_is_filled)
+            self._mark("local", occupancy_slab)
+        elif self.chunks > 1 and self.stages.local_passes_send is not None:
+            y_slab = self._chunked_local_and_exchange(occupancy_slab, unknown_is_filled)
+            self.exchange_used = "nccl"
+        else:
+            send = None
+            if self.stages.local_passes_send is not None:
+                try:
+                    send = self.stages.local_passes_send(occupancy_slab, unknown_is_filled,
+                                                         self.world_size)
+                except NotImplementedError:
+                    send = None
+            if send is None:
+                send = self.pack_send_layout(
+                    self.stages.local_passes(occupancy_slab, unknown_is_filled))
+            self._mark("local", occupancy_slab)
+            y_slab = self._exchange(send)
+            self.exchange_used = "nccl"
+        self._mark("exchange", occupancy_slab)
         sdf, min_max = self.stages.final_pass(
             y_slab, self.y_range[0], self.dims[1], resolution, add_virtual_border)
+        self._mark("final", occupancy_slab)
         if self.world_size > 1:
             # one tiny all-reduce: max over (-min, max)
             folded = torch.stack([-min_max[0], min_max[1]])
             dist.all_reduce(folded, op=dist.ReduceOp.MAX, group=self.group)
             min_max = torch.stack([-folded[0], folded[1]])
         return sdf, min_max
+
+    # ------------------------------------------------------------------ fused peer-store exchange
+    def _setup_peer_store(self, device) -> None:
+        """Two symmetric receive buffers (double-buffered across steps), mapped into every rank."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nx, ny, nz = self.dims
+            max_nyl = -(-ny // self.world_size)
+            group = self.group if self.group is not None else dist.group.WORLD
+            buffers, handles = [], []
+            for _ in range(2):
+                buffer = symm_mem.empty(nx * max_nyl * nz, dtype=torch.int32, device=device)
+                handles.append(symm_mem.rendezvous(buffer, group))
+                buffers.append(buffer)
+            self._peer = {"buffers": buffers, "handles": handles}
+        except Exception as error:  # no symmetric memory on this system: use NCCL
+            if self.exchange == "peer_store":
+                raise
+            self._peer = False
+            self._peer_error = repr(error)
+
+    def _peer_store_local_and_exchange(self, occupancy_slab, unknown_is_filled):
+        nx, _, nz = self.dims
+        nyl = self.y_range[1] - self.y_range[0]
+        index = self._step % 2
+        self._step += 1
+        buffer, handle = self._peer["buffers"][index], self._peer["handles"][index]
+        # The y pass of every rank writes its part of our y-slab into `buffer`. Double buffering
+        # plus the barrier below keeps a rank from overwriting a buffer its owner still reads.
+        self.stages.local_passes_scatter(occupancy_slab, self.x_range[0],
+                                         [int(p) for p in handle.buffer_ptrs], unknown_is_filled)
+        self._mark("local", occupancy_slab)
+        handle.barrier(channel=0)
+        return buffer[:nx * nyl * nz].view(nx, nyl, nz)
+
+    # ------------------------------------------------------------------ chunked overlap
+    def _chunked_local_and_exchange(self, occupancy_slab, unknown_is_filled):
+        """x-chunks of the slab: passes on chunk c+1 overlap the all-to-all of chunk c. The block
+        that rank g's chunk c contributes to our y-slab is rows x in [x0_g + c0, x0_g + c1): a
+        contiguous range of the destination, received in place."""
+        nx, ny, nz = self.dims
+        world = self.world_size
+        nyl = self.y_range[1] - self.y_range[0]
+        nxl = self.x_range[1] - self.x_range[0]
+        received = torch.empty((nx, nyl, nz), dtype=torch.int32, device=occupancy_slab.device)
+        # every rank must issue the same number of collectives: chunk the LARGEST slab size
+        max_nxl = -(-nx // world)
+        chunks = min(self.chunks, max_nxl)
+        works, keep = [], []
+        for c in range(chunks):
+            c0, c1 = split_range(nxl, chunks, c)
+            if c1 > c0:
+                try:
+                    send = self.stages.local_passes_send(
+                        occupancy_slab[c0:c1], unknown_is_filled, world)
+                except NotImplementedError:
+                    send = self.pack_send_layout_rows(
+                        self.stages.local_passes(occupancy_slab[c0:c1], unknown_is_filled))
+            else:
+                send = torch.empty(0, dtype=torch.int32, device=occupancy_slab.device)
+            inputs, outputs, offset = [], [], 0
+            for peer in range(world):
+                y0, y1 = split_range(ny, world, peer)
+                count = (c1 - c0) * (y1 - y0) * nz
+                inputs.append(send[offset:offset + count])
+                offset += count
+                px0, px1 = split_range(nx, world, peer)
+                pc0, pc1 = split_range(px1 - px0, chunks, c)
+                outputs.append(received[px0 + pc0:px0 + pc1].view(-1))
+            keep.append(send)
+            # grouped point-to-point (works on NCCL and gloo alike); own block = local copy
+            outputs[self.rank].copy_(inputs[self.rank])
+            ops = []
+            for peer in range(world):
+                if peer == self.rank:
+                    continue
+                if inputs[peer].numel() > 0:
+                    ops.append(dist.P2POp(dist.isend, inputs[peer], peer, group=self.group))
+                if outputs[peer].numel() > 0:
+                    ops.append(dist.P2POp(dist.irecv, outputs[peer], peer, group=self.group))
+            if ops:
+                works.extend(dist.batch_isend_irecv(ops))
+        self._mark("local", occupancy_slab)
+        for work in works:
+            work.wait()
+        return received
+
+    def pack_send_layout_rows(self, packed: torch.Tensor) -> torch.Tensor:
+        ny = self.dims[1]
+        return torch.cat([packed[:, split_range(ny, self.world_size, p)[0]:
+                                 split_range(ny, self.world_size, p)[1], :].reshape(-1)
+                          for p in range(self.world_size)])
+
+    # ------------------------------------------------------------------ optional stage timing
+    def _mark(self, name: str, like: torch.Tensor) -> None:
+        if not self.profile or not like.is_cuda:
+            return
+        if name == "start":
+            self._events = []
+        event = torch.cuda.Event(enable_timing=True)
+        event.record()
+        self._events.append((name, event))
+
+    def stage_ms(self):
+        """After a synchronise: {stage: ms} of the last profiled extract()."""
+        if not self._events:
+            return None
+        return {name: self._events[i - 1][1].elapsed_time(event)
+                for i, (name, event) in enumerate(self._events) if i > 0}
 
     def gather_to_host(self, sdf_y_slab: torch.Tensor) -> torch.Tensor | None:
         """Collects the y-slabs into one [nx, ny, nz] host tensor on rank 0 (small grids only)."""
