@@ -177,3 +177,17 @@ def test_full_size_512_properties_and_parity(shared_library, oracle):
     want, (lo, hi) = oracle.sdf(occupancy, resolution)
     np.testing.assert_array_equal(data, want)
     assert sdf.GetMinimumMaximum() == (lo, hi)
+
+
+def test_axes_longer_than_1024_and_large_distances(shared_library, oracle):
+    # > 1024 voxels along an axis (or partial distances >= 2^21) switches the envelope kernel to
+    # split stack entries (value in place, position in a uint16 side array).
+    rng = np.random.default_rng(31)
+    base = random_occupancy(rng, (5, 1100, 37), 0.03, blobs=True)
+    assert_matches_oracle(oracle, base, 0.01)                                           # y long
+    assert_matches_oracle(oracle, np.ascontiguousarray(base.transpose(1, 0, 2)), 0.01)  # x long
+    assert_matches_oracle(oracle, np.ascontiguousarray(base.transpose(0, 2, 1)), 0.01,
+                          add_virtual_border=True)                                      # z long
+    sparse = np.zeros((3, 40, 2100), dtype=np.float32)   # z distances up to 2099 -> sq > 2^21
+    sparse[1, 20, 0] = 1.0
+    assert_matches_oracle(oracle, sparse, 0.5)

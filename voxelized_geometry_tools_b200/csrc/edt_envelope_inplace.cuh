@@ -41,10 +41,16 @@ __device__ __forceinline__ Site UnpackInPlace(uint32_t e)
   return Site{v, f + v * v};
 }
 
-template <int kMode>
-__global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp) EnvelopeAxisInPlaceStackKernel(
-    uint32_t* in, typename OutputOf<kMode>::Type* out, LineFamily family, FinalizeParams finalize,
-    typename OutputOf<kMode>::Key* min_max_keys)
+// kSplit = false: one packed 32-bit entry (f << 10 | v) per slot, for axes <= 1024 voxels and
+//                  partial distances < 2^21.
+// kSplit = true:  f stays a full 31-bit word in place and v goes to `positions`, a uint16 side
+//                  array addressed exactly like the grid (2 more bytes per voxel of scratch); this
+//                  lifts the limits to 8192 voxels per axis and 2^31 - 1.
+template <int kMode, bool kSplit>
+__global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPacked) ? 16 : 12)
+    EnvelopeAxisInPlaceStackKernel(
+    uint32_t* in, typename OutputOf<kMode>::Type* out, uint16_t* positions, LineFamily family,
+    FinalizeParams finalize, typename OutputOf<kMode>::Key* min_max_keys)
 {
   using Out = typename OutputOf<kMode>::Type;
   extern __shared__ uint32_t class_smem[];  // [warp][word][lane]
@@ -74,6 +80,33 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp) EnvelopeAxisInPlace
   if (active)
   {
     uint32_t* line = in + first;
+    uint16_t* line_positions = kSplit ? (positions + first) : nullptr;
+    const auto store_entry = [&](int at_slot, int32_t v, uint32_t f)
+    {
+      const int64_t offset = static_cast<int64_t>(at_slot) * stride;
+      if constexpr (kSplit)
+      {
+        line[offset] = f;
+        line_positions[offset] = static_cast<uint16_t>(v);
+      }
+      else
+      {
+        line[offset] = PackInPlace(v, f);
+      }
+    };
+    const auto load_entry = [&](int at_slot)
+    {
+      const int64_t offset = static_cast<int64_t>(at_slot) * stride;
+      if constexpr (kSplit)
+      {
+        const int32_t v = static_cast<int32_t>(line_positions[offset]);
+        return Site{v, static_cast<int32_t>(line[offset]) + v * v};
+      }
+      else
+      {
+        return UnpackInPlace(line[offset]);
+      }
+    };
 
     // ------------------------------------------------------------------ phase 1: build stacks
     int slot = 0;   // next free stack slot == row of the line it will be written to
@@ -94,7 +127,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp) EnvelopeAxisInPlace
         top = below;
         if (depth >= 2)
         {
-          below = UnpackInPlace(line[static_cast<int64_t>(slot - 2) * stride]);
+          below = load_entry(slot - 2);
         }
         else
         {
@@ -142,7 +175,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp) EnvelopeAxisInPlace
           {
             const Site incoming{q, static_cast<int32_t>(value) + q * q};
             pop_hidden(incoming);
-            line[static_cast<int64_t>(slot) * stride] = PackInPlace(q, value);
+            store_entry(slot, q, value);
             below = top;
             top = incoming;
             depth++;
@@ -159,7 +192,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp) EnvelopeAxisInPlace
     {
       if (index < stored_total)
       {
-        return UnpackInPlace(line[static_cast<int64_t>(index) * stride]);
+        return load_entry(index);
       }
       return Site{kNoSitePosition, kNoSiteHeight};
     };
@@ -218,7 +251,15 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp) EnvelopeAxisInPlace
           // this part goes straight to its owner's receive buffer over NVLink
           const int part = (q < wide_rows) ? (q / wide)
                                            : (family.out_extra + (q - wide_rows) / family.out_base);
-          write_at = reinterpret_cast<Out*>(family.scatter_base[part])
+          // (selected with compares: indexing the kernel-parameter array with a register would
+          // force a local-memory copy of the whole parameter struct)
+          uint32_t* base = family.scatter_base[0];
+#pragma unroll
+          for (int i = 1; i < 8; i++)
+          {
+            base = (part == i) ? family.scatter_base[i] : base;
+          }
+          write_at = reinterpret_cast<Out*>(base)
               + family.inner_count * ((family.scatter_row_offset + outer) * rows + (q - y0))
               + column;
         }

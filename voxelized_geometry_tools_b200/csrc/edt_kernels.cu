@@ -85,51 +85,10 @@ int LaunchScan(const In* d_in, uint32_t* d_out, int64_t num_lines, int32_t lengt
   return VGT_B200_OK;
 }
 
-// Fallback for long axes: envelope stack in shared memory, 8-byte entries, fewer lanes per warp
-// when the line is too long for 32 stacks to fit.
-template <int kMode>
-int LaunchEnvelopeSharedStack(const uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
-                              const LineFamily& family, const FinalizeParams& finalize,
-                              typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
-{
-  constexpr int kEntryBytes = 8;
-  const int num_words = (family.length + 31) >> 5;
-  int lanes = kWarp;
-  size_t smem = 0;
-  while (true)
-  {
-    smem = (static_cast<size_t>(family.length) * kEntryBytes + static_cast<size_t>(num_words) * 4)
-        * lanes;
-    if (smem <= kMaxDynamicSmem || lanes == 1)
-    {
-      break;
-    }
-    lanes >>= 1;
-  }
-  if (smem > kMaxDynamicSmem)
-  {
-    return FailInvalid("axis of %d voxels does not fit the shared-memory envelope stack",
-                       family.length);
-  }
-  auto kernel = EnvelopeAxisKernel<kEntryBytes, kMode>;
-  VGT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(kMaxDynamicSmem)),
-               "EnvelopeAxisKernel smem attribute");
-  const int64_t tiles_per_outer = (family.inner_count + lanes - 1) / lanes;
-  const int64_t blocks = tiles_per_outer * family.num_outer;
-  if (blocks > 0x7fffffffLL)
-  {
-    return FailInvalid("grid too large for one launch");
-  }
-  kernel<<<static_cast<unsigned>(blocks), kWarp, smem, stream>>>(d_in, d_out, family, lanes,
-                                                                 finalize, d_keys);
-  VGT_CUDA_TRY(cudaGetLastError(), "EnvelopeAxisKernel launch");
-  return VGT_B200_OK;
-}
-
-template <int kMode>
+template <int kMode, bool kSplit>
 int LaunchEnvelopeInPlaceStack(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
-                               const LineFamily& family, const FinalizeParams& finalize,
+                               uint16_t* d_positions, const LineFamily& family,
+                               const FinalizeParams& finalize,
                                typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
 {
   const int num_words = (family.length + 31) >> 5;
@@ -140,15 +99,23 @@ int LaunchEnvelopeInPlaceStack(uint32_t* d_in, typename OutputOf<kMode>::Type* d
   {
     return FailInvalid("grid too large for one launch");
   }
-  EnvelopeAxisInPlaceStackKernel<kMode>
-      <<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, smem, stream>>>(
-          d_in, d_out, family, finalize, d_keys);
+  auto kernel = EnvelopeAxisInPlaceStackKernel<kMode, kSplit>;
+  if (smem > 48 * 1024)
+  {
+    VGT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)),
+                 "EnvelopeAxisInPlaceStackKernel smem attribute");
+  }
+  kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, smem, stream>>>(
+      d_in, d_out, d_positions, family, finalize, d_keys);
   VGT_CUDA_TRY(cudaGetLastError(), "EnvelopeAxisInPlaceStackKernel launch");
   return VGT_B200_OK;
 }
 
 // One strided-axis pass. d_in is DESTROYED and must not alias d_out.
-// max_input: largest finite partial squared distance the pass can see.
+// max_input: largest finite partial squared distance the pass can see. Short axes use packed
+// 32-bit stack entries; longer ones keep the site positions in a stream-ordered uint16 side array
+// (2 bytes per voxel, span = the family's element span).
 template <int kMode>
 int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
                    const LineFamily& family, int64_t max_input, const FinalizeParams& finalize,
@@ -156,9 +123,19 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
 {
   if (family.length <= kInPlaceMaxLength && max_input <= kInPlaceMaxInput)
   {
-    return LaunchEnvelopeInPlaceStack<kMode>(d_in, d_out, family, finalize, d_keys, stream);
+    return LaunchEnvelopeInPlaceStack<kMode, false>(d_in, d_out, nullptr, family, finalize,
+                                                    d_keys, stream);
   }
-  return LaunchEnvelopeSharedStack<kMode>(d_in, d_out, family, finalize, d_keys, stream);
+  if (family.length > VGT_B200_MAX_AXIS || max_input > 0x7ffffffeLL)
+  {
+    return FailInvalid("axis of %d voxels is out of range", family.length);
+  }
+  const int64_t span = (family.num_outer - 1) * family.outer_stride
+      + static_cast<int64_t>(family.length - 1) * family.line_stride + family.inner_count;
+  StreamScratch<uint16_t> positions;
+  VGT_CUDA_TRY(positions.Allocate(span, stream), "envelope position side array");
+  return LaunchEnvelopeInPlaceStack<kMode, true>(d_in, d_out, positions.get(), family, finalize,
+                                                 d_keys, stream);
 }
 
 LineFamily FamilyAlongY(int64_t nx, int64_t ny, int64_t nz)
@@ -180,11 +157,10 @@ int RunLocalPasses(const In* d_in, int64_t nx, int64_t ny, int64_t nz, int unkno
 {
   if (send_parts > 1)
   {
-    // Send layout needs the in-place kernel (it owns the output addressing).
-    if (ny > kInPlaceMaxLength || Square(nz - 1) > kInPlaceMaxInput || send_parts > ny)
+    if (send_parts > ny)
     {
-      SetLastError("send layout needs 2 <= parts <= ny <= %d", kInPlaceMaxLength);
-      return VGT_B200_ERR_UNSUPPORTED;
+      return FailInvalid("more parts (%d) than rows along y (%lld)", send_parts,
+                         static_cast<long long>(ny));
     }
     const int status = LaunchScan<In>(d_in, d_other, nx * ny, static_cast<int32_t>(nz),
                                       unknown_is_filled, stream);
