@@ -42,6 +42,13 @@ SDF_BYTES_PER_VOXEL = 24           # 3 passes x (4 B in + 4 B out), SURVEY.md se
 PASS_BYTES_PER_VOXEL = 8
 KERNELS_PER_STEP = 5               # scan, y envelope, key reset, x envelope + finalize, key decode
 CPU_SAMPLE_DIMS = (256, 256, 256)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+# capture of this very workload (profiles/r1_ncu_kernels.txt); None for anything not captured.
+NCU_DRAM_BYTES_PER_LAUNCH = {
+    ((512, 512, 512), "ScanContiguousAxisKernel (z)"): 536.9e6 + 479.6e6,
+    ((512, 512, 512), "EnvelopeAxisKernel (y)"): 712.9e6 + 577.5e6,
+    ((512, 512, 512), "EnvelopeAxisKernel (x + finalize)"): 852.9e6 + 679.4e6,
+}
 
 
 def workload_dims(n_gpus: int):
@@ -248,7 +255,9 @@ def run_ours(args):
                  "EnvelopeAxisKernel (x + finalize)"]
         achieved = PASS_BYTES_PER_VOXEL * voxels / (pass_ms[dominant] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": names[dominant], "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((tuple(dims), names[dominant])),
+                    "traffic_source": "profiles/r1_ncu_kernels.txt (ncu --set full, same workload)",
                     "peak_kind": peak_kind,
                     "algorithmic_bytes_per_launch": PASS_BYTES_PER_VOXEL * voxels,
                     "pass_ms": {"z_scan": pass_ms[0], "y_envelope": pass_ms[1],
