@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 
 #include "../../include/vgt_b200.h"
 
@@ -77,6 +78,56 @@ public:
 
 private:
   T* ptr_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Stream-ordered scratch. The default memory pool keeps freed blocks (release threshold raised
+// once per device), so steady-state calls do not touch the OS allocator.
+// ------------------------------------------------------------------------------------------------
+inline void KeepPoolMemory(int device)
+{
+  static std::once_flag flags[64];
+  if (device < 0 || device >= 64)
+  {
+    return;
+  }
+  std::call_once(flags[device], [device]()
+  {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+    {
+      unsigned long long threshold = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
+  });
+}
+
+template <typename T>
+class StreamScratch
+{
+public:
+  StreamScratch() = default;
+  StreamScratch(const StreamScratch&) = delete;
+  StreamScratch& operator=(const StreamScratch&) = delete;
+  ~StreamScratch()
+  {
+    if (ptr_ != nullptr)
+    {
+      cudaFreeAsync(ptr_, stream_);
+    }
+  }
+  cudaError_t Allocate(int64_t count, cudaStream_t stream)
+  {
+    stream_ = stream;
+    return cudaMallocAsync(reinterpret_cast<void**>(&ptr_), sizeof(T) * static_cast<size_t>(count),
+                           stream);
+  }
+  T* get() const { return ptr_; }
+
+private:
+  T* ptr_ = nullptr;
+  cudaStream_t stream_ = nullptr;
 };
 
 inline bool ValidDims(int64_t nx, int64_t ny, int64_t nz)

@@ -1,5 +1,5 @@
-// Device code of the exact signed squared EDT (sm_100a): the z scan and the strided-axis envelope
-// kernels. Included by edt_kernels.cu only. See edt_kernels.cuh for the data representation.
+// Device code of the exact signed squared EDT (sm_100a): the z scan and the pieces shared with the
+// strided-axis envelope kernel. Included by edt_kernels.cu only. See edt_kernels.cuh for the data representation.
 #pragma once
 
 #include <cstdint>
@@ -41,49 +41,13 @@ __device__ __forceinline__ uint32_t ValidBits(int word, int length)
   return (remaining >= 32) ? 0xffffffffu : ((1u << remaining) - 1u);
 }
 
-template <typename In>
-__global__ void __launch_bounds__(kScanWarpsPerBlock * kWarp) ScanContiguousAxisKernel(
-    const In* __restrict__ in, uint32_t* __restrict__ out, int64_t num_lines, int32_t length,
-    int unknown_is_filled)
+// For every 32-voxel word of a line: position of the last filled / free voxel before the word and
+// of the first one after it (kFar offsets when there is none). Warp scans over 32 words at a time
+// with a carry, so lines of any length work. `words` and the four tables live in shared memory.
+__device__ __forceinline__ void BuildWordTables(
+    const uint32_t* words, int32_t* last_filled_before, int32_t* last_free_before,
+    int32_t* first_filled_after, int32_t* first_free_after, int num_words, int length, int lane)
 {
-  extern __shared__ uint32_t scan_smem[];
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int num_words = (length + 31) >> 5;
-  const int64_t line = static_cast<int64_t>(blockIdx.x) * kScanWarpsPerBlock + warp;
-  if (line >= num_lines)
-  {
-    return;  // warp-uniform
-  }
-  uint32_t* words = scan_smem + warp * 5 * num_words;
-  int32_t* last_filled_before = reinterpret_cast<int32_t*>(words + num_words);
-  int32_t* last_free_before = last_filled_before + num_words;
-  int32_t* first_filled_after = last_free_before + num_words;
-  int32_t* first_free_after = first_filled_after + num_words;
-
-  const In* src = in + line * length;
-  uint32_t* dst = out + line * length;
-
-  // 1. classify: one ballot word per 32 voxels.
-#pragma unroll 4
-  for (int w = 0; w < num_words; w++)
-  {
-    const int z = (w << 5) + lane;
-    bool filled = false;
-    if (z < length)
-    {
-      filled = IsFilled(LoadStreaming(src + z), unknown_is_filled);
-    }
-    const uint32_t word = __ballot_sync(0xffffffffu, filled);
-    if (lane == 0)
-    {
-      words[w] = word;
-    }
-  }
-  __syncwarp();
-
-  // 2. for every word: position of the last filled / free voxel before it and the first after it
-  //    (warp scans over 32 words at a time with a carry).
   {
     int carry_filled = -kFar;
     int carry_free = -kFar;
@@ -175,6 +139,52 @@ __global__ void __launch_bounds__(kScanWarpsPerBlock * kWarp) ScanContiguousAxis
       carry_free = min(carry_free, __shfl_sync(0xffffffffu, first_free, 0));
     }
   }
+}
+
+template <typename In>
+__global__ void __launch_bounds__(kScanWarpsPerBlock * kWarp) ScanContiguousAxisKernel(
+    const In* __restrict__ in, uint32_t* __restrict__ out, int64_t num_lines, int32_t length,
+    int unknown_is_filled)
+{
+  extern __shared__ uint32_t scan_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_words = (length + 31) >> 5;
+  const int64_t line = static_cast<int64_t>(blockIdx.x) * kScanWarpsPerBlock + warp;
+  if (line >= num_lines)
+  {
+    return;  // warp-uniform
+  }
+  uint32_t* words = scan_smem + warp * 5 * num_words;
+  int32_t* last_filled_before = reinterpret_cast<int32_t*>(words + num_words);
+  int32_t* last_free_before = last_filled_before + num_words;
+  int32_t* first_filled_after = last_free_before + num_words;
+  int32_t* first_free_after = first_filled_after + num_words;
+
+  const In* src = in + line * length;
+  uint32_t* dst = out + line * length;
+
+  // 1. classify: one ballot word per 32 voxels.
+#pragma unroll 4
+  for (int w = 0; w < num_words; w++)
+  {
+    const int z = (w << 5) + lane;
+    bool filled = false;
+    if (z < length)
+    {
+      filled = IsFilled(LoadStreaming(src + z), unknown_is_filled);
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, filled);
+    if (lane == 0)
+    {
+      words[w] = word;
+    }
+  }
+  __syncwarp();
+
+  // 2. per-word tables of the nearest filled / free voxel outside the word.
+  BuildWordTables(words, last_filled_before, last_free_before, first_filled_after,
+                  first_free_after, num_words, length, lane);
   __syncwarp();
 
   // 3. per voxel: nearest opposite-class voxel inside the word (bit scan) or outside (tables).
@@ -201,14 +211,120 @@ __global__ void __launch_bounds__(kScanWarpsPerBlock * kWarp) ScanContiguousAxis
   }
 }
 
+// Four voxels per lane: 128-bit loads and stores, 128 voxels per warp iteration. Needs lines that
+// start 16-byte aligned (length % 4 == 0). Same algorithm as above; a lane's four class bits are
+// merged into its group's 32-bit word with one redux.or over the 8 lanes that share the word.
+struct Float4Source
+{
+  using Vector = float4;
+  __device__ static __forceinline__ uint32_t Nibble(const float4& v, int unknown_is_filled)
+  {
+    return (IsFilled(v.x, unknown_is_filled) ? 1u : 0u) | (IsFilled(v.y, unknown_is_filled) ? 2u : 0u)
+        | (IsFilled(v.z, unknown_is_filled) ? 4u : 0u) | (IsFilled(v.w, unknown_is_filled) ? 8u : 0u);
+  }
+};
+
+struct Uchar4Source
+{
+  using Vector = uchar4;
+  __device__ static __forceinline__ uint32_t Nibble(const uchar4& v, int)
+  {
+    return (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
+  }
+};
+
+template <typename Source>
+__global__ void __launch_bounds__(kScanWarpsPerBlock * kWarp) ScanContiguousAxisVec4Kernel(
+    const typename Source::Vector* __restrict__ in, uint4* __restrict__ out, int64_t num_lines,
+    int32_t length, int unknown_is_filled)
+{
+  using Vector = typename Source::Vector;
+  extern __shared__ uint32_t scan_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_words = (length + 31) >> 5;
+  const int64_t line = static_cast<int64_t>(blockIdx.x) * kScanWarpsPerBlock + warp;
+  if (line >= num_lines)
+  {
+    return;  // warp-uniform
+  }
+  uint32_t* words = scan_smem + warp * 5 * num_words;
+  int32_t* last_filled_before = reinterpret_cast<int32_t*>(words + num_words);
+  int32_t* last_free_before = last_filled_before + num_words;
+  int32_t* first_filled_after = last_free_before + num_words;
+  int32_t* first_free_after = first_filled_after + num_words;
+
+  const int vectors = length >> 2;  // per line
+  const Vector* src = in + line * vectors;
+  uint4* dst = out + line * vectors;
+  const int group = lane >> 3;                       // which of the 4 words of this iteration
+  const int bit0 = (lane & 7) << 2;                  // first of this lane's 4 bits in that word
+  const unsigned group_mask = 0xffu << (group << 3);
+  const int iterations = (length + 127) >> 7;
+
+  // 1. classify: 4 voxels per lane, one 32-bit class word per 8 lanes.
+#pragma unroll 2
+  for (int it = 0; it < iterations; it++)
+  {
+    const int vector_index = (it << 5) + lane;
+    uint32_t nibble = 0;
+    if (vector_index < vectors)
+    {
+      nibble = Source::Nibble(__ldcs(src + vector_index), unknown_is_filled);
+    }
+    const uint32_t word = __reduce_or_sync(group_mask, nibble << bit0);
+    const int w = (it << 2) + group;
+    if ((lane & 7) == 0 && w < num_words)
+    {
+      words[w] = word;
+    }
+  }
+  __syncwarp();
+
+  // 2. per-word tables of the nearest filled / free voxel outside the word.
+  BuildWordTables(words, last_filled_before, last_free_before, first_filled_after,
+                  first_free_after, num_words, length, lane);
+  __syncwarp();
+
+  // 3. per voxel: nearest opposite-class voxel inside the word (bit scan) or outside (tables).
+  for (int it = 0; it < iterations; it++)
+  {
+    const int vector_index = (it << 5) + lane;
+    const int w = (it << 2) + group;
+    if (vector_index >= vectors)
+    {
+      continue;
+    }
+    const uint32_t word = words[w];
+    const uint32_t valid = ValidBits(w, length);
+    const int before_filled = last_filled_before[w];
+    const int before_free = last_free_before[w];
+    const int after_filled = first_filled_after[w];
+    const int after_free = first_free_after[w];
+    uint32_t results[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+      const int bit = bit0 + k;
+      const int z = (w << 5) + bit;
+      const uint32_t filled = (word >> bit) & 1u;
+      const uint32_t opposite = (filled ? ~word : word) & valid;
+      const uint32_t below = opposite & ((1u << bit) - 1u);
+      const uint32_t above = (bit == 31) ? 0u : (opposite >> (bit + 1));
+      const int left = below ? (bit - (31 - __clz(below))) : (z - (filled ? before_free : before_filled));
+      const int right = above ? __ffs(above) : ((filled ? after_free : after_filled) - z);
+      const int nearest = min(left, right);
+      const uint32_t squared =
+          (nearest >= kFarThreshold) ? kNone : static_cast<uint32_t>(nearest * nearest);
+      results[k] = (filled << 31) | squared;
+    }
+    dst[vector_index] = make_uint4(results[0], results[1], results[2], results[3]);
+  }
+}
+
 // ================================================================================================
-// Passes B and C: a strided axis. One lane owns one line, a warp owns kWarp (or fewer, for very
-// long lines) adjacent lines, so every global access of the warp is one contiguous row segment.
-// Each lane runs the run-decomposed Felzenszwalb-Huttenlocher envelope with its stack in shared
-// memory ([slot][lane] layout: lanes never collide on a bank), then sweeps the line once more to
-// emit results. Replaces the X / Y loops of ComputeDistanceFieldTransformInPlace
-// (sdfgen.cpp:276-351) and the 1-D transforms (sdfgen.cpp:85-226) for both fields at once; in
-// finalize mode also the combine loop (sdfgen.hpp:85-108) and Lock()'s min/max (sdf.hpp:765-787).
+// Shared pieces of the strided-axis envelope kernel (edt_envelope_inplace.cuh): the site type, the
+// exact pop test, the finalize expression and the order-preserving min/max keys.
 // ================================================================================================
 struct Site
 {
@@ -218,38 +334,6 @@ struct Site
 
 constexpr int32_t kNoSitePosition = 0x7fffffff;
 constexpr int32_t kNoSiteHeight = 0x3fffffff;
-
-template <int kEntryBytes>
-struct EntryCodec;
-
-// Packed entry for lines up to 1024 voxels whose finite inputs stay below 2^22.
-template <>
-struct EntryCodec<4>
-{
-  using Storage = uint32_t;
-  static constexpr int kPositionBits = 10;
-  __device__ static __forceinline__ Storage Pack(int32_t v, int32_t f, int32_t)
-  {
-    return (static_cast<uint32_t>(f) << kPositionBits) | static_cast<uint32_t>(v);
-  }
-  __device__ static __forceinline__ Site Unpack(Storage e)
-  {
-    const int32_t v = static_cast<int32_t>(e & ((1u << kPositionBits) - 1u));
-    const int32_t f = static_cast<int32_t>(e >> kPositionBits);
-    return Site{v, f + v * v};
-  }
-};
-
-template <>
-struct EntryCodec<8>
-{
-  using Storage = int2;
-  __device__ static __forceinline__ Storage Pack(int32_t v, int32_t, int32_t h)
-  {
-    return make_int2(v, h);
-  }
-  __device__ static __forceinline__ Site Unpack(Storage e) { return Site{e.x, e.y}; }
-};
 
 // True when the middle site never owns a point of the lower envelope given its neighbours:
 // crossing(below, middle) >= crossing(middle, above), cross-multiplied (all denominators > 0).
@@ -337,303 +421,6 @@ struct OutputOf<kEmitDouble>
   using Type = double;
   using Key = unsigned long long;
 };
-
-constexpr int kPrefetch = 8;
-
-template <int kEntryBytes, int kMode>
-__global__ void __launch_bounds__(kWarp) EnvelopeAxisKernel(
-    const uint32_t* in, typename OutputOf<kMode>::Type* out, LineFamily family,
-    int lanes_per_tile, FinalizeParams finalize, typename OutputOf<kMode>::Key* min_max_keys)
-{
-  using Codec = EntryCodec<kEntryBytes>;
-  using Entry = typename Codec::Storage;
-  using Out = typename OutputOf<kMode>::Type;
-  extern __shared__ __align__(16) unsigned char envelope_smem[];
-
-  const int lane = threadIdx.x;
-  const int length = family.length;
-  const int num_words = (length + 31) >> 5;
-  Entry* stack = reinterpret_cast<Entry*>(envelope_smem);                  // [length][lanes]
-  uint32_t* class_words = reinterpret_cast<uint32_t*>(stack + static_cast<size_t>(length) * lanes_per_tile);
-
-  const int64_t tiles_per_outer = (family.inner_count + lanes_per_tile - 1) / lanes_per_tile;
-  const int64_t outer = blockIdx.x / tiles_per_outer;
-  const int64_t tile = blockIdx.x - outer * tiles_per_outer;
-  const int64_t column = tile * lanes_per_tile + lane;
-  const bool active = (lane < lanes_per_tile) && (column < family.inner_count);
-  const int64_t first = outer * family.outer_stride + column;
-  const int64_t stride = family.line_stride;
-
-  Out lane_min = PositiveInfinity<Out>();
-  Out lane_max = -PositiveInfinity<Out>();
-
-  if (active)
-  {
-    const uint32_t* src = in + first;
-
-    // ------------------------------------------------------------------ phase 1: build stacks
-    int slot = 0;        // next free stack slot (runs are stored back to back)
-    int depth = 0;       // stored sites of the current run
-    bool has_left = false;
-    Site left_zero{0, 0};  // zero-height site just before the current run
-    Site top{0, 0};
-    Site below{0, 0};
-    uint32_t previous_class = 0;
-    uint32_t word_accumulator = 0;
-
-    const auto pop_hidden = [&](const Site& incoming)
-    {
-      while ((depth >= 2 || (depth == 1 && has_left)) && MiddleIsHidden(below, top, incoming))
-      {
-        depth--;
-        slot--;
-        top = below;
-        if (depth >= 2)
-        {
-          below = Codec::Unpack(stack[static_cast<size_t>(slot - 2) * lanes_per_tile + lane]);
-        }
-        else
-        {
-          below = left_zero;  // only meaningful when depth == 1 && has_left
-        }
-      }
-    };
-
-    uint32_t current[kPrefetch];
-    uint32_t upcoming[kPrefetch];
-#pragma unroll
-    for (int u = 0; u < kPrefetch; u++)
-    {
-      current[u] = (u < length) ? __ldcg(src + static_cast<int64_t>(u) * stride) : 0u;
-    }
-    for (int q0 = 0; q0 < length; q0 += kPrefetch)
-    {
-#pragma unroll
-      for (int u = 0; u < kPrefetch; u++)
-      {
-        const int q = q0 + kPrefetch + u;
-        upcoming[u] = (q < length) ? __ldcg(src + static_cast<int64_t>(q) * stride) : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < kPrefetch; u++)
-      {
-        const int q = q0 + u;
-        if (q < length)
-        {
-          const uint32_t word = current[u];
-          const uint32_t filled = word >> 31;
-          const uint32_t value = word & kNone;
-          word_accumulator |= filled << (q & 31);
-          if ((q & 31) == 31 || q == length - 1)
-          {
-            class_words[static_cast<size_t>(q >> 5) * lanes_per_tile + lane] = word_accumulator;
-            word_accumulator = 0;
-          }
-          if (q > 0 && filled != previous_class)
-          {
-            // The run ends: voxel q is a zero-height site for it. It hides what it hides, but is
-            // not stored (phase 2 re-creates it from the class bits).
-            pop_hidden(Site{q, q * q});
-            depth = 0;
-            has_left = true;
-            left_zero = Site{q - 1, (q - 1) * (q - 1)};
-            top = left_zero;
-          }
-          previous_class = filled;
-          if (value != kNone)
-          {
-            const Site incoming{q, static_cast<int32_t>(value) + q * q};
-            pop_hidden(incoming);
-            stack[static_cast<size_t>(slot) * lanes_per_tile + lane] =
-                Codec::Pack(q, static_cast<int32_t>(value), incoming.h);
-            below = top;
-            top = incoming;
-            depth++;
-            slot++;
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kPrefetch; u++)
-      {
-        current[u] = upcoming[u];
-      }
-    }
-
-    // ------------------------------------------------------------------ phase 2: sweep
-    const int stored_total = slot;
-    int cursor = 0;  // index of the stored site held in `pending`
-    const auto load_stored = [&](int index)
-    {
-      if (index < stored_total)
-      {
-        return Codec::Unpack(stack[static_cast<size_t>(index) * lanes_per_tile + lane]);
-      }
-      return Site{kNoSitePosition, kNoSiteHeight};
-    };
-    Site pending = load_stored(0);
-    Site winner{0, kNoSiteHeight};
-    int run_end = 0;            // first position after the current run
-    bool right_zero_used = true;
-    uint32_t class_word = 0;
-    previous_class = 0;
-
-    int32_t border_yz = 0x7fffffff;
-    if (kMode != kEmitPacked && finalize.add_virtual_border != 0)
-    {
-      const int32_t y = finalize.y_offset + static_cast<int32_t>(column / finalize.nz);
-      const int32_t z = static_cast<int32_t>(column % finalize.nz);
-      if (finalize.ny_total > 1)
-      {
-        border_yz = min(border_yz, min(y + 1, finalize.ny_total - y));
-      }
-      if (finalize.nz_total > 1)
-      {
-        border_yz = min(border_yz, min(z + 1, finalize.nz_total - z));
-      }
-    }
-
-    Out* dst = out + first;
-    for (int q = 0; q < length; q++)
-    {
-      if ((q & 31) == 0)
-      {
-        class_word = class_words[static_cast<size_t>(q >> 5) * lanes_per_tile + lane];
-      }
-      const uint32_t filled = (class_word >> (q & 31)) & 1u;
-      if (q == 0 || filled != previous_class)
-      {
-        // A run starts at q: find where it ends from the class bits.
-        int w = q >> 5;
-        uint32_t different = (filled ? ~class_word : class_word) & (0xffffffffu << (q & 31));
-        while (different == 0 && ++w < num_words)
-        {
-          const uint32_t bits = class_words[static_cast<size_t>(w) * lanes_per_tile + lane];
-          different = filled ? ~bits : bits;
-        }
-        run_end = different ? min(length, (w << 5) + __ffs(different) - 1) : length;
-        // Drop stored sites of earlier runs that the sweep never reached.
-        while (pending.v < q)
-        {
-          cursor++;
-          pending = load_stored(cursor);
-        }
-        right_zero_used = (run_end >= length);
-        if (q > 0)
-        {
-          winner = Site{q - 1, (q - 1) * (q - 1)};
-        }
-        else if (pending.v < run_end)
-        {
-          winner = pending;
-          cursor++;
-          pending = load_stored(cursor);
-        }
-        else if (!right_zero_used)
-        {
-          winner = Site{run_end, run_end * run_end};
-          right_zero_used = true;
-        }
-        else
-        {
-          winner = Site{0, kNoSiteHeight};
-        }
-      }
-      previous_class = filled;
-
-      // Advance while the next candidate is strictly lower at q (F-H "while z[k+1] < q").
-      while (true)
-      {
-        Site candidate;
-        bool from_stack = false;
-        if (pending.v < run_end)
-        {
-          candidate = pending;
-          from_stack = true;
-        }
-        else if (!right_zero_used)
-        {
-          candidate = Site{run_end, run_end * run_end};
-        }
-        else
-        {
-          break;
-        }
-        const int32_t candidate_value = candidate.h - 2 * candidate.v * q;
-        const int32_t winner_value = winner.h - 2 * winner.v * q;
-        if (winner.h != kNoSiteHeight && !(candidate_value < winner_value))
-        {
-          break;
-        }
-        winner = candidate;
-        if (from_stack)
-        {
-          cursor++;
-          pending = load_stored(cursor);
-        }
-        else
-        {
-          right_zero_used = true;
-        }
-      }
-
-      uint32_t squared = kNone;
-      if (winner.h != kNoSiteHeight)
-      {
-        squared = static_cast<uint32_t>(winner.h - 2 * winner.v * q + q * q);
-      }
-
-      if constexpr (kMode == kEmitPacked)
-      {
-        reinterpret_cast<uint32_t*>(dst)[static_cast<int64_t>(q) * stride] =
-            (filled << 31) | squared;
-      }
-      else
-      {
-        if (finalize.add_virtual_border)
-        {
-          int32_t border = border_yz;
-          if (finalize.nx_total > 1)
-          {
-            border = min(border, min(q + 1, finalize.nx_total - q));
-          }
-          if (border != 0x7fffffff)
-          {
-            squared = min(squared, static_cast<uint32_t>(border * border));
-          }
-        }
-        const Out value = SignedDistanceOf<Out>(filled, squared, finalize.resolution);
-        dst[static_cast<int64_t>(q) * stride] = value;
-        lane_min = (value < lane_min) ? value : lane_min;
-        lane_max = (value > lane_max) ? value : lane_max;
-      }
-    }
-  }
-
-  if constexpr (kMode != kEmitPacked)
-  {
-    if (min_max_keys == nullptr)
-    {
-      return;
-    }
-    using Key = typename OutputOf<kMode>::Key;
-    Key key_min = OrderedKey(lane_min);
-    Key key_max = OrderedKey(lane_max);
-#pragma unroll
-    for (int offset = 16; offset > 0; offset >>= 1)
-    {
-      const Key other_min = __shfl_xor_sync(0xffffffffu, key_min, offset);
-      const Key other_max = __shfl_xor_sync(0xffffffffu, key_max, offset);
-      key_min = (other_min < key_min) ? other_min : key_min;
-      key_max = (other_max > key_max) ? other_max : key_max;
-    }
-    if (lane == 0)
-    {
-      atomicMin(min_max_keys + 0, key_min);
-      atomicMax(min_max_keys + 1, key_max);
-    }
-  }
-}
 
 // Decodes the ordered keys back into values (one thread).
 template <typename Out, typename Key>

@@ -3,7 +3,7 @@
 // edt_envelope_inplace.cuh (the fast envelope kernel). DESIGN.md has the roofline of each kernel.
 #include <cmath>
 #include <cstring>
-#include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "edt_device.cuh"
@@ -15,59 +15,7 @@ namespace edt
 {
 namespace
 {
-constexpr size_t kMaxDynamicSmem = 227 * 1024;
-
 inline int64_t Square(int64_t v) { return v * v; }
-
-// ------------------------------------------------------------------------------------------------
-// Stream-ordered scratch. The default memory pool keeps freed blocks (release threshold raised
-// once per device), so steady-state calls do not touch the OS allocator.
-// ------------------------------------------------------------------------------------------------
-void KeepPoolMemory(int device)
-{
-  static std::once_flag flags[64];
-  if (device < 0 || device >= 64)
-  {
-    return;
-  }
-  std::call_once(flags[device], [device]()
-  {
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
-    {
-      unsigned long long threshold = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-    }
-    cudaGetLastError();
-  });
-}
-
-template <typename T>
-class StreamScratch
-{
-public:
-  StreamScratch() = default;
-  StreamScratch(const StreamScratch&) = delete;
-  StreamScratch& operator=(const StreamScratch&) = delete;
-  ~StreamScratch()
-  {
-    if (ptr_ != nullptr)
-    {
-      cudaFreeAsync(ptr_, stream_);
-    }
-  }
-  cudaError_t Allocate(int64_t count, cudaStream_t stream)
-  {
-    stream_ = stream;
-    return cudaMallocAsync(reinterpret_cast<void**>(&ptr_), sizeof(T) * static_cast<size_t>(count),
-                           stream);
-  }
-  T* get() const { return ptr_; }
-
-private:
-  T* ptr_ = nullptr;
-  cudaStream_t stream_ = nullptr;
-};
 
 // ------------------------------------------------------------------------------------------------
 // Kernel launchers
@@ -79,6 +27,21 @@ int LaunchScan(const In* d_in, uint32_t* d_out, int64_t num_lines, int32_t lengt
   const int num_words = (length + 31) >> 5;
   const size_t smem = sizeof(uint32_t) * 5 * num_words * kScanWarpsPerBlock;
   const int64_t blocks = (num_lines + kScanWarpsPerBlock - 1) / kScanWarpsPerBlock;
+  // 128-bit path: every line must start 16-byte aligned in both buffers.
+  using Source = typename std::conditional<std::is_same<In, float>::value, Float4Source,
+                                           Uchar4Source>::type;
+  const bool aligned = (length % 4 == 0)
+      && (reinterpret_cast<uintptr_t>(d_in) % sizeof(typename Source::Vector) == 0)
+      && (reinterpret_cast<uintptr_t>(d_out) % sizeof(uint4) == 0);
+  if (aligned)
+  {
+    ScanContiguousAxisVec4Kernel<Source>
+        <<<static_cast<unsigned>(blocks), kScanWarpsPerBlock * kWarp, smem, stream>>>(
+            reinterpret_cast<const typename Source::Vector*>(d_in),
+            reinterpret_cast<uint4*>(d_out), num_lines, length, unknown_is_filled);
+    VGT_CUDA_TRY(cudaGetLastError(), "ScanContiguousAxisVec4Kernel launch");
+    return VGT_B200_OK;
+  }
   ScanContiguousAxisKernel<In><<<static_cast<unsigned>(blocks), kScanWarpsPerBlock * kWarp, smem,
                                  stream>>>(d_in, d_out, num_lines, length, unknown_is_filled);
   VGT_CUDA_TRY(cudaGetLastError(), "ScanContiguousAxisKernel launch");

@@ -462,6 +462,7 @@ int vgt_b200_voxelize_f64(
   }
   ScopedDevice scoped(device);
   VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+  KeepPoolMemory(device);
   const auto start_time = std::chrono::steady_clock::now();
   const int64_t num_voxels = nx * ny * nz;
   const GridFrame grid = MakeFrame(nx, ny, nz, voxel_size);
@@ -473,11 +474,12 @@ int vgt_b200_voxelize_f64(
     ~StreamGuard() { cudaStreamDestroy(s); }
   } guard{stream};
 
-  DeviceBuffer<int32_t> d_counts;
-  DeviceBuffer<float> d_occupancy;
-  VGT_CUDA_TRY(d_counts.Allocate(2 * num_voxels * (num_clouds > 0 ? num_clouds : 1)),
-               "cudaMalloc tracking grids");
-  VGT_CUDA_TRY(d_occupancy.Allocate(num_voxels), "cudaMalloc occupancy");
+  // Stream-ordered pool allocations: steady-state calls reuse the same blocks.
+  StreamScratch<int32_t> d_counts;
+  StreamScratch<float> d_occupancy;
+  VGT_CUDA_TRY(d_counts.Allocate(2 * num_voxels * (num_clouds > 0 ? num_clouds : 1), stream),
+               "tracking grid allocation");
+  VGT_CUDA_TRY(d_occupancy.Allocate(num_voxels, stream), "occupancy allocation");
   VGT_CUDA_TRY(cudaMemsetAsync(d_counts.get(), 0,
                                sizeof(int32_t) * 2 * num_voxels * (num_clouds > 0 ? num_clouds : 1),
                                stream),
@@ -490,8 +492,11 @@ int vgt_b200_voxelize_f64(
   {
     max_points = (clouds[c].num_points > max_points) ? clouds[c].num_points : max_points;
   }
-  DeviceBuffer<double> d_points;
-  VGT_CUDA_TRY(d_points.Allocate(3 * max_points), "cudaMalloc points");
+  StreamScratch<double> d_points;
+  if (max_points > 0)
+  {
+    VGT_CUDA_TRY(d_points.Allocate(3 * max_points, stream), "points allocation");
+  }
   for (int32_t c = 0; c < num_clouds; c++)
   {
     if (clouds[c].num_points == 0)
