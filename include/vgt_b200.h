@@ -152,7 +152,9 @@ VGT_B200_API int vgt_b200_edt_local_passes_dev(
 
 /* Fused compute + exchange: the same two passes, but the y pass stores part h of every line
  * straight into rank h's receive buffer through peer-mapped device pointers (NVLink stores), so
- * the kernel IS the all-to-all (the reference has no counterpart: SURVEY.md section 2.2).
+ * the kernel IS the all-to-all (the reference has no counterpart: SURVEY.md section 2.2). The
+ * passes are the Z and Y loops of ComputeDistanceFieldTransformInPlace
+ * (src/.../signed_distance_field_generation.cpp:315-390) on this rank's x-slab.
  *   peer_receive_buffers  host array of num_ranks device addresses, entry h = base of rank h's
  *                         receive buffer laid out [nx_total][rows_h][nz] (rows_h = rank h's share
  *                         of ny), mapped into this process (CUDA IPC / symmetric memory);
@@ -164,6 +166,9 @@ VGT_B200_API int vgt_b200_edt_local_passes_scatter_dev(
     int num_ranks, int64_t x_offset, const uint64_t* peer_receive_buffers, int device,
     void* stream);
 
+/* The remaining X pass (signed_distance_field_generation.cpp:276-312) fused with the combine loop
+ * and Lock() (signed_distance_field_generation.hpp:85-111) on this rank's y-slab after the
+ * exchange. d_in is destroyed. */
 VGT_B200_API int vgt_b200_edt_final_pass_f32_dev(
     int32_t* d_in, int64_t nx, int64_t ny_local, int64_t nz, int64_t y_offset,
     int64_t ny_total, double resolution, int add_virtual_border, int device, float* d_sdf_out,
