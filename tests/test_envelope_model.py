@@ -1,5 +1,6 @@
-"""CPU: a pure-Python model of the line algorithm the CUDA envelope kernel runs
-(voxelized_geometry_tools_b200/csrc/edt_envelope_inplace.cuh), checked against brute force.
+"""CPU: pure-Python models of the line algorithm the CUDA envelope kernels run
+(voxelized_geometry_tools_b200/csrc/edt_envelope_inplace.cuh and edt_envelope_lean.cuh), checked
+against brute force.
 
 The kernel cannot run without a GPU, but its algorithm can: this model mirrors the kernel's two
 phases statement by statement (same stack discipline, same integer pop test, same class-bit run
@@ -101,6 +102,117 @@ def kernel_line(classes, values):
     return out
 
 
+FAR_ZERO_SITE = 46341 + 1024
+BLOCKED_HEIGHT = 0x5FFFFFFF
+ABSENT_POSITION = 0x7FFF
+
+
+def lean_line(classes, values):
+    """Model of EnvelopeAxisLeanKernel (csrc/edt_envelope_lean.cuh): one pop loop in phase 1 (the
+    incoming site at a class change is the boundary's zero site), the per-word run-end table,
+    and a phase 2 that walks only stored sites and takes the right zero site as a min()."""
+    n = len(classes)
+    num_words = (n + 31) // 32
+    rows = [None] * n
+    class_words = [0] * num_words
+    run_end_after = [None] * num_words
+    slot = entries = 0
+    left_v = -1
+    top = below = (0, 0)
+    accumulator = 0
+    previous = classes[0]
+
+    for q in range(n):
+        filled, value = classes[q], values[q]
+        change = filled != previous
+        previous = filled
+        accumulator = (accumulator >> 1) | (filled << 31)
+        # pre-filter: keep the site only if it is strictly below the segment between its two
+        # neighbour sites (a neighbour of the other class is a zero site); NONE never filters
+        before = 0 if change else (values[q - 1] if q > 0 else NONE)
+        if q + 1 < n:
+            after = 0 if classes[q + 1] != filled else values[q + 1]
+        else:
+            after = NONE
+        on_hull_locally = 2 * value - 2 - before < after
+        finite = value != NONE and (on_hull_locally or q == 0)
+        own = (q, value + q * q)
+        incoming = (q, q * q) if change else own
+        if change or finite:
+            while entries >= 2 and hidden(below, top, incoming):
+                entries -= 1
+                slot -= 1
+                top = below
+                if entries >= 2:
+                    if entries == 2 and left_v >= 0:
+                        below = (left_v, left_v * left_v)
+                    else:
+                        below = rows[slot - 2]
+        if change:
+            for w in range((left_v + 1) >> 5, q >> 5):
+                run_end_after[w] = q
+            left_v = q - 1
+            top = (left_v, left_v * left_v)
+            entries = 1
+        if finite:
+            assert slot <= q
+            rows[slot] = own
+            slot += 1
+            below, top = top, own
+            entries += 1
+        if (q & 31) == 31:
+            class_words[q >> 5] = accumulator
+    if n & 31:
+        # arithmetic shift: the class of the last row repeats past the end of the line
+        sign = accumulator >> 31
+        shift = 32 - (n & 31)
+        word = accumulator >> shift
+        if sign:
+            word |= (0xFFFFFFFF << (32 - shift)) & 0xFFFFFFFF
+        class_words[num_words - 1] = word
+    for w in range((left_v + 1) >> 5, num_words):
+        run_end_after[w] = n
+    stored_total = slot
+
+    cursor = 0
+
+    def load_pending():
+        return rows[cursor] if cursor < stored_total else (ABSENT_POSITION, NO_HEIGHT)
+
+    pending = load_pending()
+    winner = (0, NO_HEIGHT)
+    candidate_h = BLOCKED_HEIGHT
+    right_v = FAR_ZERO_SITE
+    run_end = 0
+    previous = 0
+    out = [0] * n
+    for q in range(n):
+        w, b = q >> 5, q & 31
+        word = class_words[w]
+        filled = (word >> b) & 1
+        if filled != previous or q == 0:
+            different = ((~word if filled else word) & 0xFFFFFFFF) >> b
+            if different:
+                run_end = min(n, q + (different & -different).bit_length() - 1)
+            else:
+                run_end = run_end_after[w]
+            while pending[0] < q:
+                cursor += 1
+                pending = load_pending()
+            winner = (q - 1, (q - 1) ** 2) if q > 0 else (0, NO_HEIGHT)
+            right_v = run_end if run_end < n else FAR_ZERO_SITE
+            candidate_h = pending[1] if pending[0] < run_end else BLOCKED_HEIGHT
+            previous = filled
+        while candidate_h - 2 * pending[0] * q < winner[1] - 2 * winner[0] * q:
+            winner = (pending[0], candidate_h)
+            cursor += 1
+            pending = load_pending()
+            candidate_h = pending[1] if pending[0] < run_end else BLOCKED_HEIGHT
+        squared = NONE if winner[1] == NO_HEIGHT else winner[1] - 2 * winner[0] * q + q * q
+        out[q] = min(squared, (right_v - q) ** 2, NONE)
+    return out
+
+
 def brute_line(classes, values):
     n = len(classes)
     out = []
@@ -140,9 +252,11 @@ def random_line(rng, n):
 def test_kernel_line_model_matches_brute_force():
     rng = random.Random(1)
     for _ in range(6000):
-        n = rng.choice([1, 2, 3, 31, 32, 33, 40, 64, 65, 97])
+        n = rng.choice([1, 2, 3, 4, 5, 7, 31, 32, 33, 36, 40, 64, 65, 97])
         classes, values = random_line(rng, n)
-        assert kernel_line(classes, values) == brute_line(classes, values), (classes, values)
+        want = brute_line(classes, values)
+        assert kernel_line(classes, values) == want, (classes, values)
+        assert lean_line(classes, values) == want, (classes, values)
 
 
 def test_smooth_distance_like_lines():
@@ -154,3 +268,4 @@ def test_smooth_distance_like_lines():
         classes = [1 if abs(i - n / 3) < 4 else 0 for i in range(n)]
         values = [int((i - centre) ** 2) + offset for i in range(n)]
         assert kernel_line(classes, values) == brute_line(classes, values)
+        assert lean_line(classes, values) == brute_line(classes, values)

@@ -1,0 +1,486 @@
+// The strided-axis envelope kernel for axes of at most 1024 voxels (sm_100a).
+// Included by edt_kernels.cu after edt_device.cuh.
+//
+// Same algorithm and data layout as EnvelopeAxisInPlaceStackKernel (edt_envelope_inplace.cuh):
+// one lane owns one line, a warp owns 32 z-adjacent lines (every row access of the warp is one
+// 128-byte segment), the Felzenszwalb-Huttenlocher stack of a line lives IN PLACE in the rows of
+// the line that were already consumed, packed (f << 10 | v). What differs is the instruction
+// budget. The round-1 profile showed that kernel bound by issued instructions (~280 warp
+// instructions per row of 32 voxels), a third of them in branches taken by 1-4 lanes (run
+// boundaries, sweep advances) and another third in fixed per-row bookkeeping. Here:
+//   * every address is one IMAD.WIDE.U32 (32-bit row index x 32-bit byte stride + 64-bit base);
+//   * phase 1 has ONE pop loop: at a class change the incoming site is the zero-height site of
+//     the boundary, otherwise the voxel's own site; the change-only work is a short branch;
+//   * phase 1 records, per 32-row word, where the run covering the end of that word ends, so
+//     phase 2 finds the end of a run with one bit scan or one table read instead of a search;
+//   * phase 2 takes the zero site right of the run as a min() in the output expression, so the
+//     sweep only ever walks stored sites and the advance body is a load and a decode;
+//   * phase 2 walks word by word (class word in a register, no per-row shared-memory logic);
+//   * when (largest h) x (length) < 2^31 the pop test is done in 32-bit arithmetic;
+//   * send-layout output and the virtual border are template flags, out of the common path.
+//
+// Replaces the X / Y loops of ComputeDistanceFieldTransformInPlace (sdfgen.cpp:276-351) and the
+// 1-D transforms (sdfgen.cpp:85-226) for both fields at once; in finalize mode also the combine
+// loop (sdfgen.hpp:85-108) and Lock()'s min/max (sdf.hpp:765-787).
+//
+// The input buffer is destroyed; the output must be a different buffer.
+#pragma once
+
+#include "edt_device.cuh"
+#include "edt_envelope_inplace.cuh"
+
+namespace vgt_b200
+{
+namespace edt
+{
+namespace
+{
+// crossing(below, middle) >= crossing(middle, above), cross-multiplied; see MiddleIsHidden.
+template <bool kNarrow>
+__device__ __forceinline__ bool HiddenTest(int32_t below_v, int32_t below_h, int32_t middle_v,
+                                           int32_t middle_h, int32_t above_v, int32_t above_h)
+{
+  if constexpr (kNarrow)
+  {
+    // |h differences| * (position differences) < 2^31 is guaranteed by the launcher.
+    return (middle_h - below_h) * (above_v - middle_v) >= (above_h - middle_h) * (middle_v - below_v);
+  }
+  else
+  {
+    return static_cast<long long>(middle_h - below_h) * static_cast<long long>(above_v - middle_v)
+        >= static_cast<long long>(above_h - middle_h) * static_cast<long long>(middle_v - below_v);
+  }
+}
+
+// 32-bit global load under a predicate (0 when not taken) without a branch: the compiler turns
+// `if (take) e = *p;` inside the divergent pop / advance loops into a BSSY / BRA / BSYNC
+// sandwich that costs more issue slots than the load itself.
+__device__ __forceinline__ uint32_t LoadStackEntryIf(bool take, const uint32_t* address)
+{
+  uint32_t value;
+  asm volatile(
+      "{\n"
+      "  .reg .pred take;\n"
+      "  setp.ne.u32 take, %2, 0;\n"
+      "  mov.u32 %0, 0;\n"
+      "  @take ld.global.u32 %0, [%1];\n"
+      "}\n"
+      : "=r"(value)
+      : "l"(address), "r"(static_cast<uint32_t>(take))
+      : "memory");
+  return value;
+}
+
+// Shared memory per warp: class words [num_words][32] (uint32) followed by the run-end table
+// [num_words][32] (uint16): entry w of a lane = first row after the end of word w whose class
+// differs from the class of the word's last row (`length` when there is none).
+__host__ __device__ inline size_t LeanSharedBytesPerWarp(int length)
+{
+  const int num_words = (length + 31) >> 5;
+  return static_cast<size_t>(num_words) * kWarp * (sizeof(uint32_t) + sizeof(uint16_t));
+}
+
+// A zero site that is "not there": far enough that its squared distance is >= kNone for every
+// q < 1024, near enough that the square still fits 32 bits.
+constexpr int32_t kFarZeroSite = 46341 + kInPlaceMaxLength;
+// Height of a stored site that must not be taken (it belongs to a later run): above
+// kNoSiteHeight even after the -2*v*q term, so it never beats an absent winner.
+constexpr int32_t kBlockedHeight = 0x5fffffff;
+// Position of "no stored site left": above every row index, small enough that the -2*v*q term
+// of the comparison cannot overflow or pull kBlockedHeight below kNoSiteHeight.
+constexpr int32_t kAbsentPosition = 0x7fff;
+
+template <int kMode, bool kNarrow, bool kSend, bool kBorder>
+__global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPacked) ? 16 : 12)
+    EnvelopeAxisLeanKernel(uint32_t* in, typename OutputOf<kMode>::Type* out, LineFamily family,
+                           FinalizeParams finalize, typename OutputOf<kMode>::Key* min_max_keys)
+{
+  using Out = typename OutputOf<kMode>::Type;
+  extern __shared__ uint32_t lean_smem[];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int length = family.length;
+  const int num_words = (length + 31) >> 5;
+  // (uint32 words + uint16 table) of one warp = 6 bytes * num_words * 32: a multiple of 4.
+  // Both arrays are indexed [word][lane]; the pointers below already include the lane.
+  uint32_t* const class_words =
+      lean_smem + static_cast<size_t>(warp) * (LeanSharedBytesPerWarp(length) / sizeof(uint32_t))
+      + lane;
+  uint16_t* const run_end_after =
+      reinterpret_cast<uint16_t*>(class_words - lane + static_cast<size_t>(num_words) * kWarp)
+      + lane;
+
+  const int64_t tiles_per_outer = (family.inner_count + kWarp - 1) / kWarp;
+  const int64_t tile_index = static_cast<int64_t>(blockIdx.x) * kLineWarpsPerBlock + warp;
+  if (tile_index >= tiles_per_outer * family.num_outer)
+  {
+    return;  // warp-uniform
+  }
+  const int64_t outer = tile_index / tiles_per_outer;
+  const int64_t tile = tile_index - outer * tiles_per_outer;
+  const int64_t column = tile * kWarp + lane;
+  const bool active = column < family.inner_count;
+  const int64_t first = outer * family.outer_stride + column;
+  const uint32_t stride_bytes = static_cast<uint32_t>(family.line_stride) * 4u;
+
+  Out lane_min = PositiveInfinity<Out>();
+  Out lane_max = -PositiveInfinity<Out>();
+
+  if (active)
+  {
+    char* const line = reinterpret_cast<char*>(in + first);
+    const auto row_address = [&](uint32_t row)
+    {
+      return reinterpret_cast<uint32_t*>(line + static_cast<uint64_t>(row) * stride_bytes);
+    };
+
+    // ------------------------------------------------------------------ phase 1: build stacks
+    // Entries of the current run: [implicit zero site left of the run (if any)] + stored sites.
+    uint32_t slot = 0;    // stored sites of the whole line so far == next free row
+    int entries = 0;      // entries of the current run, the implicit left site included
+    int32_t left_v = -1;  // position of the zero site left of the run; -1: the run starts the line
+    int32_t top_v = 0, top_h = 0, below_v = 0, below_h = 0;
+    uint32_t word_accumulator = 0;
+
+    // next_word: the word of row q + 1, or kNone with the class of `word` when there is none
+    // (or it is not known yet), which disables the pre-filter below for this row.
+    const auto process_row = [&](const int q, const uint32_t word, uint32_t& previous_word,
+                                 const uint32_t next_word)
+    {
+      const uint32_t value = word & kNone;
+      const bool change = static_cast<int32_t>(word ^ previous_word) < 0;
+      // Pre-filter: a site that lies on or above the segment between its two neighbour sites
+      // g(q-1), g(q+1) (g = f + v^2; a neighbour of the other class is a zero site, f = 0) is not
+      // a vertex of the lower hull, so pushing it would only make the next row pop it again.
+      // About 40 % of the sites of a distance-like field go this way. kNone neighbours make
+      // the signed comparison fail, so they never filter.
+      const int32_t before = change ? 0 : static_cast<int32_t>(previous_word & kNone);
+      const int32_t after = (static_cast<int32_t>(word ^ next_word) < 0)
+          ? 0 : static_cast<int32_t>(next_word & kNone);
+      const bool on_hull_locally = 2 * static_cast<int32_t>(value) - 2 - before < after;
+      previous_word = word;
+      // bit b of the accumulator after 32 rows = class of row 32w + b
+      word_accumulator = (word_accumulator >> 1) | (word & kClassBit);
+      const bool finite = (value != kNone) && (on_hull_locally || q == 0);
+      const int32_t qq = q * q;
+      const int32_t own_h = static_cast<int32_t>(value) + qq;
+      // The site that arrives at this row: the zero-height site that closes the run at a class
+      // change (it hides what it hides but is never stored: phase 2 re-creates it from the class
+      // bits), else the voxel's own site.
+      const int32_t incoming_h = change ? qq : own_h;
+      if (change || finite)
+      {
+        while (entries >= 2 && HiddenTest<kNarrow>(below_v, below_h, top_v, top_h, q, incoming_h))
+        {
+          entries--;
+          slot--;
+          top_v = below_v;
+          top_h = below_h;
+          if (entries >= 2)
+          {
+            const bool from_left = (entries == 2) && (left_v >= 0);
+            const uint32_t e = LoadStackEntryIf(!from_left, row_address(slot - 2));
+            const int32_t v = static_cast<int32_t>(e & (kInPlaceMaxLength - 1));
+            const int32_t site_v = from_left ? left_v : v;
+            below_v = site_v;
+            below_h = static_cast<int32_t>(e >> kInPlacePositionBits) + site_v * site_v;
+          }
+        }
+      }
+      if (change)
+      {
+        // words whose last row the closed run covers: the run that covers them ends at q
+#pragma unroll 1
+        for (int w = (left_v + 1) >> 5; w < (q >> 5); w++)
+        {
+          run_end_after[w * kWarp] = static_cast<uint16_t>(q);
+        }
+        left_v = q - 1;
+        top_v = left_v;
+        top_h = left_v * left_v;
+        entries = 1;
+      }
+      if (finite)
+      {
+        // (after a change the run holds one entry, so no pop test is due for the own site)
+        *row_address(slot) = (value << kInPlacePositionBits) | static_cast<uint32_t>(q);
+        slot++;
+        below_v = top_v;
+        below_h = top_h;
+        top_v = q;
+        top_h = own_h;
+        entries++;
+      }
+    };
+
+    {
+      constexpr int kBatch = 2;
+      uint32_t next_rows[kBatch];
+      const int full = length & ~(kBatch - 1);
+      if (full > 0)
+      {
+#pragma unroll
+        for (int u = 0; u < kBatch; u++)
+        {
+          next_rows[u] = __ldcs(row_address(static_cast<uint32_t>(u)));
+        }
+      }
+      // the first row never is a class change
+      uint32_t previous_word = (full > 0) ? next_rows[0] : __ldcs(row_address(0));
+      int q0 = 0;
+      for (; q0 < full; q0 += kBatch)
+      {
+        uint32_t rows[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; u++)
+        {
+          rows[u] = next_rows[u];
+        }
+        if (q0 + kBatch < full)
+        {
+          // prefetch the next batch: its rows are above every slot this batch can write
+#pragma unroll
+          for (int u = 0; u < kBatch; u++)
+          {
+            next_rows[u] = __ldcs(row_address(static_cast<uint32_t>(q0 + kBatch + u)));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; u++)
+        {
+          // after the last full batch next_rows still holds this batch: no filtering there
+          const uint32_t next_word = (u + 1 < kBatch)
+              ? rows[u + 1]
+              : ((q0 + kBatch < full) ? next_rows[0] : (rows[u] | kNone));
+          process_row(q0 + u, rows[u], previous_word, next_word);
+        }
+        if ((q0 & 31) == 32 - kBatch)
+        {
+          class_words[(q0 >> 5) * kWarp] = word_accumulator;
+        }
+      }
+#pragma unroll 1
+      for (int q = q0; q < length; q++)
+      {
+        const uint32_t word = __ldcs(row_address(static_cast<uint32_t>(q)));
+        process_row(q, word, previous_word, word | kNone);
+        if ((q & 31) == 31)
+        {
+          class_words[(q >> 5) * kWarp] = word_accumulator;
+        }
+      }
+      if ((length & 31) != 0)
+      {
+        // align the partial last word; the arithmetic shift repeats the class of the last row
+        // in the bits past the end of the line, so they never read as a class change
+        class_words[(num_words - 1) * kWarp] = static_cast<uint32_t>(
+            static_cast<int32_t>(word_accumulator) >> (32 - (length & 31)));
+      }
+#pragma unroll 1
+      for (int w = (left_v + 1) >> 5; w < num_words; w++)
+      {
+        run_end_after[w * kWarp] = static_cast<uint16_t>(length);
+      }
+    }
+
+    // ------------------------------------------------------------------ phase 2: sweep
+    // Per run: the winner starts as the zero site left of the run, the sweep walks the run's
+    // stored sites, and the zero site right of the run enters as a min() at the output.
+    const uint32_t stored_total = slot;
+    uint32_t cursor = 0;
+    int32_t pending_v = kAbsentPosition;  // the next stored site, decoded
+    int32_t pending_h = kNoSiteHeight;
+    // The entry after the pending one is already in flight (raw), so an advance never waits for
+    // memory unless two advances follow each other closely. Entries written in phase 1 have
+    // mostly left L2 by now (all tiles of the grid are in flight at once).
+    uint32_t following_raw = LoadStackEntryIf(1u < stored_total, row_address(1));
+    const auto decode_pending = [&](const uint32_t e, const bool present)
+    {
+      const int32_t v = static_cast<int32_t>(e & (kInPlaceMaxLength - 1));
+      pending_v = present ? v : kAbsentPosition;
+      pending_h = static_cast<int32_t>(e >> kInPlacePositionBits) + v * v;  // unused when absent
+    };
+    decode_pending(LoadStackEntryIf(0u < stored_total, row_address(0)), 0u < stored_total);
+    const auto load_pending = [&]()
+    {
+      // cursor was just incremented: the pending entry is the one that was in flight
+      decode_pending(following_raw, cursor < stored_total);
+      following_raw = LoadStackEntryIf(cursor + 1 < stored_total, row_address(cursor + 1));
+    };
+    int32_t winner_v = 0, winner_h = kNoSiteHeight;
+    int32_t candidate_h = kBlockedHeight;  // pending_h if the pending site is in this run
+    int32_t right_v = kFarZeroSite;
+    int run_end = 0;
+
+    int32_t border_yz = 0x7fffffff;
+    if constexpr (kBorder)
+    {
+      const int32_t y = finalize.y_offset + static_cast<int32_t>(column / finalize.nz);
+      const int32_t z = static_cast<int32_t>(column % finalize.nz);
+      if (finalize.ny_total > 1)
+      {
+        border_yz = min(border_yz, min(y + 1, finalize.ny_total - y));
+      }
+      if (finalize.nz_total > 1)
+      {
+        border_yz = min(border_yz, min(z + 1, finalize.nz_total - z));
+      }
+    }
+
+    // Output row pointer. In send layout it jumps at part boundaries, which are the same for
+    // every lane, so that check is warp-uniform.
+    char* write_at = reinterpret_cast<char*>(out + first);
+    const uint32_t out_stride_bytes =
+        static_cast<uint32_t>(family.line_stride) * static_cast<uint32_t>(sizeof(Out));
+    int next_part_start = 0;
+    uint32_t previous_class = 0;
+    int q = 0;
+    for (int w = 0; w < num_words; w++)
+    {
+      const uint32_t class_word = class_words[w * kWarp];
+      const int word_rows = min(32, length - (w << 5));
+      for (int b = 0; b < word_rows; b++, q++)
+      {
+        if constexpr (kSend)
+        {
+          if (q == next_part_start)
+          {
+            // Part h covers rows [y0, y0 + rows); its block starts at inner * num_outer * y0.
+            const int wide = family.out_base + 1;
+            const int wide_rows = family.out_extra * wide;
+            int y0;
+            int rows;
+            if (q < wide_rows)
+            {
+              y0 = (q / wide) * wide;
+              rows = wide;
+            }
+            else
+            {
+              y0 = wide_rows + ((q - wide_rows) / family.out_base) * family.out_base;
+              rows = family.out_base;
+            }
+            next_part_start = y0 + rows;
+            Out* part_row;
+            if (family.scatter_base[0] != nullptr)
+            {
+              // this part goes straight to its owner's receive buffer over NVLink
+              const int part = (q < wide_rows)
+                  ? (q / wide)
+                  : (family.out_extra + (q - wide_rows) / family.out_base);
+              // (selected with compares: indexing the kernel-parameter array with a register
+              // would force a local-memory copy of the whole parameter struct)
+              uint32_t* base = family.scatter_base[0];
+#pragma unroll
+              for (int i = 1; i < 8; i++)
+              {
+                base = (part == i) ? family.scatter_base[i] : base;
+              }
+              part_row = reinterpret_cast<Out*>(base)
+                  + family.inner_count * ((family.scatter_row_offset + outer) * rows + (q - y0))
+                  + column;
+            }
+            else
+            {
+              part_row = out + family.inner_count * (family.num_outer * y0 + outer * rows + (q - y0))
+                  + column;
+            }
+            write_at = reinterpret_cast<char*>(part_row);
+          }
+        }
+        const uint32_t filled = (class_word >> b) & 1u;
+        if (filled != previous_class || q == 0)
+        {
+          // A run starts at q. Its end: the next opposite-class bit of this word, else the table.
+          const uint32_t different = (filled ? ~class_word : class_word) >> b;
+          run_end = different ? min(length, q + __ffs(different) - 1)
+                              : static_cast<int>(run_end_after[w * kWarp]);
+          // Drop stored sites of earlier runs that the sweep never reached.
+          while (pending_v < q)
+          {
+            cursor++;
+            load_pending();
+          }
+          winner_v = (q > 0) ? q - 1 : 0;
+          winner_h = (q > 0) ? (q - 1) * (q - 1) : kNoSiteHeight;
+          right_v = (run_end < length) ? run_end : kFarZeroSite;
+          candidate_h = (pending_v < run_end) ? pending_h : kBlockedHeight;
+          previous_class = filled;
+        }
+
+        // Advance while the next stored site of the run is strictly lower at q (F-H
+        // "while z[k+1] < q"). An absent winner carries kNoSiteHeight and loses to any real
+        // site; a site of a later run carries kBlockedHeight and never wins.
+        const int32_t minus_two_q = -2 * q;
+        while (candidate_h + pending_v * minus_two_q < winner_h + winner_v * minus_two_q)
+        {
+          winner_v = pending_v;
+          winner_h = candidate_h;
+          cursor++;
+          load_pending();
+          candidate_h = (pending_v < run_end) ? pending_h : kBlockedHeight;
+        }
+
+        // squared distance: the stored / left winner, or the zero site right of the run
+        uint32_t squared = (winner_h != kNoSiteHeight)
+            ? static_cast<uint32_t>(winner_h + winner_v * minus_two_q + q * q)
+            : kNone;
+        const uint32_t to_right = static_cast<uint32_t>(right_v - q);
+        squared = min(min(squared, to_right * to_right), kNone);
+
+        if constexpr (kMode == kEmitPacked)
+        {
+          __stcs(reinterpret_cast<uint32_t*>(write_at), (filled << 31) | squared);
+        }
+        else
+        {
+          if constexpr (kBorder)
+          {
+            int32_t border = border_yz;
+            if (finalize.nx_total > 1)
+            {
+              border = min(border, min(q + 1, finalize.nx_total - q));
+            }
+            if (border != 0x7fffffff)
+            {
+              squared = min(squared, static_cast<uint32_t>(border * border));
+            }
+          }
+          const Out value = SignedDistanceOf<Out>(filled, squared, finalize.resolution);
+          __stcs(reinterpret_cast<Out*>(write_at), value);
+          lane_min = (value < lane_min) ? value : lane_min;
+          lane_max = (value > lane_max) ? value : lane_max;
+        }
+        write_at += out_stride_bytes;
+      }
+    }
+  }
+
+  if constexpr (kMode != kEmitPacked)
+  {
+    if (min_max_keys == nullptr)
+    {
+      return;
+    }
+    using Key = typename OutputOf<kMode>::Key;
+    Key key_min = OrderedKey(lane_min);
+    Key key_max = OrderedKey(lane_max);
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1)
+    {
+      const Key other_min = __shfl_xor_sync(0xffffffffu, key_min, offset);
+      const Key other_max = __shfl_xor_sync(0xffffffffu, key_max, offset);
+      key_min = (other_min < key_min) ? other_min : key_min;
+      key_max = (other_max > key_max) ? other_max : key_max;
+    }
+    if (lane == 0)
+    {
+      atomicMin(min_max_keys + 0, key_min);
+      atomicMax(min_max_keys + 1, key_max);
+    }
+  }
+}
+}  // namespace
+}  // namespace edt
+}  // namespace vgt_b200

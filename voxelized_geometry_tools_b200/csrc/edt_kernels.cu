@@ -2,12 +2,14 @@
 // Device code: edt_device.cuh (z scan, shared-memory envelope fallback, finalize helpers) and
 // edt_envelope_inplace.cuh (the fast envelope kernel). DESIGN.md has the roofline of each kernel.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
 #include "edt_device.cuh"
 #include "edt_envelope_inplace.cuh"
+#include "edt_envelope_lean.cuh"
 
 namespace vgt_b200
 {
@@ -75,6 +77,69 @@ int LaunchEnvelopeInPlaceStack(uint32_t* d_in, typename OutputOf<kMode>::Type* d
   return VGT_B200_OK;
 }
 
+template <int kMode, bool kNarrow, bool kSend, bool kBorder>
+int LaunchEnvelopeLeanKernel(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
+                             const LineFamily& family, const FinalizeParams& finalize,
+                             typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
+{
+  const size_t smem = LeanSharedBytesPerWarp(family.length) * kLineWarpsPerBlock;
+  const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
+  const int64_t blocks = (tiles + kLineWarpsPerBlock - 1) / kLineWarpsPerBlock;
+  if (blocks > 0x7fffffffLL)
+  {
+    return FailInvalid("grid too large for one launch");
+  }
+  auto kernel = EnvelopeAxisLeanKernel<kMode, kNarrow, kSend, kBorder>;
+  kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, smem, stream>>>(
+      d_in, d_out, family, finalize, d_keys);
+  VGT_CUDA_TRY(cudaGetLastError(), "EnvelopeAxisLeanKernel launch");
+  return VGT_B200_OK;
+}
+
+// Send-layout output exists only for the packed intermediate, the virtual border only for the
+// finalizing pass, so each mode instantiates two of the four flag combinations.
+template <int kMode, bool kNarrow>
+int LaunchEnvelopeLean(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
+                       const LineFamily& family, const FinalizeParams& finalize,
+                       typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
+{
+  if constexpr (kMode == kEmitPacked)
+  {
+    if (family.out_parts > 0)
+    {
+      return LaunchEnvelopeLeanKernel<kMode, kNarrow, true, false>(d_in, d_out, family, finalize,
+                                                                   d_keys, stream);
+    }
+    return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, false>(d_in, d_out, family, finalize,
+                                                                  d_keys, stream);
+  }
+  else
+  {
+    if (family.out_parts > 0)
+    {
+      return FailInvalid("send layout is only available for the packed intermediate");
+    }
+    if (finalize.add_virtual_border != 0)
+    {
+      return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, true>(d_in, d_out, family, finalize,
+                                                                   d_keys, stream);
+    }
+    return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, false>(d_in, d_out, family, finalize,
+                                                                  d_keys, stream);
+  }
+}
+
+// Debug / A-B switch: VGT_B200_ENVELOPE=inplace forces the round-1 kernel.
+inline bool LeanEnvelopeEnabled()
+{
+  static const bool enabled = []()
+  {
+    const char* choice = std::getenv("VGT_B200_ENVELOPE");
+    return choice == nullptr || std::strcmp(choice, "inplace") != 0;
+  }();
+  return enabled;
+}
+
 // One strided-axis pass. d_in is DESTROYED and must not alias d_out.
 // max_input: largest finite partial squared distance the pass can see. Short axes use packed
 // 32-bit stack entries; longer ones keep the site positions in a stream-ordered uint16 side array
@@ -84,6 +149,17 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
                    const LineFamily& family, int64_t max_input, const FinalizeParams& finalize,
                    typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
 {
+  if (family.length <= kInPlaceMaxLength && max_input <= kInPlaceMaxInput
+      && family.line_stride * 4 <= 0xffffffffLL && LeanEnvelopeEnabled())
+  {
+    // 32-bit pop test when no product of an h difference and a position difference can overflow.
+    const int64_t max_h = max_input + Square(family.length - 1);
+    if (max_h * family.length < (int64_t{1} << 31))
+    {
+      return LaunchEnvelopeLean<kMode, true>(d_in, d_out, family, finalize, d_keys, stream);
+    }
+    return LaunchEnvelopeLean<kMode, false>(d_in, d_out, family, finalize, d_keys, stream);
+  }
   if (family.length <= kInPlaceMaxLength && max_input <= kInPlaceMaxInput)
   {
     return LaunchEnvelopeInPlaceStack<kMode, false>(d_in, d_out, nullptr, family, finalize,
