@@ -52,25 +52,6 @@ __device__ __forceinline__ bool HiddenTest(int32_t below_v, int32_t below_h, int
   }
 }
 
-// 32-bit global load under a predicate (0 when not taken) without a branch: the compiler turns
-// `if (take) e = *p;` inside the divergent pop / advance loops into a BSSY / BRA / BSYNC
-// sandwich that costs more issue slots than the load itself.
-__device__ __forceinline__ uint32_t LoadStackEntryIf(bool take, const uint32_t* address)
-{
-  uint32_t value;
-  asm volatile(
-      "{\n"
-      "  .reg .pred take;\n"
-      "  setp.ne.u32 take, %2, 0;\n"
-      "  mov.u32 %0, 0;\n"
-      "  @take ld.global.u32 %0, [%1];\n"
-      "}\n"
-      : "=r"(value)
-      : "l"(address), "r"(static_cast<uint32_t>(take))
-      : "memory");
-  return value;
-}
-
 // Shared memory per warp: class words [num_words][32] (uint32) followed by the run-end table
 // [num_words][32] (uint16): entry w of a lane = first row after the end of word w whose class
 // differs from the class of the word's last row (`length` when there is none).
@@ -177,15 +158,15 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
           slot--;
           top_v = below_v;
           top_h = below_h;
-          if (entries >= 2)
-          {
-            const bool from_left = (entries == 2) && (left_v >= 0);
-            const uint32_t e = LoadStackEntryIf(!from_left, row_address(slot - 2));
-            const int32_t v = static_cast<int32_t>(e & (kInPlaceMaxLength - 1));
-            const int32_t site_v = from_left ? left_v : v;
-            below_v = site_v;
-            below_h = static_cast<int32_t>(e >> kInPlacePositionBits) + site_v * site_v;
-          }
+          // The entry under the new top: the implicit left site when the run holds one stored
+          // site, else stored entry slot - 2. The load is unconditional (clamped to row 0 when
+          // there is nothing to read): a branch around it costs more than the spare load.
+          const uint32_t e = *row_address(static_cast<uint32_t>(max(static_cast<int32_t>(slot) - 2, 0)));
+          const bool from_left = (entries == 2) && (left_v >= 0);
+          const int32_t site_v = from_left ? left_v : static_cast<int32_t>(e & (kInPlaceMaxLength - 1));
+          const int32_t site_f = from_left ? 0 : static_cast<int32_t>(e >> kInPlacePositionBits);
+          below_v = site_v;
+          below_h = site_f + site_v * site_v;
         }
       }
       if (change)
@@ -294,19 +275,21 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
     // The entry after the pending one is already in flight (raw), so an advance never waits for
     // memory unless two advances follow each other closely. Entries written in phase 1 have
     // mostly left L2 by now (all tiles of the grid are in flight at once).
-    uint32_t following_raw = LoadStackEntryIf(1u < stored_total, row_address(1));
+    const uint32_t last_row = static_cast<uint32_t>(length - 1);
+    uint32_t following_raw = *row_address(min(1u, last_row));
     const auto decode_pending = [&](const uint32_t e, const bool present)
     {
       const int32_t v = static_cast<int32_t>(e & (kInPlaceMaxLength - 1));
       pending_v = present ? v : kAbsentPosition;
       pending_h = static_cast<int32_t>(e >> kInPlacePositionBits) + v * v;  // unused when absent
     };
-    decode_pending(LoadStackEntryIf(0u < stored_total, row_address(0)), 0u < stored_total);
+    decode_pending(*row_address(0), 0u < stored_total);
     const auto load_pending = [&]()
     {
       // cursor was just incremented: the pending entry is the one that was in flight
       decode_pending(following_raw, cursor < stored_total);
-      following_raw = LoadStackEntryIf(cursor + 1 < stored_total, row_address(cursor + 1));
+      // (unconditional, clamped to the line: a branch around the load costs more than the load)
+      following_raw = *row_address(min(cursor + 1, last_row));
     };
     int32_t winner_v = 0, winner_h = kNoSiteHeight;
     int32_t candidate_h = kBlockedHeight;  // pending_h if the pending site is in this run
