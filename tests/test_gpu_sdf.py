@@ -179,6 +179,16 @@ def test_full_size_512_properties_and_parity(shared_library, oracle):
     assert sdf.GetMinimumMaximum() == (lo, hi)
 
 
+def test_pipelined_host_entry_odd_shape(shared_library, oracle):
+    # >= 2^24 voxels: the host entry overlaps the slab copies with the passes (x-slabs in,
+    # y-slabs out as strided 2-D copies). Odd extents so that no slab boundary is aligned.
+    rng = np.random.default_rng(37)
+    occupancy = random_occupancy(rng, (70, 515, 470), 0.05, blobs=True)
+    assert occupancy.size >= 2 ** 24
+    assert_matches_oracle(oracle, occupancy, 0.03)
+    assert_matches_oracle(oracle, occupancy, 0.03, add_virtual_border=True, dtype=np.float64)
+
+
 def test_axes_longer_than_1024_and_large_distances(shared_library, oracle):
     # > 1024 voxels along an axis (or partial distances >= 2^21) switches the envelope kernel to
     # split stack entries (value in place, position in a uint16 side array).

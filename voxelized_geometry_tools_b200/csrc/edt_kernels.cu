@@ -370,6 +370,166 @@ struct StreamGuard
   }
 };
 
+struct EventGuard
+{
+  cudaEvent_t event = nullptr;
+  ~EventGuard()
+  {
+    if (event != nullptr)
+    {
+      cudaEventDestroy(event);
+    }
+  }
+};
+
+// Grids above this size go through the pipelined host path (copies overlapped with the passes).
+constexpr int64_t kPipelineMinVoxels = int64_t{1} << 24;
+constexpr int kPipelineChunks = 8;
+
+// x envelope + finalize on the column range [y0 * nz, y1 * nz) of a FULL grid [nx, ny, nz] (line
+// stride ny * nz): the y-chunked final pass of the pipelined host path. Keys are reset / decoded
+// by the caller. d_packed is destroyed in that range.
+template <int kMode>
+int RunFinalPassColumns(uint32_t* d_packed, int64_t nx, int64_t ny, int64_t nz, int64_t y0,
+                        int64_t y1, double resolution, int add_virtual_border,
+                        typename OutputOf<kMode>::Type* d_out,
+                        typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
+{
+  FinalizeParams finalize{};
+  finalize.resolution = resolution;
+  finalize.add_virtual_border = add_virtual_border;
+  finalize.nx_total = static_cast<int32_t>(nx);
+  finalize.ny_total = static_cast<int32_t>(ny);
+  finalize.nz_total = static_cast<int32_t>(nz);
+  finalize.y_offset = static_cast<int32_t>(y0);
+  finalize.nz = static_cast<int32_t>(nz);
+  const LineFamily family{1, 0, (y1 - y0) * nz, ny * nz, static_cast<int32_t>(nx)};
+  return LaunchEnvelope<kMode>(d_packed + y0 * nz, d_out + y0 * nz, family,
+                               Square(nz - 1) + Square(ny - 1), finalize, d_keys, stream);
+}
+
+// Host-pointer entry for large grids: the input arrives in x-slabs, and the z and y passes of a
+// slab (independent per x) run while the next slab is still on the bus; the x pass + finalize
+// runs in y-slabs, each copied back (a strided 2-D copy) while the next one is computed. PCIe
+// stays busy from the first byte in to the last byte out; only one slab of compute is exposed
+// at either end.
+template <typename In, int kMode>
+int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, double resolution,
+                         int unknown_is_filled, int add_virtual_border,
+                         typename OutputOf<kMode>::Type* h_out,
+                         typename OutputOf<kMode>::Type* out_min,
+                         typename OutputOf<kMode>::Type* out_max)
+{
+  using Out = typename OutputOf<kMode>::Type;
+  using Key = typename OutputOf<kMode>::Key;
+  const int64_t count = nx * ny * nz;
+  const int64_t plane = ny * nz;
+  StreamGuard compute, copy_in, copy_out;
+  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&compute.stream, cudaStreamNonBlocking), "stream");
+  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&copy_in.stream, cudaStreamNonBlocking), "stream");
+  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&copy_out.stream, cudaStreamNonBlocking), "stream");
+  StreamScratch<In> d_in;
+  StreamScratch<Out> d_out;
+  StreamScratch<uint32_t> scratch;
+  StreamScratch<Out> d_min_max;
+  StreamScratch<Key> keys;
+  VGT_CUDA_TRY(d_in.Allocate(count, compute.stream), "input grid allocation");
+  VGT_CUDA_TRY(d_out.Allocate(count, compute.stream), "SDF allocation");
+  VGT_CUDA_TRY(scratch.Allocate(count, compute.stream), "SDF scratch allocation");
+  VGT_CUDA_TRY(d_min_max.Allocate(2, compute.stream), "min/max allocation");
+  VGT_CUDA_TRY(keys.Allocate(2, compute.stream), "min/max scratch");
+  ResetMinMaxKeysKernel<Key><<<1, 1, 0, compute.stream>>>(keys.get());
+  EventGuard allocated;
+  VGT_CUDA_TRY(cudaEventCreateWithFlags(&allocated.event, cudaEventDisableTiming), "event");
+  VGT_CUDA_TRY(cudaEventRecord(allocated.event, compute.stream), "event record");
+  VGT_CUDA_TRY(cudaStreamWaitEvent(copy_in.stream, allocated.event, 0), "stream wait");
+  VGT_CUDA_TRY(cudaStreamWaitEvent(copy_out.stream, allocated.event, 0), "stream wait");
+
+  uint32_t* const d_front = reinterpret_cast<uint32_t*>(d_out.get());
+  const int in_chunks = static_cast<int>(nx < kPipelineChunks ? nx : kPipelineChunks);
+  EventGuard arrived[kPipelineChunks];
+  int status = VGT_B200_OK;
+  for (int c = 0; c < in_chunks && status == VGT_B200_OK; c++)
+  {
+    const int64_t x0 = nx * c / in_chunks;
+    const int64_t x1 = nx * (c + 1) / in_chunks;
+    VGT_CUDA_TRY(cudaMemcpyAsync(d_in.get() + x0 * plane, h_in + x0 * plane,
+                                 sizeof(In) * (x1 - x0) * plane, cudaMemcpyHostToDevice,
+                                 copy_in.stream),
+                 "copy grid slab to device");
+    VGT_CUDA_TRY(cudaEventCreateWithFlags(&arrived[c].event, cudaEventDisableTiming), "event");
+    VGT_CUDA_TRY(cudaEventRecord(arrived[c].event, copy_in.stream), "event record");
+    VGT_CUDA_TRY(cudaStreamWaitEvent(compute.stream, arrived[c].event, 0), "stream wait");
+    // z scan into the front buffer, y envelope into the scratch (or z scan straight into the
+    // scratch when there is no y axis): after this the packed field of the slab is in `scratch`.
+    if (ny <= 1)
+    {
+      status = LaunchScan<In>(d_in.get() + x0 * plane, scratch.get() + x0 * plane,
+                              (x1 - x0) * ny, static_cast<int32_t>(nz), unknown_is_filled,
+                              compute.stream);
+    }
+    else
+    {
+      status = LaunchScan<In>(d_in.get() + x0 * plane, d_front + x0 * plane, (x1 - x0) * ny,
+                              static_cast<int32_t>(nz), unknown_is_filled, compute.stream);
+      if (status == VGT_B200_OK)
+      {
+        status = LaunchEnvelope<kEmitPacked>(d_front + x0 * plane, scratch.get() + x0 * plane,
+                                             FamilyAlongY(x1 - x0, ny, nz), Square(nz - 1),
+                                             FinalizeParams{}, nullptr, compute.stream);
+      }
+    }
+  }
+  const int out_chunks = static_cast<int>(ny < kPipelineChunks ? ny : kPipelineChunks);
+  EventGuard finished[kPipelineChunks];
+  for (int c = 0; c < out_chunks && status == VGT_B200_OK; c++)
+  {
+    const int64_t y0 = ny * c / out_chunks;
+    const int64_t y1 = ny * (c + 1) / out_chunks;
+    status = RunFinalPassColumns<kMode>(scratch.get(), nx, ny, nz, y0, y1, resolution,
+                                        add_virtual_border, d_out.get(), keys.get(),
+                                        compute.stream);
+    if (status != VGT_B200_OK)
+    {
+      break;
+    }
+    VGT_CUDA_TRY(cudaEventCreateWithFlags(&finished[c].event, cudaEventDisableTiming), "event");
+    VGT_CUDA_TRY(cudaEventRecord(finished[c].event, compute.stream), "event record");
+    VGT_CUDA_TRY(cudaStreamWaitEvent(copy_out.stream, finished[c].event, 0), "stream wait");
+    VGT_CUDA_TRY(cudaMemcpy2DAsync(h_out + y0 * nz, sizeof(Out) * plane, d_out.get() + y0 * nz,
+                                   sizeof(Out) * plane, sizeof(Out) * (y1 - y0) * nz,
+                                   static_cast<size_t>(nx), cudaMemcpyDeviceToHost,
+                                   copy_out.stream),
+                 "copy SDF slab to host");
+  }
+  Out min_max[2];
+  if (status == VGT_B200_OK)
+  {
+    DecodeMinMaxKernel<Out, Key><<<1, 1, 0, compute.stream>>>(keys.get(), d_min_max.get());
+    cudaMemcpyAsync(min_max, d_min_max.get(), sizeof(Out) * 2, cudaMemcpyDeviceToHost,
+                    compute.stream);
+  }
+  const cudaError_t sync_in = cudaStreamSynchronize(copy_in.stream);
+  const cudaError_t sync_compute = cudaStreamSynchronize(compute.stream);
+  const cudaError_t sync_out = cudaStreamSynchronize(copy_out.stream);
+  if (status != VGT_B200_OK)
+  {
+    return status;
+  }
+  VGT_CUDA_TRY(sync_in, "copy grid to device");
+  VGT_CUDA_TRY(sync_compute, "SDF generation");
+  VGT_CUDA_TRY(sync_out, "copy SDF to host");
+  if (out_min != nullptr)
+  {
+    *out_min = min_max[0];
+  }
+  if (out_max != nullptr)
+  {
+    *out_max = min_max[1];
+  }
+  return VGT_B200_OK;
+}
+
 // Host-pointer entry: allocate, copy in, run, copy out, synchronise.
 template <typename In, int kMode>
 int SdfFromHost(const In* h_in, int64_t nx, int64_t ny, int64_t nz, double resolution,
@@ -387,6 +547,11 @@ int SdfFromHost(const In* h_in, int64_t nx, int64_t ny, int64_t nz, double resol
   VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
   KeepPoolMemory(device);
   const int64_t count = nx * ny * nz;
+  if (count >= kPipelineMinVoxels && nx > 1)
+  {
+    return SdfFromHostPipelined<In, kMode>(h_in, nx, ny, nz, resolution, unknown_is_filled,
+                                           add_virtual_border, h_out, out_min, out_max);
+  }
   StreamGuard guard;
   VGT_CUDA_TRY(cudaStreamCreateWithFlags(&guard.stream, cudaStreamNonBlocking),
                "cudaStreamCreate");
