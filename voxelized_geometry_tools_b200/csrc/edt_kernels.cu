@@ -10,6 +10,7 @@
 #include "edt_device.cuh"
 #include "edt_envelope_inplace.cuh"
 #include "edt_envelope_lean.cuh"
+#include "edt_scan_registers.cuh"
 
 namespace vgt_b200
 {
@@ -35,6 +36,34 @@ int LaunchScan(const In* d_in, uint32_t* d_out, int64_t num_lines, int32_t lengt
   const bool aligned = (length % 4 == 0)
       && (reinterpret_cast<uintptr_t>(d_in) % sizeof(typename Source::Vector) == 0)
       && (reinterpret_cast<uintptr_t>(d_out) % sizeof(uint4) == 0);
+  if (aligned && length <= 1024)
+  {
+    // whole line in registers: 1, 2, 4 or 8 iterations of 128 voxels
+    const auto launch = [&](auto kernel)
+    {
+      kernel<<<static_cast<unsigned>(blocks), kScanWarpsPerBlock * kWarp, 0, stream>>>(
+          reinterpret_cast<const typename Source::Vector*>(d_in), reinterpret_cast<uint4*>(d_out),
+          num_lines, length, unknown_is_filled);
+    };
+    if (length <= 128)
+    {
+      launch(ScanContiguousAxisRegistersKernel<Source, 1>);
+    }
+    else if (length <= 256)
+    {
+      launch(ScanContiguousAxisRegistersKernel<Source, 2>);
+    }
+    else if (length <= 512)
+    {
+      launch(ScanContiguousAxisRegistersKernel<Source, 4>);
+    }
+    else
+    {
+      launch(ScanContiguousAxisRegistersKernel<Source, 8>);
+    }
+    VGT_CUDA_TRY(cudaGetLastError(), "ScanContiguousAxisRegistersKernel launch");
+    return VGT_B200_OK;
+  }
   if (aligned)
   {
     ScanContiguousAxisVec4Kernel<Source>
