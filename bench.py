@@ -42,13 +42,21 @@ SDF_BYTES_PER_VOXEL = 24           # 3 passes x (4 B in + 4 B out), SURVEY.md se
 PASS_BYTES_PER_VOXEL = 8
 KERNELS_PER_STEP = 5               # scan, y envelope, key reset, x envelope + finalize, key decode
 CPU_SAMPLE_DIMS = (256, 256, 256)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-# capture of this very workload (profiles/r1_ncu_kernels.txt); None for anything not captured.
-NCU_DRAM_BYTES_PER_LAUNCH = {
-    ((512, 512, 512), "ScanContiguousAxisKernel (z)"): 536.9e6 + 479.6e6,
-    ((512, 512, 512), "EnvelopeAxisKernel (y)"): 712.9e6 + 577.5e6,
-    ((512, 512, 512), "EnvelopeAxisKernel (x + finalize)"): 852.9e6 + 679.4e6,
-}
+PASS_NAMES = ["ScanContiguousAxisRegistersKernel (z)", "EnvelopeAxisLeanKernel (y)",
+              "EnvelopeAxisLeanKernel (x + finalize)"]
+NCU_TRAFFIC_FILE = REPO / "profiles" / "ncu_traffic.json"
+
+
+def ncu_dram_bytes_per_launch(dims, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
+    `ncu --set full` capture of this very workload (profiles/ncu_traffic.json, written by
+    profiles/ncu_traffic.py from the .ncu-rep); None for anything not captured."""
+    try:
+        table = json.loads(NCU_TRAFFIC_FILE.read_text())
+        entry = table["x".join(map(str, dims))][kernel]
+        return float(entry["dram_bytes_read"]) + float(entry["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def workload_dims(n_gpus: int):
@@ -251,17 +259,20 @@ def run_ours(args):
     roofline = None
     if pass_ms is not None:
         dominant = max(range(3), key=lambda i: pass_ms[i])
-        names = ["ScanContiguousAxisKernel (z)", "EnvelopeAxisKernel (y)",
-                 "EnvelopeAxisKernel (x + finalize)"]
+        names = PASS_NAMES
         achieved = PASS_BYTES_PER_VOXEL * voxels / (pass_ms[dominant] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": names[dominant], "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((tuple(dims), names[dominant])),
-                    "traffic_source": "profiles/r1_ncu_kernels.txt (ncu --set full, same workload)",
+                    "traffic": ncu_dram_bytes_per_launch(dims, names[dominant]),
+                    "traffic_source": "profiles/ncu_traffic.json (ncu --set full, same workload)",
                     "peak_kind": peak_kind,
                     "algorithmic_bytes_per_launch": PASS_BYTES_PER_VOXEL * voxels,
                     "pass_ms": {"z_scan": pass_ms[0], "y_envelope": pass_ms[1],
                                 "x_envelope_finalize": pass_ms[2]},
+                    "pass_frac_of_peak": {
+                        name: PASS_BYTES_PER_VOXEL * voxels / (ms * 1e-3) / 1e9 / peak
+                        for name, ms in zip(("z_scan", "y_envelope", "x_envelope_finalize"),
+                                            pass_ms)},
                     "whole_sdf": {"achieved": SDF_BYTES_PER_VOXEL * voxels / (ms_per_step * 1e-3) / 1e9,
                                   "frac": SDF_BYTES_PER_VOXEL * voxels / (ms_per_step * 1e-3) / 1e9
                                   / (peak * n_gpus),

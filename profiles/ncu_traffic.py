@@ -1,0 +1,40 @@
+#!/usr/bin/env python3
+"""Writes profiles/ncu_traffic.json (per-launch DRAM bytes of the three SDF kernels) from an
+`ncu --set full` report of `profiles/run_sdf_once.py <n>`: ncu_traffic.py <report.ncu-rep> <n>"""
+import csv
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+report, n = sys.argv[1], int(sys.argv[2])
+raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True,
+                     text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+header, units = rows[0], rows[1]
+scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def value(row, name):
+    i = header.index(name)
+    return float(row[i]) * scale[units[i]]
+
+
+labels = {"ScanContiguousAxis": "ScanContiguousAxisRegistersKernel (z)",
+          "EnvelopeAxisLeanKernel<0": "EnvelopeAxisLeanKernel (y)",
+          "EnvelopeAxisLeanKernel<1": "EnvelopeAxisLeanKernel (x + finalize)"}
+out = {}
+for row in rows[2:]:
+    name = row[header.index("Kernel Name")]
+    for key, label in labels.items():
+        if key in name and label not in out:
+            out[label] = {"dram_bytes_read": value(row, "dram__bytes_read.sum"),
+                          "dram_bytes_write": value(row, "dram__bytes_write.sum"),
+                          "gpu_time_ms_under_ncu": float(row[header.index("gpu__time_duration.sum")])
+                          * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[units[header.index("gpu__time_duration.sum")]],
+                          "report": Path(report).name}
+path = Path(__file__).resolve().parent / "ncu_traffic.json"
+table = json.loads(path.read_text()) if path.exists() else {}
+table[f"{n}x{n}x{n}"] = out
+path.write_text(json.dumps(table, indent=1) + "\n")
+print(json.dumps(out, indent=1))

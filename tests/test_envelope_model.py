@@ -102,9 +102,9 @@ def kernel_line(classes, values):
     return out
 
 
-FAR_ZERO_SITE = 46341 + 1024
+FAR_ZERO_SITE = 46341 + 8192
 BLOCKED_HEIGHT = 0x5FFFFFFF
-ABSENT_POSITION = 0x7FFF
+ABSENT_POSITION = 0x4000
 
 
 def lean_line(classes, values):

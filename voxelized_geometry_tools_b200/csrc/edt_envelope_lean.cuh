@@ -1,10 +1,13 @@
-// The strided-axis envelope kernel for axes of at most 1024 voxels (sm_100a).
+// The strided-axis envelope kernel (sm_100a): axes up to 8192 voxels.
 // Included by edt_kernels.cu after edt_device.cuh.
 //
 // Same algorithm and data layout as EnvelopeAxisInPlaceStackKernel (edt_envelope_inplace.cuh):
 // one lane owns one line, a warp owns 32 z-adjacent lines (every row access of the warp is one
 // 128-byte segment), the Felzenszwalb-Huttenlocher stack of a line lives IN PLACE in the rows of
-// the line that were already consumed, packed (f << 10 | v). What differs is the instruction
+// the line that were already consumed. Axes of at most 1024 voxels whose partial distances stay
+// below 2^21 pack an entry into the row itself (f << 10 | v); longer axes / larger distances keep
+// f in the row and v in a uint16 side array addressed exactly like the grid (kSplit, 2 more
+// bytes per voxel of scratch). What differs is the instruction
 // budget. The round-1 profile showed that kernel bound by issued instructions (~280 warp
 // instructions per row of 32 voxels), a third of them in branches taken by 1-4 lanes (run
 // boundaries, sweep advances) and another third in fixed per-row bookkeeping. Here:
@@ -52,45 +55,46 @@ __device__ __forceinline__ bool HiddenTest(int32_t below_v, int32_t below_h, int
   }
 }
 
-// Shared memory per warp: class words [num_words][32] (uint32) followed by the run-end table
-// [num_words][32] (uint16): entry w of a lane = first row after the end of word w whose class
-// differs from the class of the word's last row (`length` when there is none).
-__host__ __device__ inline size_t LeanSharedBytesPerWarp(int length)
+// Per-launch scratch in global memory (no shared memory at all, so occupancy is set by registers
+// only and the whole L1 serves the stack accesses): class words [num_words][lines] (uint32, bit b
+// of word w of a line = class of row 32 w + b) followed by the run-end table [num_words][lines]
+// (uint16): entry w of a line = first row after the end of word w whose class differs from the
+// class of the word's last row (`length` when there is none). A warp reads / writes 32 adjacent
+// lines of one word: one 128-byte (64-byte) segment per 32 rows.
+__host__ __device__ inline size_t LeanScratchBytes(int length, int64_t lines)
 {
-  const int num_words = (length + 31) >> 5;
-  return static_cast<size_t>(num_words) * kWarp * (sizeof(uint32_t) + sizeof(uint16_t));
+  const int64_t num_words = (length + 31) >> 5;
+  return static_cast<size_t>(num_words * lines) * (sizeof(uint32_t) + sizeof(uint16_t));
 }
 
 // A zero site that is "not there": far enough that its squared distance is >= kNone for every
-// q < 1024, near enough that the square still fits 32 bits.
-constexpr int32_t kFarZeroSite = 46341 + kInPlaceMaxLength;
+// q < 8192, near enough that the square still fits 32 bits.
+constexpr int32_t kFarZeroSite = 46341 + VGT_B200_MAX_AXIS;
 // Height of a stored site that must not be taken (it belongs to a later run): above
 // kNoSiteHeight even after the -2*v*q term, so it never beats an absent winner.
 constexpr int32_t kBlockedHeight = 0x5fffffff;
 // Position of "no stored site left": above every row index, small enough that the -2*v*q term
 // of the comparison cannot overflow or pull kBlockedHeight below kNoSiteHeight.
-constexpr int32_t kAbsentPosition = 0x7fff;
+constexpr int32_t kAbsentPosition = 0x4000;
 
-template <int kMode, bool kNarrow, bool kSend, bool kBorder>
+// A stored site as read back from the stack: position and f (h = f + v * v).
+struct StackEntry
+{
+  int32_t v;
+  int32_t f;
+};
+
+template <int kMode, bool kNarrow, bool kSend, bool kBorder, bool kSplit>
 __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPacked) ? 16 : 12)
-    EnvelopeAxisLeanKernel(uint32_t* in, typename OutputOf<kMode>::Type* out, LineFamily family,
-                           FinalizeParams finalize, typename OutputOf<kMode>::Key* min_max_keys)
+    EnvelopeAxisLeanKernel(uint32_t* in, typename OutputOf<kMode>::Type* out, uint16_t* positions,
+                           uint32_t* class_scratch, LineFamily family, FinalizeParams finalize,
+                           typename OutputOf<kMode>::Key* min_max_keys)
 {
   using Out = typename OutputOf<kMode>::Type;
-  extern __shared__ uint32_t lean_smem[];
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int length = family.length;
   const int num_words = (length + 31) >> 5;
-  // (uint32 words + uint16 table) of one warp = 6 bytes * num_words * 32: a multiple of 4.
-  // Both arrays are indexed [word][lane]; the pointers below already include the lane.
-  uint32_t* const class_words =
-      lean_smem + static_cast<size_t>(warp) * (LeanSharedBytesPerWarp(length) / sizeof(uint32_t))
-      + lane;
-  uint16_t* const run_end_after =
-      reinterpret_cast<uint16_t*>(class_words - lane + static_cast<size_t>(num_words) * kWarp)
-      + lane;
 
   const int64_t tiles_per_outer = (family.inner_count + kWarp - 1) / kWarp;
   const int64_t tile_index = static_cast<int64_t>(blockIdx.x) * kLineWarpsPerBlock + warp;
@@ -104,6 +108,21 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
   const bool active = column < family.inner_count;
   const int64_t first = outer * family.outer_stride + column;
   const uint32_t stride_bytes = static_cast<uint32_t>(family.line_stride) * 4u;
+  // scratch of this line: class word w at class_words + w * lines, table entry w likewise
+  const int64_t lines = family.num_outer * family.inner_count;
+  const uint32_t word_stride_bytes = static_cast<uint32_t>(lines) * 4u;
+  char* const class_words =
+      reinterpret_cast<char*>(class_scratch + outer * family.inner_count + column);
+  const auto class_word_address = [&](uint32_t w)
+  {
+    return reinterpret_cast<uint32_t*>(class_words + static_cast<uint64_t>(w) * word_stride_bytes);
+  };
+  const auto run_end_address = [&](uint32_t w)
+  {
+    char* const table = reinterpret_cast<char*>(class_scratch + static_cast<int64_t>(num_words) * lines)
+        + 2 * (outer * family.inner_count + column);
+    return reinterpret_cast<uint16_t*>(table + static_cast<uint64_t>(w) * (word_stride_bytes >> 1));
+  };
 
   Out lane_min = PositiveInfinity<Out>();
   Out lane_max = -PositiveInfinity<Out>();
@@ -114,6 +133,39 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
     const auto row_address = [&](uint32_t row)
     {
       return reinterpret_cast<uint32_t*>(line + static_cast<uint64_t>(row) * stride_bytes);
+    };
+    // stack entries: (f << 10 | v) in the row, or f in the row and v in the side array
+    char* const line_positions = kSplit ? reinterpret_cast<char*>(positions + first) : nullptr;
+    const auto position_address = [&](uint32_t row)
+    {
+      return reinterpret_cast<uint16_t*>(line_positions
+                                         + static_cast<uint64_t>(row) * (stride_bytes >> 1));
+    };
+    const auto store_entry = [&](uint32_t at_slot, int32_t v, uint32_t f)
+    {
+      if constexpr (kSplit)
+      {
+        *row_address(at_slot) = f;
+        *position_address(at_slot) = static_cast<uint16_t>(v);
+      }
+      else
+      {
+        *row_address(at_slot) = (f << kInPlacePositionBits) | static_cast<uint32_t>(v);
+      }
+    };
+    const auto load_entry = [&](uint32_t at_slot)
+    {
+      const uint32_t e = *row_address(at_slot);
+      if constexpr (kSplit)
+      {
+        return StackEntry{static_cast<int32_t>(*position_address(at_slot)),
+                          static_cast<int32_t>(e)};
+      }
+      else
+      {
+        return StackEntry{static_cast<int32_t>(e & (kInPlaceMaxLength - 1)),
+                          static_cast<int32_t>(e >> kInPlacePositionBits)};
+      }
     };
 
     // ------------------------------------------------------------------ phase 1: build stacks
@@ -161,10 +213,11 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
           // The entry under the new top: the implicit left site when the run holds one stored
           // site, else stored entry slot - 2. The load is unconditional (clamped to row 0 when
           // there is nothing to read): a branch around it costs more than the spare load.
-          const uint32_t e = *row_address(static_cast<uint32_t>(max(static_cast<int32_t>(slot) - 2, 0)));
+          const StackEntry e =
+              load_entry(static_cast<uint32_t>(max(static_cast<int32_t>(slot) - 2, 0)));
           const bool from_left = (entries == 2) && (left_v >= 0);
-          const int32_t site_v = from_left ? left_v : static_cast<int32_t>(e & (kInPlaceMaxLength - 1));
-          const int32_t site_f = from_left ? 0 : static_cast<int32_t>(e >> kInPlacePositionBits);
+          const int32_t site_v = from_left ? left_v : e.v;
+          const int32_t site_f = from_left ? 0 : e.f;
           below_v = site_v;
           below_h = site_f + site_v * site_v;
         }
@@ -175,7 +228,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
 #pragma unroll 1
         for (int w = (left_v + 1) >> 5; w < (q >> 5); w++)
         {
-          run_end_after[w * kWarp] = static_cast<uint16_t>(q);
+          *run_end_address(static_cast<uint32_t>(w)) = static_cast<uint16_t>(q);
         }
         left_v = q - 1;
         top_v = left_v;
@@ -185,7 +238,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
       if (finite)
       {
         // (after a change the run holds one entry, so no pop test is due for the own site)
-        *row_address(slot) = (value << kInPlacePositionBits) | static_cast<uint32_t>(q);
+        store_entry(slot, q, value);
         slot++;
         below_v = top_v;
         below_h = top_h;
@@ -238,7 +291,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
         }
         if ((q0 & 31) == 32 - kBatch)
         {
-          class_words[(q0 >> 5) * kWarp] = word_accumulator;
+          __stcs(class_word_address(static_cast<uint32_t>(q0 >> 5)), word_accumulator);
         }
       }
 #pragma unroll 1
@@ -248,20 +301,21 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
         process_row(q, word, previous_word, word | kNone);
         if ((q & 31) == 31)
         {
-          class_words[(q >> 5) * kWarp] = word_accumulator;
+          __stcs(class_word_address(static_cast<uint32_t>(q >> 5)), word_accumulator);
         }
       }
       if ((length & 31) != 0)
       {
         // align the partial last word; the arithmetic shift repeats the class of the last row
         // in the bits past the end of the line, so they never read as a class change
-        class_words[(num_words - 1) * kWarp] = static_cast<uint32_t>(
-            static_cast<int32_t>(word_accumulator) >> (32 - (length & 31)));
+        __stcs(class_word_address(static_cast<uint32_t>(num_words - 1)),
+               static_cast<uint32_t>(static_cast<int32_t>(word_accumulator)
+                                     >> (32 - (length & 31))));
       }
 #pragma unroll 1
       for (int w = (left_v + 1) >> 5; w < num_words; w++)
       {
-        run_end_after[w * kWarp] = static_cast<uint16_t>(length);
+        *run_end_address(static_cast<uint32_t>(w)) = static_cast<uint16_t>(length);
       }
     }
 
@@ -272,24 +326,42 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
     uint32_t cursor = 0;
     int32_t pending_v = kAbsentPosition;  // the next stored site, decoded
     int32_t pending_h = kNoSiteHeight;
-    // The entry after the pending one is already in flight (raw), so an advance never waits for
+    // The entry after the pending one is already in flight, so an advance never waits for
     // memory unless two advances follow each other closely. Entries written in phase 1 have
     // mostly left L2 by now (all tiles of the grid are in flight at once).
     const uint32_t last_row = static_cast<uint32_t>(length - 1);
-    uint32_t following_raw = *row_address(min(1u, last_row));
-    const auto decode_pending = [&](const uint32_t e, const bool present)
+    // (kept undecoded: one register when entries are packed)
+    uint32_t following_word = *row_address(min(1u, last_row));
+    uint32_t following_position = kSplit ? *position_address(min(1u, last_row)) : 0u;
+    const auto decode_entry = [&](const uint32_t word, const uint32_t position)
     {
-      const int32_t v = static_cast<int32_t>(e & (kInPlaceMaxLength - 1));
-      pending_v = present ? v : kAbsentPosition;
-      pending_h = static_cast<int32_t>(e >> kInPlacePositionBits) + v * v;  // unused when absent
+      if constexpr (kSplit)
+      {
+        return StackEntry{static_cast<int32_t>(position), static_cast<int32_t>(word)};
+      }
+      else
+      {
+        return StackEntry{static_cast<int32_t>(word & (kInPlaceMaxLength - 1)),
+                          static_cast<int32_t>(word >> kInPlacePositionBits)};
+      }
     };
-    decode_pending(*row_address(0), 0u < stored_total);
+    const auto decode_pending = [&](const StackEntry e, const bool present)
+    {
+      pending_v = present ? e.v : kAbsentPosition;
+      pending_h = e.f + e.v * e.v;  // unused when absent
+    };
+    decode_pending(load_entry(0), 0u < stored_total);
     const auto load_pending = [&]()
     {
       // cursor was just incremented: the pending entry is the one that was in flight
-      decode_pending(following_raw, cursor < stored_total);
+      decode_pending(decode_entry(following_word, following_position), cursor < stored_total);
       // (unconditional, clamped to the line: a branch around the load costs more than the load)
-      following_raw = *row_address(min(cursor + 1, last_row));
+      const uint32_t row = min(cursor + 1, last_row);
+      following_word = *row_address(row);
+      if constexpr (kSplit)
+      {
+        following_position = *position_address(row);
+      }
     };
     int32_t winner_v = 0, winner_h = kNoSiteHeight;
     int32_t candidate_h = kBlockedHeight;  // pending_h if the pending site is in this run
@@ -319,9 +391,18 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
     int next_part_start = 0;
     uint32_t previous_class = 0;
     int q = 0;
+    // class word and table entry of the next word are loaded one word ahead
+    uint32_t next_class_word = __ldcs(class_word_address(0));
+    uint32_t next_run_end = __ldcs(run_end_address(0));
     for (int w = 0; w < num_words; w++)
     {
-      const uint32_t class_word = class_words[w * kWarp];
+      const uint32_t class_word = next_class_word;
+      const int run_end_after_word = static_cast<int>(next_run_end);
+      {
+        const uint32_t ahead = static_cast<uint32_t>(min(w + 1, num_words - 1));
+        next_class_word = __ldcs(class_word_address(ahead));
+        next_run_end = __ldcs(run_end_address(ahead));
+      }
       const int word_rows = min(32, length - (w << 5));
       for (int b = 0; b < word_rows; b++, q++)
       {
@@ -378,7 +459,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
           // A run starts at q. Its end: the next opposite-class bit of this word, else the table.
           const uint32_t different = (filled ? ~class_word : class_word) >> b;
           run_end = different ? min(length, q + __ffs(different) - 1)
-                              : static_cast<int>(run_end_after[w * kWarp]);
+                              : run_end_after_word;
           // Drop stored sites of earlier runs that the sweep never reached.
           while (pending_v < q)
           {

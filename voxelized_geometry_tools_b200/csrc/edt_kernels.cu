@@ -106,41 +106,48 @@ int LaunchEnvelopeInPlaceStack(uint32_t* d_in, typename OutputOf<kMode>::Type* d
   return VGT_B200_OK;
 }
 
-template <int kMode, bool kNarrow, bool kSend, bool kBorder>
+template <int kMode, bool kNarrow, bool kSend, bool kBorder, bool kSplit>
 int LaunchEnvelopeLeanKernel(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
-                             const LineFamily& family, const FinalizeParams& finalize,
+                             uint16_t* d_positions, const LineFamily& family,
+                             const FinalizeParams& finalize,
                              typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
 {
-  const size_t smem = LeanSharedBytesPerWarp(family.length) * kLineWarpsPerBlock;
   const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
   const int64_t blocks = (tiles + kLineWarpsPerBlock - 1) / kLineWarpsPerBlock;
-  if (blocks > 0x7fffffffLL)
+  const int64_t lines = family.num_outer * family.inner_count;
+  if (blocks > 0x7fffffffLL || lines * 4 > 0xffffffffLL)
   {
     return FailInvalid("grid too large for one launch");
   }
-  auto kernel = EnvelopeAxisLeanKernel<kMode, kNarrow, kSend, kBorder>;
-  kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, smem, stream>>>(
-      d_in, d_out, family, finalize, d_keys);
+  // class words + run-end table of every line (6 bytes per 32 voxels), stream-ordered
+  StreamScratch<uint32_t> class_scratch;
+  VGT_CUDA_TRY(class_scratch.Allocate(
+                   static_cast<int64_t>((LeanScratchBytes(family.length, lines) + 3) / 4), stream),
+               "envelope class-word scratch");
+  auto kernel = EnvelopeAxisLeanKernel<kMode, kNarrow, kSend, kBorder, kSplit>;
+  kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, 0, stream>>>(
+      d_in, d_out, d_positions, class_scratch.get(), family, finalize, d_keys);
   VGT_CUDA_TRY(cudaGetLastError(), "EnvelopeAxisLeanKernel launch");
   return VGT_B200_OK;
 }
 
 // Send-layout output exists only for the packed intermediate, the virtual border only for the
 // finalizing pass, so each mode instantiates two of the four flag combinations.
-template <int kMode, bool kNarrow>
+template <int kMode, bool kNarrow, bool kSplit>
 int LaunchEnvelopeLean(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
-                       const LineFamily& family, const FinalizeParams& finalize,
-                       typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
+                       uint16_t* d_positions, const LineFamily& family,
+                       const FinalizeParams& finalize, typename OutputOf<kMode>::Key* d_keys,
+                       cudaStream_t stream)
 {
   if constexpr (kMode == kEmitPacked)
   {
     if (family.out_parts > 0)
     {
-      return LaunchEnvelopeLeanKernel<kMode, kNarrow, true, false>(d_in, d_out, family, finalize,
-                                                                   d_keys, stream);
+      return LaunchEnvelopeLeanKernel<kMode, kNarrow, true, false, kSplit>(
+          d_in, d_out, d_positions, family, finalize, d_keys, stream);
     }
-    return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, false>(d_in, d_out, family, finalize,
-                                                                  d_keys, stream);
+    return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, false, kSplit>(
+        d_in, d_out, d_positions, family, finalize, d_keys, stream);
   }
   else
   {
@@ -150,11 +157,11 @@ int LaunchEnvelopeLean(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
     }
     if (finalize.add_virtual_border != 0)
     {
-      return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, true>(d_in, d_out, family, finalize,
-                                                                   d_keys, stream);
+      return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, true, kSplit>(
+          d_in, d_out, d_positions, family, finalize, d_keys, stream);
     }
-    return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, false>(d_in, d_out, family, finalize,
-                                                                  d_keys, stream);
+    return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, false, kSplit>(
+        d_in, d_out, d_positions, family, finalize, d_keys, stream);
   }
 }
 
@@ -169,39 +176,55 @@ inline bool LeanEnvelopeEnabled()
   return enabled;
 }
 
+// Largest finite partial squared distance the lean kernel's 32-bit sentinels leave room for
+// (heights h = f + v^2 must stay well below kNoSiteHeight = 2^30 - 1). Every grid whose axes fit
+// VGT_B200_MAX_AXIS stays below it: 2 * 8191^2 < 2^28.
+constexpr int64_t kLeanMaxInput = (int64_t{1} << 29) - 1;
+
 // One strided-axis pass. d_in is DESTROYED and must not alias d_out.
 // max_input: largest finite partial squared distance the pass can see. Short axes use packed
-// 32-bit stack entries; longer ones keep the site positions in a stream-ordered uint16 side array
-// (2 bytes per voxel, span = the family's element span).
+// 32-bit stack entries; longer ones keep the site positions in a stream-ordered uint16 side array.
+
 template <int kMode>
 int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
                    const LineFamily& family, int64_t max_input, const FinalizeParams& finalize,
                    typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
 {
-  if (family.length <= kInPlaceMaxLength && max_input <= kInPlaceMaxInput
-      && family.line_stride * 4 <= 0xffffffffLL && LeanEnvelopeEnabled())
+  if (family.length > VGT_B200_MAX_AXIS || max_input > 0x7ffffffeLL)
+  {
+    return FailInvalid("axis of %d voxels is out of range", family.length);
+  }
+  const bool packed = family.length <= kInPlaceMaxLength && max_input <= kInPlaceMaxInput;
+  const bool lean = LeanEnvelopeEnabled() && family.line_stride * 4 <= 0xffffffffLL
+      && max_input <= kLeanMaxInput;
+  if (lean && packed)
   {
     // 32-bit pop test when no product of an h difference and a position difference can overflow.
     const int64_t max_h = max_input + Square(family.length - 1);
     if (max_h * family.length < (int64_t{1} << 31))
     {
-      return LaunchEnvelopeLean<kMode, true>(d_in, d_out, family, finalize, d_keys, stream);
+      return LaunchEnvelopeLean<kMode, true, false>(d_in, d_out, nullptr, family, finalize,
+                                                    d_keys, stream);
     }
-    return LaunchEnvelopeLean<kMode, false>(d_in, d_out, family, finalize, d_keys, stream);
+    return LaunchEnvelopeLean<kMode, false, false>(d_in, d_out, nullptr, family, finalize, d_keys,
+                                                   stream);
   }
-  if (family.length <= kInPlaceMaxLength && max_input <= kInPlaceMaxInput)
+  if (packed)
   {
     return LaunchEnvelopeInPlaceStack<kMode, false>(d_in, d_out, nullptr, family, finalize,
                                                     d_keys, stream);
   }
-  if (family.length > VGT_B200_MAX_AXIS || max_input > 0x7ffffffeLL)
-  {
-    return FailInvalid("axis of %d voxels is out of range", family.length);
-  }
+  // Longer axes / larger distances: site positions go to a stream-ordered uint16 side array
+  // (2 bytes per voxel, span = the family's element span).
   const int64_t span = (family.num_outer - 1) * family.outer_stride
       + static_cast<int64_t>(family.length - 1) * family.line_stride + family.inner_count;
   StreamScratch<uint16_t> positions;
   VGT_CUDA_TRY(positions.Allocate(span, stream), "envelope position side array");
+  if (lean)
+  {
+    return LaunchEnvelopeLean<kMode, false, true>(d_in, d_out, positions.get(), family, finalize,
+                                                  d_keys, stream);
+  }
   return LaunchEnvelopeInPlaceStack<kMode, true>(d_in, d_out, positions.get(), family, finalize,
                                                  d_keys, stream);
 }
