@@ -179,6 +179,32 @@ def test_full_size_512_properties_and_parity(shared_library, oracle):
     assert sdf.GetMinimumMaximum() == (lo, hi)
 
 
+@pytest.mark.parametrize("shape", [(5, 9, 128), (4, 7, 132), (6, 5, 256), (3, 11, 640),
+                                   (2, 6, 1024), (3, 5, 1028), (4, 6, 98)])
+def test_z_scan_variants(shared_library, oracle, shape):
+    # z lengths that select each z-scan kernel: 1, 2, 4 and 8 register iterations (<= 1024
+    # voxels, multiple of 4), the shared-memory 128-bit kernel (> 1024) and the scalar one
+    # (length not a multiple of 4).
+    rng = np.random.default_rng(shape[2])
+    for fill in (0.02, 0.4):
+        occupancy = random_occupancy(rng, shape, fill, blobs=True)
+        assert_matches_oracle(oracle, occupancy, 0.05)
+    empty = np.zeros(shape, dtype=np.float32)
+    assert_matches_oracle(oracle, empty, 0.05)
+    empty[0, 0, shape[2] - 1] = 1.0
+    assert_matches_oracle(oracle, empty, 0.05)
+
+
+def test_long_axes_through_the_lean_kernel(shared_library, oracle):
+    # y and x lines of 2048+ voxels: split stack entries (f in the row, position in the side
+    # array), 64-bit pop test, class words for 64+ words per line.
+    rng = np.random.default_rng(43)
+    base = random_occupancy(rng, (3, 2300, 36), 0.04, blobs=True)
+    assert_matches_oracle(oracle, base, 0.02)
+    assert_matches_oracle(oracle, np.ascontiguousarray(base.transpose(1, 0, 2)), 0.02,
+                          add_virtual_border=True)
+
+
 def test_pipelined_host_entry_odd_shape(shared_library, oracle):
     # >= 2^24 voxels: the host entry overlaps the slab copies with the passes (x-slabs in,
     # y-slabs out as strided 2-D copies). Odd extents so that no slab boundary is aligned.
