@@ -84,8 +84,13 @@ struct StackEntry
   int32_t f;
 };
 
-template <int kMode, bool kNarrow, bool kSend, bool kBorder, bool kSplit>
-__global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPacked) ? 16 : 12)
+// kBlocksPerSm: resident blocks (of 4 warps) the register budget is cut for. The finalizing modes
+// run at 8 (64 registers, no spills: faster than 10 or 12 blocks with spills in the hot loops).
+// The packed mode is built for 12 (40 registers, no spills) and for 16 (32 registers, a few
+// spilled words); the launcher takes 16 only when it saves a whole wave (e.g. 8192 warp-tiles on
+// 148 SMs: one wave at 64 warps per SM, 1.15 at 48).
+template <int kMode, bool kNarrow, bool kSend, bool kBorder, bool kSplit, int kBlocksPerSm>
+__global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     EnvelopeAxisLeanKernel(uint32_t* in, typename OutputOf<kMode>::Type* out, uint16_t* positions,
                            uint32_t* class_scratch, LineFamily family, FinalizeParams finalize,
                            typename OutputOf<kMode>::Key* min_max_keys)
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int length = family.length;
-  const int num_words = (length + 31) >> 5;
+  const int num_words = static_cast<int>(family.num_words);
 
   const int64_t tiles_per_outer = (family.inner_count + kWarp - 1) / kWarp;
   const int64_t tile_index = static_cast<int64_t>(blockIdx.x) * kLineWarpsPerBlock + warp;
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
   const int64_t column = tile * kWarp + lane;
   const bool active = column < family.inner_count;
   const int64_t first = outer * family.outer_stride + column;
-  const uint32_t stride_bytes = static_cast<uint32_t>(family.line_stride) * 4u;
+  const uint32_t stride_bytes = family.stride_bytes;
   // scratch of this line: class word w at class_words + w * lines, table entry w likewise
   const int64_t lines = family.num_outer * family.inner_count;
   const uint32_t word_stride_bytes = static_cast<uint32_t>(lines) * 4u;
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
     // The entry after the pending one is already in flight, so an advance never waits for
     // memory unless two advances follow each other closely. Entries written in phase 1 have
     // mostly left L2 by now (all tiles of the grid are in flight at once).
-    const uint32_t last_row = static_cast<uint32_t>(length - 1);
+    const uint32_t last_row = family.last_row;
     // (kept undecoded: one register when entries are packed)
     uint32_t following_word = *row_address(min(1u, last_row));
     uint32_t following_position = kSplit ? *position_address(min(1u, last_row)) : 0u;
@@ -383,28 +388,29 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
       }
     }
 
-    // Output row pointer. In send layout it jumps at part boundaries, which are the same for
-    // every lane, so that check is warp-uniform.
-    char* write_at = reinterpret_cast<char*>(out + first);
-    const uint32_t out_stride_bytes =
-        static_cast<uint32_t>(family.line_stride) * static_cast<uint32_t>(sizeof(Out));
+    // Output rows: row q is at write_origin + q * out_stride_bytes (one IMAD.WIDE per row). In
+    // send layout the origin jumps at part boundaries, which are the same for every lane, so
+    // that check is warp-uniform.
+    char* write_origin = reinterpret_cast<char*>(out + first);
+    const uint32_t out_stride_bytes = family.out_stride_bytes;
     int next_part_start = 0;
     uint32_t previous_class = 0;
     int q = 0;
     // class word and table entry of the next word are loaded one word ahead
     uint32_t next_class_word = __ldcs(class_word_address(0));
     uint32_t next_run_end = __ldcs(run_end_address(0));
-    for (int w = 0; w < num_words; w++)
+    uint32_t class_word = 0;
+    int run_end_after_word = 0;
+    const auto next_word = [&](const int w)
     {
-      const uint32_t class_word = next_class_word;
-      const int run_end_after_word = static_cast<int>(next_run_end);
-      {
-        const uint32_t ahead = static_cast<uint32_t>(min(w + 1, num_words - 1));
-        next_class_word = __ldcs(class_word_address(ahead));
-        next_run_end = __ldcs(run_end_address(ahead));
-      }
-      const int word_rows = min(32, length - (w << 5));
-      for (int b = 0; b < word_rows; b++, q++)
+      class_word = next_class_word;
+      run_end_after_word = static_cast<int>(next_run_end);
+      const uint32_t ahead = static_cast<uint32_t>(min(w + 1, num_words - 1));
+      next_class_word = __ldcs(class_word_address(ahead));
+      next_run_end = __ldcs(run_end_address(ahead));
+    };
+    // one row of the sweep; b = q % 32
+    const auto sweep_row = [&](const int b)
       {
         if constexpr (kSend)
         {
@@ -450,16 +456,18 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
               part_row = out + family.inner_count * (family.num_outer * y0 + outer * rows + (q - y0))
                   + column;
             }
-            write_at = reinterpret_cast<char*>(part_row);
+            write_origin = reinterpret_cast<char*>(part_row)
+                - static_cast<uint64_t>(static_cast<uint32_t>(q)) * out_stride_bytes;
           }
         }
-        const uint32_t filled = (class_word >> b) & 1u;
+        const uint32_t remaining_bits = class_word >> b;  // bit 0 = class of row q
+        const uint32_t filled = remaining_bits & 1u;
         if (filled != previous_class || q == 0)
         {
-          // A run starts at q. Its end: the next opposite-class bit of this word, else the table.
-          const uint32_t different = (filled ? ~class_word : class_word) >> b;
-          run_end = different ? min(length, q + __ffs(different) - 1)
-                              : run_end_after_word;
+          // A run starts at q. Its end: the next opposite-class bit of this word, else the table
+          // (bits past the end of the line repeat the last class, so they never end a run).
+          const uint32_t different = filled ? ~remaining_bits & (0xffffffffu >> b) : remaining_bits;
+          run_end = different ? q + __ffs(different) - 1 : run_end_after_word;
           // Drop stored sites of earlier runs that the sweep never reached.
           while (pending_v < q)
           {
@@ -493,9 +501,11 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
         const uint32_t to_right = static_cast<uint32_t>(right_v - q);
         squared = min(min(squared, to_right * to_right), kNone);
 
+        char* const write_at =
+            write_origin + static_cast<uint64_t>(static_cast<uint32_t>(q)) * out_stride_bytes;
         if constexpr (kMode == kEmitPacked)
         {
-          __stcs(reinterpret_cast<uint32_t*>(write_at), (filled << 31) | squared);
+          __stcs(reinterpret_cast<uint32_t*>(write_at), (remaining_bits << 31) | squared);
         }
         else
         {
@@ -516,7 +526,27 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, (kMode == kEmitPack
           lane_min = (value < lane_min) ? value : lane_min;
           lane_max = (value > lane_max) ? value : lane_max;
         }
-        write_at += out_stride_bytes;
+        q++;
+      };
+    // full words with a constant trip count, then the partial last word
+    const int full_words = length >> 5;
+    for (int w = 0; w < full_words; w++)
+    {
+      next_word(w);
+#pragma unroll 1
+      for (int b = 0; b < 32; b++)
+      {
+        sweep_row(b);
+      }
+    }
+    if ((length & 31) != 0)
+    {
+      next_word(full_words);
+      const int tail_rows = length & 31;
+#pragma unroll 1
+      for (int b = 0; b < tail_rows; b++)
+      {
+        sweep_row(b);
       }
     }
   }

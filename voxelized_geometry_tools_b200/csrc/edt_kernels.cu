@@ -106,6 +106,25 @@ int LaunchEnvelopeInPlaceStack(uint32_t* d_in, typename OutputOf<kMode>::Type* d
   return VGT_B200_OK;
 }
 
+// SM count of the current device (148 on B200), cached per host thread.
+inline int64_t MultiprocessorCount()
+{
+  static thread_local int cached_device = -1;
+  static thread_local int cached_count = 148;
+  int device = 0;
+  if (cudaGetDevice(&device) == cudaSuccess && device != cached_device)
+  {
+    int count = 0;
+    if (cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess
+        && count > 0)
+    {
+      cached_count = count;
+      cached_device = device;
+    }
+  }
+  return cached_count;
+}
+
 template <int kMode, bool kNarrow, bool kSend, bool kBorder, bool kSplit>
 int LaunchEnvelopeLeanKernel(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
                              uint16_t* d_positions, const LineFamily& family,
@@ -124,9 +143,36 @@ int LaunchEnvelopeLeanKernel(uint32_t* d_in, typename OutputOf<kMode>::Type* d_o
   VGT_CUDA_TRY(class_scratch.Allocate(
                    static_cast<int64_t>((LeanScratchBytes(family.length, lines) + 3) / 4), stream),
                "envelope class-word scratch");
-  auto kernel = EnvelopeAxisLeanKernel<kMode, kNarrow, kSend, kBorder, kSplit>;
-  kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, 0, stream>>>(
-      d_in, d_out, d_positions, class_scratch.get(), family, finalize, d_keys);
+  LineFamily derived = family;
+  derived.stride_bytes = static_cast<uint32_t>(family.line_stride * 4);
+  derived.out_stride_bytes = static_cast<uint32_t>(
+      family.line_stride * static_cast<int64_t>(sizeof(typename OutputOf<kMode>::Type)));
+  derived.last_row = static_cast<uint32_t>(family.length - 1);
+  derived.num_words = static_cast<uint32_t>((family.length + 31) >> 5);
+  const auto launch = [&](auto kernel)
+  {
+    kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, 0, stream>>>(
+        d_in, d_out, d_positions, class_scratch.get(), derived, finalize, d_keys);
+  };
+  if constexpr (kMode == kEmitPacked)
+  {
+    // 16 blocks per SM (32 registers) only when that saves a whole wave over 12 (40 registers)
+    const int64_t sms = MultiprocessorCount();
+    const int64_t waves_at_16 = (blocks + sms * 16 - 1) / (sms * 16);
+    const int64_t waves_at_12 = (blocks + sms * 12 - 1) / (sms * 12);
+    if (waves_at_16 == 1 && waves_at_12 > 1)
+    {
+      launch(EnvelopeAxisLeanKernel<kMode, kNarrow, kSend, kBorder, kSplit, 16>);
+    }
+    else
+    {
+      launch(EnvelopeAxisLeanKernel<kMode, kNarrow, kSend, kBorder, kSplit, 12>);
+    }
+  }
+  else
+  {
+    launch(EnvelopeAxisLeanKernel<kMode, kNarrow, kSend, kBorder, kSplit, 8>);
+  }
   VGT_CUDA_TRY(cudaGetLastError(), "EnvelopeAxisLeanKernel launch");
   return VGT_B200_OK;
 }
@@ -195,7 +241,7 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
     return FailInvalid("axis of %d voxels is out of range", family.length);
   }
   const bool packed = family.length <= kInPlaceMaxLength && max_input <= kInPlaceMaxInput;
-  const bool lean = LeanEnvelopeEnabled() && family.line_stride * 4 <= 0xffffffffLL
+  const bool lean = LeanEnvelopeEnabled() && family.line_stride * 8 <= 0xffffffffLL
       && max_input <= kLeanMaxInput;
   if (lean && packed)
   {

@@ -51,6 +51,12 @@ struct LineFamily
   // The y pass then IS the all-to-all: no collective call, no intermediate copy.
   int64_t scatter_row_offset;
   uint32_t* scatter_base[8];
+  // Derived values, filled by the launcher (FillDerived) so that the kernels read them straight
+  // from the constant bank as instruction operands instead of re-deriving them in the hot loops.
+  uint32_t stride_bytes;      // line_stride * 4 (the packed intermediate)
+  uint32_t out_stride_bytes;  // line_stride * sizeof(output element)
+  uint32_t last_row;          // length - 1
+  uint32_t num_words;         // ceil(length / 32)
 };
 
 // What the last pass needs to turn squared voxel distances into the SDF.
