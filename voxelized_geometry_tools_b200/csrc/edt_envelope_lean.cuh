@@ -101,23 +101,23 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
   const int length = family.length;
   const int num_words = static_cast<int>(family.num_words);
 
-  const int64_t tiles_per_outer = (family.inner_count + kWarp - 1) / kWarp;
-  const int64_t tile_index = static_cast<int64_t>(blockIdx.x) * kLineWarpsPerBlock + warp;
-  if (tile_index >= tiles_per_outer * family.num_outer)
+  // (the launcher guarantees that tile, line and column counts fit 31 bits)
+  const uint32_t tiles_per_outer = static_cast<uint32_t>((family.inner_count + kWarp - 1) / kWarp);
+  const uint32_t tile_index = blockIdx.x * kLineWarpsPerBlock + warp;
+  if (tile_index >= tiles_per_outer * static_cast<uint32_t>(family.num_outer))
   {
     return;  // warp-uniform
   }
-  const int64_t outer = tile_index / tiles_per_outer;
-  const int64_t tile = tile_index - outer * tiles_per_outer;
-  const int64_t column = tile * kWarp + lane;
-  const bool active = column < family.inner_count;
-  const int64_t first = outer * family.outer_stride + column;
+  const uint32_t outer = tile_index / tiles_per_outer;
+  const uint32_t column = (tile_index - outer * tiles_per_outer) * kWarp + lane;
+  const bool active = column < static_cast<uint32_t>(family.inner_count);
+  const int64_t first = static_cast<int64_t>(outer) * family.outer_stride + column;
   const uint32_t stride_bytes = family.stride_bytes;
   // scratch of this line: class word w at class_words + w * lines, table entry w likewise
   const int64_t lines = family.num_outer * family.inner_count;
   const uint32_t word_stride_bytes = static_cast<uint32_t>(lines) * 4u;
-  char* const class_words =
-      reinterpret_cast<char*>(class_scratch + outer * family.inner_count + column);
+  const uint32_t line_index = outer * static_cast<uint32_t>(family.inner_count) + column;
+  char* const class_words = reinterpret_cast<char*>(class_scratch + line_index);
   const auto class_word_address = [&](uint32_t w)
   {
     return reinterpret_cast<uint32_t*>(class_words + static_cast<uint64_t>(w) * word_stride_bytes);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
   const auto run_end_address = [&](uint32_t w)
   {
     char* const table = reinterpret_cast<char*>(class_scratch + static_cast<int64_t>(num_words) * lines)
-        + 2 * (outer * family.inner_count + column);
+        + 2 * static_cast<uint64_t>(line_index);
     return reinterpret_cast<uint16_t*>(table + static_cast<uint64_t>(w) * (word_stride_bytes >> 1));
   };
 
@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
 
   if (active)
   {
-    char* const line = reinterpret_cast<char*>(in + first);
+    // Pinned in a register pair: the compiler otherwise re-derives it from the kernel parameters
+    // (ten instructions) at every prefetch inside the hot loop, which is issue-bound.
+    char* line = reinterpret_cast<char*>(in + first);
+    asm volatile("" : "+l"(line));
     const auto row_address = [&](uint32_t row)
     {
       return reinterpret_cast<uint32_t*>(line + static_cast<uint64_t>(row) * stride_bytes);
