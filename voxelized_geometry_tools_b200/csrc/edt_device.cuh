@@ -396,6 +396,30 @@ __device__ __forceinline__ Out SignedDistanceOf(uint32_t filled, uint32_t square
   return filled ? -magnitude : magnitude;
 }
 
+// The same value through the per-call magnitude table when the squared distance is inside it.
+template <typename Out>
+__device__ __forceinline__ Out SignedDistanceFromTable(uint32_t filled, uint32_t squared,
+                                                       double resolution, const Out* table,
+                                                       uint32_t table_size)
+{
+  if (squared < table_size)
+  {
+    const Out magnitude = __ldg(table + squared);
+    return filled ? -magnitude : magnitude;
+  }
+  return SignedDistanceOf<Out>(filled, squared, resolution);
+}
+
+template <typename Out>
+__global__ void BuildMagnitudeTableKernel(Out* table, uint32_t size, double resolution)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < size)
+  {
+    table[s] = SignedDistanceOf<Out>(0u, s, resolution);
+  }
+}
+
 enum EnvelopeMode
 {
   kEmitPacked = 0,  // int32 sign-fused word out

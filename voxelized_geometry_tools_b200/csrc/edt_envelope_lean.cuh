@@ -524,7 +524,9 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
               squared = min(squared, static_cast<uint32_t>(border * border));
             }
           }
-          const Out value = SignedDistanceOf<Out>(filled, squared, finalize.resolution);
+          const Out value = SignedDistanceFromTable<Out>(
+              filled, squared, finalize.resolution,
+              static_cast<const Out*>(finalize.magnitude_table), finalize.magnitude_table_size);
           __stcs(reinterpret_cast<Out*>(write_at), value);
           lane_min = (value < lane_min) ? value : lane_min;
           lane_max = (value > lane_max) ? value : lane_max;

@@ -339,6 +339,37 @@ int RunLocalPasses(const In* d_in, int64_t nx, int64_t ny, int64_t nz, int unkno
                                      FinalizeParams{}, nullptr, stream);
 }
 
+// Per-call table of finished magnitudes for the finalizing pass (FinalizeParams::magnitude_table):
+// every squared distance the grid can produce, capped at 2^20 entries (4 / 8 MB); larger values
+// take the direct fp64 path in the kernel.
+constexpr int64_t kMagnitudeTableMaxEntries = int64_t{1} << 20;
+
+template <typename Out>
+class MagnitudeTable
+{
+public:
+  int Build(int64_t nx, int64_t ny, int64_t nz, double resolution, cudaStream_t stream)
+  {
+    const int64_t largest = Square(nx - 1) + Square(ny - 1) + Square(nz - 1);
+    size_ = static_cast<uint32_t>(std::min(largest + 1, kMagnitudeTableMaxEntries));
+    VGT_CUDA_TRY(table_.Allocate(size_, stream), "magnitude table allocation");
+    const unsigned threads = 256;
+    BuildMagnitudeTableKernel<Out><<<(size_ + threads - 1) / threads, threads, 0, stream>>>(
+        table_.get(), size_, resolution);
+    VGT_CUDA_TRY(cudaGetLastError(), "BuildMagnitudeTableKernel launch");
+    return VGT_B200_OK;
+  }
+  void Attach(FinalizeParams& finalize) const
+  {
+    finalize.magnitude_table = table_.get();
+    finalize.magnitude_table_size = size_;
+  }
+
+private:
+  StreamScratch<Out> table_;
+  uint32_t size_ = 0;
+};
+
 // x envelope on an [nx, ny_local, nz] block + finalize. d_packed is destroyed.
 template <int kMode>
 int RunFinalPass(uint32_t* d_packed, int64_t nx, int64_t ny_local, int64_t nz, int64_t y_offset,
@@ -362,6 +393,15 @@ int RunFinalPass(uint32_t* d_packed, int64_t nx, int64_t ny_local, int64_t nz, i
   finalize.nz_total = static_cast<int32_t>(nz);
   finalize.y_offset = static_cast<int32_t>(y_offset);
   finalize.nz = static_cast<int32_t>(nz);
+  MagnitudeTable<Out> magnitudes;
+  {
+    const int built = magnitudes.Build(nx, ny_total, nz, resolution, stream);
+    if (built != VGT_B200_OK)
+    {
+      return built;
+    }
+    magnitudes.Attach(finalize);
+  }
   const int status = LaunchEnvelope<kMode>(d_packed, d_out, FamilyAlongX(nx, ny_local, nz),
                                            Square(nz - 1) + Square(ny_total - 1), finalize,
                                            keys.get(), stream);
@@ -491,9 +531,12 @@ template <int kMode>
 int RunFinalPassColumns(uint32_t* d_packed, int64_t nx, int64_t ny, int64_t nz, int64_t y0,
                         int64_t y1, double resolution, int add_virtual_border,
                         typename OutputOf<kMode>::Type* d_out,
-                        typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
+                        typename OutputOf<kMode>::Key* d_keys,
+                        const MagnitudeTable<typename OutputOf<kMode>::Type>& magnitudes,
+                        cudaStream_t stream)
 {
   FinalizeParams finalize{};
+  magnitudes.Attach(finalize);
   finalize.resolution = resolution;
   finalize.add_virtual_border = add_virtual_border;
   finalize.nx_total = static_cast<int32_t>(nx);
@@ -578,6 +621,11 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
       }
     }
   }
+  MagnitudeTable<Out> magnitudes;
+  if (status == VGT_B200_OK)
+  {
+    status = magnitudes.Build(nx, ny, nz, resolution, compute.stream);
+  }
   const int out_chunks = static_cast<int>(ny < kPipelineChunks ? ny : kPipelineChunks);
   EventGuard finished[kPipelineChunks];
   for (int c = 0; c < out_chunks && status == VGT_B200_OK; c++)
@@ -585,7 +633,7 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
     const int64_t y0 = ny * c / out_chunks;
     const int64_t y1 = ny * (c + 1) / out_chunks;
     status = RunFinalPassColumns<kMode>(scratch.get(), nx, ny, nz, y0, y1, resolution,
-                                        add_virtual_border, d_out.get(), keys.get(),
+                                        add_virtual_border, d_out.get(), keys.get(), magnitudes,
                                         compute.stream);
     if (status != VGT_B200_OK)
     {

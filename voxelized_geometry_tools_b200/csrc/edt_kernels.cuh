@@ -72,6 +72,12 @@ struct FinalizeParams
   int32_t nz_total;
   int32_t y_offset;
   int32_t nz;  // columns per y row of this family
+  // Optional table of the finished magnitudes, magnitude_table[s] = (Out)(sqrt((double)s) *
+  // resolution) for s < magnitude_table_size, built per call by BuildMagnitudeTableKernel with
+  // the very expression of the direct path: one (mostly L1-resident) load replaces the fp64
+  // square root for every squared distance below the table size. nullptr / 0: no table.
+  const void* magnitude_table;
+  uint32_t magnitude_table_size;
 };
 }  // namespace edt
 }  // namespace vgt_b200
