@@ -349,6 +349,21 @@ def run_ours(args):
     if not distributed and not args.skip_voxelizer:
         voxelizer = bench_voxelizer(dev, peak, include_cpu=not args.skip_cpu)
 
+    # ---- BASELINE configs 1 and 3 (parity-test cases): device-resident SDF time beside the line
+    other_configs = None
+    if not distributed:
+        other_configs = {}
+        box = torch.from_numpy(synthetic.box_scene(128)).to(dev)
+        box_out = torch.empty_like(box)
+        for _ in range(3):
+            vdev.signed_distance_field(box, RESOLUTION, out=box_out)
+        torch.cuda.synchronize(dev)
+        box_ms = [sum(vdev.signed_distance_field_profile(box, RESOLUTION, box_out))
+                  for _ in range(10)]
+        other_configs["config1_128^3_box_scene_sdf_ms"] = statistics.median(box_ms)
+        other_configs["config1_note"] = ("8 MiB per buffer: L2-resident, so a time, not a "
+                                         "roofline fraction (SURVEY.md section 8d)")
+
     cpu_baseline = None
     if rank == 0 and not distributed and not args.skip_cpu:
         full = cpu_reference_arm(1, 0)
@@ -375,6 +390,8 @@ def run_ours(args):
         }
         if voxelizer is not None:
             line["voxelizer"] = voxelizer
+        if other_configs is not None:
+            line["other_configs"] = other_configs
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
@@ -419,6 +436,14 @@ def bench_voxelizer(dev, peak, include_cpu=True):
         increments = int(counts.sum(dtype=torch.int64).item())
     raycast = statistics.mean(raycast_ms)
     filt = statistics.mean(filter_ms)
+    # "... then SDF" (config 3): the SDF of the voxelized map, device-resident
+    sdf_out = torch.empty_like(occupancy)
+    for _ in range(2):
+        vdev.signed_distance_field(occupancy, scene["voxel_size"], out=sdf_out)
+    torch.cuda.synchronize(dev)
+    sdf_after_ms = statistics.median(
+        sum(vdev.signed_distance_field_profile(occupancy, scene["voxel_size"], sdf_out))
+        for _ in range(7))
     voxels = n ** 3
     filter_bytes = (8 * len(clouds) + 8) * voxels
 
@@ -450,6 +475,7 @@ def bench_voxelizer(dev, peak, include_cpu=True):
     return {"metric": "voxelization_mrays_per_s", "value": finite_rays / (raycast * 1e-3) / 1e6,
             "unit": "Mrays/s", "rays": finite_rays, "grid": f"{n}^3", "cameras": len(clouds),
             "raycast_ms": raycast, "filter_ms": filt, "zero_ms": statistics.mean(zero_ms),
+            "sdf_of_voxelized_map_ms": sdf_after_ms,
             "atomic_increments": increments,
             "counter_increments_per_s_G": increments / (raycast * 1e-3) / 1e9,
             "e2e": {"value": finite_rays / host_seconds / 1e6, "unit": "Mrays/s",

@@ -269,3 +269,4 @@ def test_smooth_distance_like_lines():
         values = [int((i - centre) ** 2) + offset for i in range(n)]
         assert kernel_line(classes, values) == brute_line(classes, values)
         assert lean_line(classes, values) == brute_line(classes, values)
+
