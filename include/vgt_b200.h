@@ -90,6 +90,56 @@ VGT_B200_API int vgt_b200_sdf_from_mask_f64(
     const uint8_t* filled_mask, int64_t nx, int64_t ny, int64_t nz, double resolution,
     int add_virtual_border, int device, double* sdf_out, double* out_min, double* out_max);
 
+/* ---- the other map types ----
+ * OccupancyComponentMap, TaggedObjectOccupancyMap and TaggedObjectOccupancyComponentMap store
+ * packed cells of 8 or 16 bytes whose first word is the float occupancy and whose second word is
+ * the object id (tagged maps) or the component (component map, never read here):
+ *   include/.../occupancy_component_map.hpp:28-64, tagged_object_occupancy_map.hpp:28-68,
+ *   tagged_object_occupancy_component_map.hpp:17-60 (static_asserts pin the sizes).
+ * `cells` is GetImmutableRawData().data() of such a map; the filled predicate runs on the device.
+ *
+ * vgt_b200_sdf_from_cells_*: replaces ExtractSignedDistanceField<T>(objects_to_use, parameters)
+ *   (tagged_object_occupancy_map.hpp:199-247, tagged_object_occupancy_component_map.hpp:360-410)
+ *   and, with num_object_ids == 0, OccupancyComponentMap::ExtractSignedDistanceField<T>
+ *   (occupancy_component_map.hpp:270-306): a cell is filled iff the occupancy rule holds and
+ *   (num_object_ids == 0 or its object id is listed). */
+VGT_B200_API int vgt_b200_sdf_from_cells_f32(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const uint32_t* object_ids,
+    int64_t num_object_ids, int device, float* sdf_out, float* out_min, float* out_max);
+
+VGT_B200_API int vgt_b200_sdf_from_cells_f64(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const uint32_t* object_ids,
+    int64_t num_object_ids, int device, double* sdf_out, double* out_min, double* out_max);
+
+/* Replaces MakeSeparateObjectSDFs<T>(object_ids, parameters)
+ * (tagged_object_occupancy_map.hpp:249-262): one SDF per listed object, the cells uploaded once.
+ * sdf_out holds num_object_ids grids back to back, out_min / out_max one value per object. */
+VGT_B200_API int vgt_b200_sdf_per_object_f32(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const uint32_t* object_ids,
+    int64_t num_object_ids, int device, float* sdf_out, float* out_min, float* out_max);
+
+VGT_B200_API int vgt_b200_sdf_per_object_f64(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const uint32_t* object_ids,
+    int64_t num_object_ids, int device, double* sdf_out, double* out_min, double* out_max);
+
+/* Replaces ExtractFreeAndNamedObjectsSignedDistanceField<T>(parameters)
+ * (tagged_object_occupancy_map.hpp:293-378): the SDF of all filled cells and the SDF of the
+ * filled cells of named objects (id > 0), merged (free >= 0 -> free; else named <= -0 -> named;
+ * else 0), min/max of the merged field. */
+VGT_B200_API int vgt_b200_sdf_free_and_named_f32(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, float* sdf_out, float* out_min,
+    float* out_max);
+
+VGT_B200_API int vgt_b200_sdf_free_and_named_f64(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, double* sdf_out, double* out_min,
+    double* out_max);
+
 /* Parity hook for internal::ComputeDistanceFieldTransformInPlace on the two 0/inf fields
  * (include/.../signed_distance_field_generation.hpp:34-37, 47-80): both squared fields in voxel
  * units as int32, VGT_B200_SQ_INF where the reference holds +inf. Host pointers. */

@@ -187,6 +187,53 @@ def sdf_from_mask(mask, resolution: float, add_virtual_border: bool = False,
     return out, (min_max[0], min_max[1])
 
 
+# ------------------------------------------------------------------------------------------------
+# The other map types. Plain numpy over the pinned pieces above:
+# the only new arithmetic is the filled predicate and the free / named merge.
+# ------------------------------------------------------------------------------------------------
+def cells_filled_mask(cells, unknown_is_filled: bool = True, objects_to_use=(),
+                      named_only: bool = False):
+    """The is_filled_fn of the cell maps, evaluated over the whole grid:
+    occupancy_component_map.hpp:276-299 (occupancy rule only),
+    tagged_object_occupancy_map.hpp:213-241 (occupancy rule and: no objects listed, or the
+    cell's object id is listed), tagged_object_occupancy_map.hpp:316-334 (named objects: id > 0)."""
+    occupancy = cells["occupancy"]
+    filled = occupancy > np.float32(0.5)
+    if unknown_is_filled:
+        filled = filled | (occupancy == np.float32(0.5))
+    if named_only:
+        filled = filled & (cells["object_id"] > 0)
+    else:
+        listed = [int(i) for i in objects_to_use]
+        if listed:
+            filled = filled & np.isin(cells["object_id"], np.array(listed, dtype=np.uint32))
+    return filled
+
+
+def sdf_from_cells(cells, resolution: float, unknown_is_filled: bool = True,
+                   add_virtual_border: bool = False, objects_to_use=(), named_only: bool = False,
+                   dtype=np.float32, threads: int = 0):
+    """ExtractSignedDistanceField of a cell map: predicate -> internal::ExtractSignedDistanceField
+    (signed_distance_field_generation.hpp:115-285). Returns (sdf, (min, max))."""
+    mask = cells_filled_mask(cells, unknown_is_filled, objects_to_use, named_only)
+    # an occupancy of exactly 1 / 0 makes the OccupancyMap entry evaluate the same predicate
+    return sdf(mask.astype(np.float32), resolution, True, add_virtual_border, threads, dtype)
+
+
+def sdf_free_and_named(cells, resolution: float, unknown_is_filled: bool = True,
+                       add_virtual_border: bool = False, dtype=np.float32, threads: int = 0):
+    """ExtractFreeAndNamedObjectsSignedDistanceField (tagged_object_occupancy_map.hpp:293-378):
+    free >= 0 -> free; else named <= -0 -> named; else 0; then Lock()'s min/max."""
+    free, _ = sdf_from_cells(cells, resolution, unknown_is_filled, add_virtual_border, (),
+                             False, dtype, threads)
+    named, _ = sdf_from_cells(cells, resolution, unknown_is_filled, add_virtual_border, (),
+                              True, dtype, threads)
+    zero = np.zeros((), dtype=dtype)
+    combined = np.where(free >= zero, free, np.where(named <= -zero, named, zero))
+    combined = combined.astype(dtype)
+    return combined, (combined.min(), combined.max())
+
+
 def raycast_cloud(points_xyz, x_gc, max_range: float, dims, voxel_size: float,
                   counts: np.ndarray | None = None, threads: int = 0):
     """Accumulates one cloud into counts[x, y, z, 2] (0 = seen free, 1 = seen filled).

@@ -1,0 +1,55 @@
+"""CPU: the oracle's restatement of the other map types' SDF entry points (SURVEY.md section 8f,
+rank 1) against the reference's own assertions: the four map types produce the same SDF for the
+same occupancy (test/sdf_generation_test.cpp:152-189), and hand-checked predicate / merge cases."""
+import numpy as np
+
+from voxelized_geometry_tools_b200 import grids
+
+from .conftest import occupancy_from_golden_case
+
+
+def tagged_cells(occupancy, object_ids, dtype=grids.TAGGED_OBJECT_OCCUPANCY_CELL):
+    cells = np.zeros(occupancy.shape, dtype=dtype)
+    cells["occupancy"] = occupancy
+    cells["object_id"] = object_ids
+    return cells
+
+
+def test_four_map_types_agree_on_the_reference_cases(oracle, sdf_goldens):
+    for case in sdf_goldens["cases"]:
+        occupancy, resolution = occupancy_from_golden_case(case)
+        want, want_extrema = oracle.sdf(occupancy, resolution)
+        component = np.zeros(occupancy.shape, dtype=grids.OCCUPANCY_COMPONENT_CELL)
+        component["occupancy"] = occupancy
+        component["component"] = 7
+        ids = np.arange(occupancy.size, dtype=np.uint32).reshape(occupancy.shape) % 5
+        for cells in (component, tagged_cells(occupancy, ids),
+                      tagged_cells(occupancy, ids, grids.TAGGED_OBJECT_OCCUPANCY_COMPONENT_CELL)):
+            objects = () if "object_id" in (cells.dtype.names or ()) else ()
+            got, extrema = oracle.sdf_from_cells(cells, resolution, objects_to_use=objects)
+            np.testing.assert_array_equal(got, want)
+            assert extrema == want_extrema
+
+
+def test_object_predicates(oracle):
+    occupancy = np.array([0.0, 1.0, 0.5, 1.0, 0.7, 0.2], dtype=np.float32).reshape(1, 1, 6)
+    ids = np.array([0, 3, 3, 0, 9, 9], dtype=np.uint32).reshape(1, 1, 6)
+    cells = tagged_cells(occupancy, ids)
+    mask = oracle.cells_filled_mask
+    assert mask(cells).ravel().tolist() == [False, True, True, True, True, False]
+    assert mask(cells, unknown_is_filled=False).ravel().tolist() == [False, True, False, True, True, False]
+    assert mask(cells, objects_to_use=[3]).ravel().tolist() == [False, True, True, False, False, False]
+    assert mask(cells, objects_to_use=[9, 3, 3]).ravel().tolist() == [False, True, True, False, True, False]
+    assert mask(cells, objects_to_use=[5]).ravel().tolist() == [False] * 6
+    assert mask(cells, named_only=True).ravel().tolist() == [False, True, True, False, True, False]
+
+
+def test_free_and_named_merge(oracle):
+    # x line: free | unnamed obstacle (id 0) | free | named obstacle (id 2)
+    occupancy = np.array([0, 0, 1, 1, 0, 0, 1], dtype=np.float32).reshape(7, 1, 1)
+    ids = np.array([0, 0, 0, 0, 0, 0, 2], dtype=np.uint32).reshape(7, 1, 1)
+    got, (lo, hi) = oracle.sdf_free_and_named(tagged_cells(occupancy, ids), 1.0)
+    # free cells keep the distance to the nearest obstacle of any kind; the unnamed obstacle is
+    # not inside a named object, so it reads 0; the named cell reads its depth inside named space
+    assert got.ravel().tolist() == [2.0, 1.0, 0.0, 0.0, 1.0, 1.0, -1.0]
+    assert (lo, hi) == (-1.0, 2.0)

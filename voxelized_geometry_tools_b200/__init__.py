@@ -13,9 +13,12 @@ from ._capi import BackendUnavailable, device_count  # noqa: F401
 from .grids import (  # noqa: F401
     ComputeSquaredDistanceFields,
     ExtractSignedDistanceFieldFromMask,
+    OccupancyComponentMap,
     OccupancyMap,
     SignedDistanceField,
     SignedDistanceFieldGenerationParameters,
+    TaggedObjectOccupancyComponentMap,
+    TaggedObjectOccupancyMap,
     VoxelGridSizes,
 )
 from .pointcloud_voxelization import (  # noqa: F401

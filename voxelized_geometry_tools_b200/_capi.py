@@ -52,6 +52,18 @@ SIGNATURES = {
                                           _f32p]),
     "vgt_b200_sdf_from_mask_f64": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _vp, _f64p,
                                           _f64p]),
+    "vgt_b200_sdf_from_cells_f32": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _int, _vp, _i64,
+                                           _int, _vp, _f32p, _f32p]),
+    "vgt_b200_sdf_from_cells_f64": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _int, _vp, _i64,
+                                           _int, _vp, _f64p, _f64p]),
+    "vgt_b200_sdf_per_object_f32": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _int, _vp, _i64,
+                                           _int, _vp, _vp, _vp]),
+    "vgt_b200_sdf_per_object_f64": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _int, _vp, _i64,
+                                           _int, _vp, _vp, _vp]),
+    "vgt_b200_sdf_free_and_named_f32": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _int, _int,
+                                               _vp, _f32p, _f32p]),
+    "vgt_b200_sdf_free_and_named_f64": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _int, _int,
+                                               _vp, _f64p, _f64p]),
     "vgt_b200_edt_sq_i32": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "vgt_b200_sdf_f32_dev": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _int, _vp, _vp, _vp]),
     "vgt_b200_sdf_f32_dev_profile": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _int, _vp, _vp,

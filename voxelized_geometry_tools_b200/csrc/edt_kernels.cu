@@ -1,7 +1,9 @@
 // Host orchestration + C-ABI entry points of the occupancy -> SignedDistanceField path (sm_100a).
 // Device code: edt_device.cuh (z scan, shared-memory envelope fallback, finalize helpers) and
 // edt_envelope_inplace.cuh (the fast envelope kernel). DESIGN.md has the roofline of each kernel.
+#include <algorithm>
 #include <cmath>
+#include <vector>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -11,6 +13,7 @@
 #include "edt_envelope_inplace.cuh"
 #include "edt_envelope_lean.cuh"
 #include "edt_scan_registers.cuh"
+#include "edt_cells.cuh"
 
 namespace vgt_b200
 {
@@ -737,6 +740,253 @@ int SdfFromHost(const In* h_in, int64_t nx, int64_t ny, int64_t nz, double resol
   }
   return VGT_B200_OK;
 }
+// ------------------------------------------------------------------------------------------------
+// Other map types: cells { float occupancy; uint32 object_id; ... } (edt_cells.cuh)
+// ------------------------------------------------------------------------------------------------
+int CheckCellArguments(const void* cells, int cell_bytes, const void* out, int64_t nx, int64_t ny,
+                       int64_t nz, double resolution, const uint32_t* object_ids,
+                       int64_t num_object_ids)
+{
+  const int check = CheckSdfArguments(cells, out, nx, ny, nz, resolution);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  if (cell_bytes != 8 && cell_bytes != 16)
+  {
+    return FailInvalid("cell size must be 8 or 16 bytes, got %d", cell_bytes);
+  }
+  if (num_object_ids < 0 || num_object_ids > 0x7fffffffLL
+      || (num_object_ids > 0 && object_ids == nullptr))
+  {
+    return FailInvalid("invalid object id list");
+  }
+  return VGT_B200_OK;
+}
+
+// Device-resident cells -> SDF of the voxels the rule marks filled.
+template <int kMode>
+int SdfFromCellsOnDevice(const uint32_t* d_cells, int cell_words, int64_t nx, int64_t ny,
+                         int64_t nz, double resolution, int unknown_is_filled,
+                         int add_virtual_border, int object_rule, const uint32_t* d_sorted_ids,
+                         int num_ids, typename OutputOf<kMode>::Type* d_sdf,
+                         typename OutputOf<kMode>::Type* d_min_max, cudaStream_t stream)
+{
+  const int64_t count = nx * ny * nz;
+  StreamScratch<uint8_t> mask;
+  VGT_CUDA_TRY(mask.Allocate(count, stream), "filled mask allocation");
+  const int threads = 256;
+  CellsToMaskKernel<<<static_cast<unsigned>((count + threads - 1) / threads), threads, 0,
+                      stream>>>(d_cells, cell_words, count, unknown_is_filled, object_rule,
+                                d_sorted_ids, num_ids, mask.get());
+  VGT_CUDA_TRY(cudaGetLastError(), "CellsToMaskKernel launch");
+  return SdfOnDevice<uint8_t, kMode>(mask.get(), nx, ny, nz, resolution, 0, add_virtual_border,
+                                     d_sdf, d_min_max, stream);
+}
+
+// Cells and (sorted) object ids uploaded once for one or several SDFs.
+struct CellUpload
+{
+  StreamScratch<uint32_t> cells;
+  StreamScratch<uint32_t> ids;
+  std::vector<uint32_t> sorted;
+  int Upload(const void* h_cells, int cell_bytes, int64_t count, const uint32_t* object_ids,
+             int64_t num_object_ids, cudaStream_t stream)
+  {
+    VGT_CUDA_TRY(cells.Allocate(count * (cell_bytes / 4), stream), "cell array allocation");
+    VGT_CUDA_TRY(cudaMemcpyAsync(cells.get(), h_cells, static_cast<size_t>(count) * cell_bytes,
+                                 cudaMemcpyHostToDevice, stream),
+                 "copy cells to device");
+    sorted.assign(object_ids, object_ids + num_object_ids);
+    std::sort(sorted.begin(), sorted.end());
+    sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+    if (!sorted.empty())
+    {
+      VGT_CUDA_TRY(ids.Allocate(static_cast<int64_t>(sorted.size()), stream), "id allocation");
+      VGT_CUDA_TRY(cudaMemcpyAsync(ids.get(), sorted.data(), sizeof(uint32_t) * sorted.size(),
+                                   cudaMemcpyHostToDevice, stream),
+                   "copy object ids to device");
+    }
+    return VGT_B200_OK;
+  }
+};
+
+// num_sdfs == 1: one SDF of the cells whose object id is in object_ids (all objects when the
+// list is empty). per_object: one SDF per listed object id (MakeSeparateObjectSDFs), results
+// back to back in h_out.
+template <int kMode>
+int SdfFromCellsHost(const void* h_cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz,
+                     double resolution, int unknown_is_filled, int add_virtual_border,
+                     const uint32_t* object_ids, int64_t num_object_ids, bool per_object,
+                     int device, typename OutputOf<kMode>::Type* h_out,
+                     typename OutputOf<kMode>::Type* out_min,
+                     typename OutputOf<kMode>::Type* out_max)
+{
+  using Out = typename OutputOf<kMode>::Type;
+  const int check = CheckCellArguments(h_cells, cell_bytes, h_out, nx, ny, nz, resolution,
+                                       object_ids, num_object_ids);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  ScopedDevice scoped(device);
+  VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+  KeepPoolMemory(device);
+  const int64_t count = nx * ny * nz;
+  StreamGuard guard;
+  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&guard.stream, cudaStreamNonBlocking),
+               "cudaStreamCreate");
+  cudaStream_t stream = guard.stream;
+  CellUpload upload;
+  const int uploaded = upload.Upload(h_cells, cell_bytes, count, object_ids,
+                                     per_object ? 0 : num_object_ids, stream);
+  if (uploaded != VGT_B200_OK)
+  {
+    return uploaded;
+  }
+  const int64_t num_sdfs = per_object ? num_object_ids : 1;
+  StreamScratch<Out> d_out;
+  StreamScratch<Out> d_min_max;
+  StreamScratch<uint32_t> d_one_id;
+  VGT_CUDA_TRY(d_out.Allocate(count, stream), "SDF allocation");
+  VGT_CUDA_TRY(d_min_max.Allocate(2 * std::max<int64_t>(num_sdfs, 1), stream), "min/max");
+  if (per_object && num_sdfs > 0)
+  {
+    VGT_CUDA_TRY(d_one_id.Allocate(num_sdfs, stream), "id allocation");
+    VGT_CUDA_TRY(cudaMemcpyAsync(d_one_id.get(), object_ids, sizeof(uint32_t) * num_sdfs,
+                                 cudaMemcpyHostToDevice, stream),
+                 "copy object ids to device");
+  }
+  std::vector<Out> min_max(static_cast<size_t>(2 * std::max<int64_t>(num_sdfs, 1)));
+  for (int64_t k = 0; k < num_sdfs; k++)
+  {
+    int status;
+    if (per_object)
+    {
+      status = SdfFromCellsOnDevice<kMode>(upload.cells.get(), cell_bytes / 4, nx, ny, nz,
+                                           resolution, unknown_is_filled, add_virtual_border,
+                                           kListedObjects, d_one_id.get() + k, 1, d_out.get(),
+                                           d_min_max.get() + 2 * k, stream);
+    }
+    else
+    {
+      const int num_ids = static_cast<int>(upload.sorted.size());
+      status = SdfFromCellsOnDevice<kMode>(upload.cells.get(), cell_bytes / 4, nx, ny, nz,
+                                           resolution, unknown_is_filled, add_virtual_border,
+                                           num_ids > 0 ? kListedObjects : kAnyObject,
+                                           upload.ids.get(), num_ids, d_out.get(),
+                                           d_min_max.get(), stream);
+    }
+    if (status != VGT_B200_OK)
+    {
+      cudaStreamSynchronize(stream);
+      return status;
+    }
+    // (stream order: the copy finishes before the next SDF overwrites d_out)
+    VGT_CUDA_TRY(cudaMemcpyAsync(h_out + k * count, d_out.get(), sizeof(Out) * count,
+                                 cudaMemcpyDeviceToHost, stream),
+                 "copy SDF to host");
+  }
+  if (num_sdfs > 0)
+  {
+    VGT_CUDA_TRY(cudaMemcpyAsync(min_max.data(), d_min_max.get(), sizeof(Out) * 2 * num_sdfs,
+                                 cudaMemcpyDeviceToHost, stream),
+                 "copy min/max to host");
+  }
+  VGT_CUDA_TRY(cudaStreamSynchronize(stream), "SDF generation from cells");
+  for (int64_t k = 0; k < num_sdfs; k++)
+  {
+    if (out_min != nullptr)
+    {
+      out_min[k] = min_max[2 * k];
+    }
+    if (out_max != nullptr)
+    {
+      out_max[k] = min_max[2 * k + 1];
+    }
+  }
+  return VGT_B200_OK;
+}
+
+// ExtractFreeAndNamedObjectsSignedDistanceField (tagged_object_occupancy_map.hpp:293-378): the
+// SDF of every filled cell, the SDF of the filled cells of named objects (id > 0), merged.
+template <int kMode>
+int SdfFreeAndNamedHost(const void* h_cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz,
+                        double resolution, int unknown_is_filled, int add_virtual_border,
+                        int device, typename OutputOf<kMode>::Type* h_out,
+                        typename OutputOf<kMode>::Type* out_min,
+                        typename OutputOf<kMode>::Type* out_max)
+{
+  using Out = typename OutputOf<kMode>::Type;
+  using Key = typename OutputOf<kMode>::Key;
+  const int check = CheckCellArguments(h_cells, cell_bytes, h_out, nx, ny, nz, resolution,
+                                       nullptr, 0);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  ScopedDevice scoped(device);
+  VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+  KeepPoolMemory(device);
+  const int64_t count = nx * ny * nz;
+  StreamGuard guard;
+  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&guard.stream, cudaStreamNonBlocking),
+               "cudaStreamCreate");
+  cudaStream_t stream = guard.stream;
+  CellUpload upload;
+  const int uploaded = upload.Upload(h_cells, cell_bytes, count, nullptr, 0, stream);
+  if (uploaded != VGT_B200_OK)
+  {
+    return uploaded;
+  }
+  StreamScratch<Out> d_free;
+  StreamScratch<Out> d_named;
+  StreamScratch<Out> d_min_max;
+  StreamScratch<Key> keys;
+  VGT_CUDA_TRY(d_free.Allocate(count, stream), "SDF allocation");
+  VGT_CUDA_TRY(d_named.Allocate(count, stream), "SDF allocation");
+  VGT_CUDA_TRY(d_min_max.Allocate(2, stream), "min/max allocation");
+  VGT_CUDA_TRY(keys.Allocate(2, stream), "min/max scratch");
+  int status = SdfFromCellsOnDevice<kMode>(upload.cells.get(), cell_bytes / 4, nx, ny, nz,
+                                           resolution, unknown_is_filled, add_virtual_border,
+                                           kAnyObject, nullptr, 0, d_free.get(), nullptr, stream);
+  if (status == VGT_B200_OK)
+  {
+    status = SdfFromCellsOnDevice<kMode>(upload.cells.get(), cell_bytes / 4, nx, ny, nz,
+                                         resolution, unknown_is_filled, add_virtual_border,
+                                         kNamedObjects, nullptr, 0, d_named.get(), nullptr,
+                                         stream);
+  }
+  if (status != VGT_B200_OK)
+  {
+    cudaStreamSynchronize(stream);
+    return status;
+  }
+  ResetMinMaxKeysKernel<Key><<<1, 1, 0, stream>>>(keys.get());
+  const int threads = 256;
+  MergeFreeAndNamedKernel<Out, Key>
+      <<<static_cast<unsigned>((count + threads - 1) / threads), threads, 0, stream>>>(
+          d_free.get(), d_named.get(), count, d_free.get(), keys.get());
+  DecodeMinMaxKernel<Out, Key><<<1, 1, 0, stream>>>(keys.get(), d_min_max.get());
+  VGT_CUDA_TRY(cudaGetLastError(), "MergeFreeAndNamedKernel launch");
+  Out min_max[2];
+  VGT_CUDA_TRY(cudaMemcpyAsync(h_out, d_free.get(), sizeof(Out) * count, cudaMemcpyDeviceToHost,
+                               stream),
+               "copy SDF to host");
+  VGT_CUDA_TRY(cudaMemcpyAsync(min_max, d_min_max.get(), sizeof(Out) * 2, cudaMemcpyDeviceToHost,
+                               stream),
+               "copy min/max to host");
+  VGT_CUDA_TRY(cudaStreamSynchronize(stream), "free-and-named SDF generation");
+  if (out_min != nullptr)
+  {
+    *out_min = min_max[0];
+  }
+  if (out_max != nullptr)
+  {
+    *out_max = min_max[1];
+  }
+  return VGT_B200_OK;
+}
 }  // namespace
 }  // namespace edt
 }  // namespace vgt_b200
@@ -968,6 +1218,66 @@ int vgt_b200_sdf_from_mask_f64(
 {
   return SdfFromHost<uint8_t, kEmitDouble>(filled_mask, nx, ny, nz, resolution, 0,
                                            add_virtual_border, device, sdf_out, out_min, out_max);
+}
+
+int vgt_b200_sdf_from_cells_f32(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const uint32_t* object_ids,
+    int64_t num_object_ids, int device, float* sdf_out, float* out_min, float* out_max)
+{
+  return SdfFromCellsHost<kEmitFloat>(cells, cell_bytes, nx, ny, nz, resolution,
+                                      unknown_is_filled, add_virtual_border, object_ids,
+                                      num_object_ids, false, device, sdf_out, out_min, out_max);
+}
+
+int vgt_b200_sdf_from_cells_f64(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const uint32_t* object_ids,
+    int64_t num_object_ids, int device, double* sdf_out, double* out_min, double* out_max)
+{
+  return SdfFromCellsHost<kEmitDouble>(cells, cell_bytes, nx, ny, nz, resolution,
+                                       unknown_is_filled, add_virtual_border, object_ids,
+                                       num_object_ids, false, device, sdf_out, out_min, out_max);
+}
+
+int vgt_b200_sdf_per_object_f32(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const uint32_t* object_ids,
+    int64_t num_object_ids, int device, float* sdf_out, float* out_min, float* out_max)
+{
+  return SdfFromCellsHost<kEmitFloat>(cells, cell_bytes, nx, ny, nz, resolution,
+                                      unknown_is_filled, add_virtual_border, object_ids,
+                                      num_object_ids, true, device, sdf_out, out_min, out_max);
+}
+
+int vgt_b200_sdf_per_object_f64(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const uint32_t* object_ids,
+    int64_t num_object_ids, int device, double* sdf_out, double* out_min, double* out_max)
+{
+  return SdfFromCellsHost<kEmitDouble>(cells, cell_bytes, nx, ny, nz, resolution,
+                                       unknown_is_filled, add_virtual_border, object_ids,
+                                       num_object_ids, true, device, sdf_out, out_min, out_max);
+}
+
+int vgt_b200_sdf_free_and_named_f32(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, float* sdf_out, float* out_min,
+    float* out_max)
+{
+  return SdfFreeAndNamedHost<kEmitFloat>(cells, cell_bytes, nx, ny, nz, resolution,
+                                         unknown_is_filled, add_virtual_border, device, sdf_out,
+                                         out_min, out_max);
+}
+
+int vgt_b200_sdf_free_and_named_f64(
+    const void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, int device, double* sdf_out, double* out_min,
+    double* out_max)
+{
+  return SdfFreeAndNamedHost<kEmitDouble>(cells, cell_bytes, nx, ny, nz, resolution,
+                                          unknown_is_filled, add_virtual_border, device, sdf_out,
+                                          out_min, out_max);
 }
 
 int vgt_b200_edt_sq_i32(

@@ -10,6 +10,11 @@ reference's own (paths relative to the reference checkout):
   FromVoxelCounts; cell count = ceil(size / voxel_size), consistent with
   test/sdf_generation_test.cpp:267-272 -> 4 x 8 x 12)
 
+* ``OccupancyComponentMap``, ``TaggedObjectOccupancyMap``, ``TaggedObjectOccupancyComponentMap``
+  (SURVEY.md section 8f, rank 1): the cell layouts and the SDF entry points of
+  occupancy_component_map.hpp:270-306, tagged_object_occupancy_map.hpp:199-378 and
+  tagged_object_occupancy_component_map.hpp:360-575.
+
 Only what the occupancy -> SDF path needs is here: storage, the filled predicate's inputs, the
 Extract entry points and Lock()/min-max. Queries, gradients and serialization are out of scope.
 """
@@ -252,6 +257,175 @@ class OccupancyMap:
 
     def ExtractSignedDistanceFieldDouble(self, parameters, device: int = 0):
         return self.ExtractSignedDistanceField(parameters, np.float64, device)
+
+
+# Packed cell layouts of the other map types; the reference pins their sizes with static_asserts
+# (occupancy_component_map.hpp:66-71, tagged_object_occupancy_map.hpp:66-70,
+# tagged_object_occupancy_component_map.hpp:62-66).
+OCCUPANCY_COMPONENT_CELL = np.dtype([("occupancy", "<f4"), ("component", "<u4")])
+TAGGED_OBJECT_OCCUPANCY_CELL = np.dtype([("occupancy", "<f4"), ("object_id", "<u4")])
+TAGGED_OBJECT_OCCUPANCY_COMPONENT_CELL = np.dtype(
+    [("occupancy", "<f4"), ("object_id", "<u4"), ("component", "<u4"),
+     ("spatial_segment", "<u4")])
+
+
+class _CellGrid:
+    """A dense grid of packed cells indexed [x, y, z]; what the three maps below share."""
+
+    CELL = None
+
+    def __init__(self, origin_transform, frame: str, sizes: VoxelGridSizes,
+                 data: np.ndarray | None = None):
+        self._origin_transform = np.array(origin_transform, dtype=np.float64).reshape(4, 4)
+        self._frame = frame
+        self._sizes = sizes
+        if data is None:
+            self._data = np.zeros(sizes.shape, dtype=self.CELL)
+        else:
+            data = np.ascontiguousarray(data, dtype=self.CELL)
+            if data.shape != sizes.shape:
+                raise ValueError("data shape does not match the grid sizes")
+            self._data = data
+
+    def NumXVoxels(self):
+        return self._sizes.num_x_voxels
+
+    def NumYVoxels(self):
+        return self._sizes.num_y_voxels
+
+    def NumZVoxels(self):
+        return self._sizes.num_z_voxels
+
+    def ControlSizes(self):
+        return self._sizes
+
+    def Frame(self):
+        return self._frame
+
+    def OriginTransform(self):
+        return self._origin_transform
+
+    def HasUniformVoxelSize(self) -> bool:
+        return True
+
+    def GetMutableRawData(self) -> np.ndarray:
+        return self._data
+
+    def GetImmutableRawData(self) -> np.ndarray:
+        return self._data
+
+    # ------------------------------------------------------------------ shared plumbing
+    def _wrap(self, out, lo, hi, parameters):
+        sdf = SignedDistanceField(self._origin_transform, self._frame, self._sizes, out,
+                                  parameters.OOBValue(),
+                                  minimum_maximum=(out.dtype.type(lo), out.dtype.type(hi)))
+        sdf.Lock()
+        return sdf
+
+    def _from_cells(self, objects_to_use, parameters, dtype, device):
+        _capi.require_device(device)
+        suffix, scalar = _scalar_suffix(dtype)
+        ids = np.ascontiguousarray(list(objects_to_use), dtype=np.uint32)
+        out = np.empty(self._sizes.shape, dtype=dtype)
+        lo, hi = scalar(), scalar()
+        function = getattr(_capi.library(), "vgt_b200_sdf_from_cells_" + suffix)
+        code = function(self._data.ctypes.data, self.CELL.itemsize, *self._sizes.shape,
+                        self._sizes.voxel_size, int(parameters.UnknownIsFilled()),
+                        int(parameters.AddVirtualBorder()),
+                        ids.ctypes.data if ids.size else None, ids.size, device, out.ctypes.data,
+                        ctypes.byref(lo), ctypes.byref(hi))
+        _capi.check(code)
+        return self._wrap(out, lo.value, hi.value, parameters)
+
+
+def _scalar_suffix(dtype):
+    if np.dtype(dtype) == np.float32:
+        return "f32", ctypes.c_float
+    if np.dtype(dtype) == np.float64:
+        return "f64", ctypes.c_double
+    raise ValueError("SDF scalar type must be float32 or float64")
+
+
+class OccupancyComponentMap(_CellGrid):
+    """occupancy_component_map.hpp: cells {occupancy, component}; the component never enters the
+    SDF predicate (occupancy_component_map.hpp:270-306)."""
+
+    CELL = OCCUPANCY_COMPONENT_CELL
+
+    def ExtractSignedDistanceField(self, parameters, dtype=np.float32, device: int = 0):
+        return self._from_cells((), parameters, dtype, device)
+
+    def ExtractSignedDistanceFieldFloat(self, parameters, device: int = 0):
+        return self.ExtractSignedDistanceField(parameters, np.float32, device)
+
+    def ExtractSignedDistanceFieldDouble(self, parameters, device: int = 0):
+        return self.ExtractSignedDistanceField(parameters, np.float64, device)
+
+
+class TaggedObjectOccupancyMap(_CellGrid):
+    """tagged_object_occupancy_map.hpp: cells {occupancy, object_id}."""
+
+    CELL = TAGGED_OBJECT_OCCUPANCY_CELL
+
+    def ExtractSignedDistanceField(self, objects_to_use, parameters, dtype=np.float32,
+                                   device: int = 0):
+        """Filled = occupancy rule and (no objects listed or object id listed)
+        (tagged_object_occupancy_map.hpp:199-247)."""
+        return self._from_cells(objects_to_use, parameters, dtype, device)
+
+    def ExtractSignedDistanceFieldFloat(self, objects_to_use, parameters, device: int = 0):
+        return self.ExtractSignedDistanceField(objects_to_use, parameters, np.float32, device)
+
+    def ExtractSignedDistanceFieldDouble(self, objects_to_use, parameters, device: int = 0):
+        return self.ExtractSignedDistanceField(objects_to_use, parameters, np.float64, device)
+
+    def MakeSeparateObjectSDFs(self, object_ids, parameters, dtype=np.float32, device: int = 0):
+        """One SDF per object id, the cells uploaded once
+        (tagged_object_occupancy_map.hpp:249-262). Returns {object_id: SignedDistanceField}."""
+        _capi.require_device(device)
+        suffix, _ = _scalar_suffix(dtype)
+        ids = np.ascontiguousarray(list(object_ids), dtype=np.uint32)
+        if ids.size == 0:
+            return {}
+        out = np.empty((ids.size,) + self._sizes.shape, dtype=dtype)
+        lows = np.empty(ids.size, dtype=dtype)
+        highs = np.empty(ids.size, dtype=dtype)
+        function = getattr(_capi.library(), "vgt_b200_sdf_per_object_" + suffix)
+        code = function(self._data.ctypes.data, self.CELL.itemsize, *self._sizes.shape,
+                        self._sizes.voxel_size, int(parameters.UnknownIsFilled()),
+                        int(parameters.AddVirtualBorder()), ids.ctypes.data, ids.size, device,
+                        out.ctypes.data, lows.ctypes.data, highs.ctypes.data)
+        _capi.check(code)
+        return {int(object_id): self._wrap(out[k], lows[k], highs[k], parameters)
+                for k, object_id in enumerate(ids)}
+
+    def MakeAllObjectSDFs(self, parameters, dtype=np.float32, device: int = 0):
+        """Every object id > 0 present in the map (tagged_object_occupancy_map.hpp:264-291)."""
+        object_ids = np.unique(self._data["object_id"])
+        return self.MakeSeparateObjectSDFs([i for i in object_ids.tolist() if i > 0], parameters,
+                                           dtype, device)
+
+    def ExtractFreeAndNamedObjectsSignedDistanceField(self, parameters, dtype=np.float32,
+                                                      device: int = 0):
+        """tagged_object_occupancy_map.hpp:293-378."""
+        _capi.require_device(device)
+        suffix, scalar = _scalar_suffix(dtype)
+        out = np.empty(self._sizes.shape, dtype=dtype)
+        lo, hi = scalar(), scalar()
+        function = getattr(_capi.library(), "vgt_b200_sdf_free_and_named_" + suffix)
+        code = function(self._data.ctypes.data, self.CELL.itemsize, *self._sizes.shape,
+                        self._sizes.voxel_size, int(parameters.UnknownIsFilled()),
+                        int(parameters.AddVirtualBorder()), device, out.ctypes.data,
+                        ctypes.byref(lo), ctypes.byref(hi))
+        _capi.check(code)
+        return self._wrap(out, lo.value, hi.value, parameters)
+
+
+class TaggedObjectOccupancyComponentMap(TaggedObjectOccupancyMap):
+    """tagged_object_occupancy_component_map.hpp: 16-byte cells {occupancy, object_id, component,
+    spatial_segment}; the same SDF entry points (:360-575)."""
+
+    CELL = TAGGED_OBJECT_OCCUPANCY_COMPONENT_CELL
 
 
 def ExtractSignedDistanceFieldFromMask(filled_mask: np.ndarray, origin_transform, frame: str,
