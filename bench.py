@@ -368,6 +368,11 @@ def run_ours(args):
         other_configs["config1_note"] = ("8 MiB per buffer: L2-resident, so a time, not a "
                                          "roofline fraction (SURVEY.md section 8d)")
 
+    # ---- per-object SDF batch of a tagged map through the host entry ----
+    other_map_types = None
+    if not distributed:
+        other_map_types = bench_tagged_map(local_rank, include_cpu=not args.skip_cpu)
+
     cpu_baseline = None
     if rank == 0 and not distributed and not args.skip_cpu:
         full = cpu_reference_arm(1, 0)
@@ -396,9 +401,52 @@ def run_ours(args):
             line["voxelizer"] = voxelizer
         if other_configs is not None:
             line["other_configs"] = other_configs
+        if other_map_types is not None:
+            line["other_map_types"] = other_map_types
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
+
+
+def bench_tagged_map(device_index, include_cpu=True):
+    """TaggedObjectOccupancyMap::MakeSeparateObjectSDFs over a 256^3 map with 8 named objects
+    (tagged_object_occupancy_map.hpp:249-262) and ExtractFreeAndNamedObjectsSignedDistanceField,
+    host buffers in and out (vgt_b200_sdf_per_object_f32 / vgt_b200_sdf_free_and_named_f32)."""
+    import numpy as np
+    import voxelized_geometry_tools_b200 as vgt
+    from voxelized_geometry_tools_b200 import grids, synthetic
+    n, objects = 256, 8
+    occupancy = synthetic.clustered_spheres_occupancy((n, n, n))
+    cells = np.zeros((n, n, n), dtype=grids.TAGGED_OBJECT_OCCUPANCY_CELL)
+    cells["occupancy"] = occupancy
+    block = np.add.outer(np.add.outer(np.arange(n) // 64, np.arange(n) // 64 * 2),
+                         np.arange(n) // 128)
+    cells["object_id"] = (block % objects + 1).astype(np.uint32)
+    sizes = vgt.VoxelGridSizes.FromVoxelCounts(RESOLUTION, (n, n, n))
+    tagged = vgt.TaggedObjectOccupancyMap(np.eye(4), "world", sizes, cells)
+    parameters = vgt.SignedDistanceFieldGenerationParameters()
+    ids = list(range(1, objects + 1))
+    tagged.MakeSeparateObjectSDFs(ids[:2], parameters, device=device_index)
+    begin = time.perf_counter()
+    tagged.MakeSeparateObjectSDFs(ids, parameters, device=device_index)
+    batch_seconds = time.perf_counter() - begin
+    begin = time.perf_counter()
+    tagged.ExtractFreeAndNamedObjectsSignedDistanceField(parameters, device=device_index)
+    merged_seconds = time.perf_counter() - begin
+    voxels = float(n) ** 3
+    result = {"grid": f"{n}^3 TaggedObjectOccupancyMap, {objects} objects",
+              "per_object_batch_ms": batch_seconds * 1e3,
+              "per_object_batch_gvoxels_per_s": objects * voxels / batch_seconds / 1e9,
+              "free_and_named_ms": merged_seconds * 1e3,
+              "api": "MakeSeparateObjectSDFs / ExtractFreeAndNamedObjectsSignedDistanceField "
+                     "(host buffers, pageable numpy arrays)"}
+    if include_cpu:
+        from oracle import oracle
+        begin = time.perf_counter()
+        oracle.sdf_from_cells(cells, RESOLUTION, objects_to_use=[1], threads=0)
+        result["cpu_one_object_ms"] = (time.perf_counter() - begin) * 1e3
+        result["cpu_cores"] = oracle.max_threads()
+    return result
 
 
 def bench_voxelizer(dev, peak, include_cpu=True):
