@@ -28,7 +28,7 @@ namespace
 {
 // kIterations = ceil(length / 128) rounded up to 1, 2, 4 or 8 (so at most 32 words per line).
 template <typename Source, int kIterations>
-__global__ void __launch_bounds__(kScanWarpsPerBlock* kWarp) ScanContiguousAxisRegistersKernel(
+__global__ void __launch_bounds__(kScanWarpsPerBlock* kWarp, 8) ScanContiguousAxisRegistersKernel(
     const typename Source::Vector* __restrict__ in, uint4* __restrict__ out, int64_t num_lines,
     int32_t length, int unknown_is_filled)
 {
