@@ -79,23 +79,26 @@ __global__ void CellsToMaskKernel(const uint32_t* __restrict__ cells, int cell_w
 
 // ExtractFreeAndNamedObjectsSignedDistanceField's merge (tagged_object_occupancy_map.hpp:344-369):
 //   free >= 0 -> free;  else named <= -0 -> named;  else 0.   Then Lock()'s min/max.
+// Grid-stride: a fixed grid, so the min/max atomics are two per warp of the grid, not two per
+// 32 voxels (all to the same two addresses, which the L2 serialises).
 template <typename Out, typename Key>
 __global__ void MergeFreeAndNamedKernel(const Out* __restrict__ free_sdf,
                                         const Out* __restrict__ named_sdf, int64_t count,
                                         Out* __restrict__ combined, Key* min_max_keys)
 {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  Out value = PositiveInfinity<Out>();
   Out low = PositiveInfinity<Out>();
   Out high = -PositiveInfinity<Out>();
-  if (i < count)
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+       i += stride)
   {
     const Out free_value = free_sdf[i];
     const Out named_value = named_sdf[i];
-    value = (free_value >= Out(0)) ? free_value : ((named_value <= Out(0)) ? named_value : Out(0));
+    const Out value =
+        (free_value >= Out(0)) ? free_value : ((named_value <= Out(0)) ? named_value : Out(0));
     combined[i] = value;
-    low = value;
-    high = value;
+    low = (value < low) ? value : low;
+    high = (value > high) ? value : high;
   }
   Key key_min = OrderedKey(low);
   Key key_max = OrderedKey(high);

@@ -964,8 +964,9 @@ int SdfFreeAndNamedHost(const void* h_cells, int cell_bytes, int64_t nx, int64_t
   }
   ResetMinMaxKeysKernel<Key><<<1, 1, 0, stream>>>(keys.get());
   const int threads = 256;
-  MergeFreeAndNamedKernel<Out, Key>
-      <<<static_cast<unsigned>((count + threads - 1) / threads), threads, 0, stream>>>(
+  const int64_t merge_blocks =
+      std::min<int64_t>((count + threads - 1) / threads, MultiprocessorCount() * 16);
+  MergeFreeAndNamedKernel<Out, Key><<<static_cast<unsigned>(merge_blocks), threads, 0, stream>>>(
           d_free.get(), d_named.get(), count, d_free.get(), keys.get());
   DecodeMinMaxKernel<Out, Key><<<1, 1, 0, stream>>>(keys.get(), d_min_max.get());
   VGT_CUDA_TRY(cudaGetLastError(), "MergeFreeAndNamedKernel launch");
