@@ -317,6 +317,27 @@ def run_ours(args):
                "h2d_bytes_per_step": int(4 * voxels), "d2h_bytes_per_step": int(4 * voxels + 8),
                "ms_per_step": e2e_seconds * 1e3,
                "api": "vgt_b200_sdf_f32 (host pointers, pinned)"}
+        # the same call with PAGEABLE buffers (what std::vector / numpy callers hand over): the
+        # library stages them through pinned slots with several host threads
+        pageable_in = host_in.numpy().copy()
+        pageable_out = np.empty_like(pageable_in)
+
+        def pageable_step():
+            code = lib.vgt_b200_sdf_f32(pageable_in.ctypes.data, *local_shape, RESOLUTION, 1, 0,
+                                        local_rank, pageable_out.ctypes.data, ctypes.byref(lo),
+                                        ctypes.byref(hi))
+            _capi.check(code)
+
+        for _ in range(2):
+            pageable_step()
+        begin = time.perf_counter()
+        for _ in range(e2e_steps):
+            pageable_step()
+        pageable_seconds = (time.perf_counter() - begin) / e2e_steps
+        e2e["pageable_buffers"] = {"value": voxels / pageable_seconds / 1e9,
+                                   "unit": "Gvoxels/s", "ms_per_step": pageable_seconds * 1e3,
+                                   "equals_pinned_result": bool(
+                                       np.array_equal(pageable_out, host_out.numpy()))}
     else:
         # Per-rank host slabs in, y-slabs out, through the sharded public API; pinned buffers on
         # both sides (as at N=1), reused across steps.

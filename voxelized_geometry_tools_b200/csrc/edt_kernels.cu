@@ -9,6 +9,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "host_transfer.cuh"
 #include "edt_device.cuh"
 #include "edt_envelope_inplace.cuh"
 #include "edt_envelope_lean.cuh"
@@ -590,6 +591,8 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
   VGT_CUDA_TRY(cudaStreamWaitEvent(copy_out.stream, allocated.event, 0), "stream wait");
 
   uint32_t* const d_front = reinterpret_cast<uint32_t*>(d_out.get());
+  // pageable caller buffers go through pinned slots filled / drained by several host threads
+  StagedTransfer transfer;
   const int in_chunks = static_cast<int>(nx < kPipelineChunks ? nx : kPipelineChunks);
   EventGuard arrived[kPipelineChunks];
   int status = VGT_B200_OK;
@@ -597,10 +600,13 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
   {
     const int64_t x0 = nx * c / in_chunks;
     const int64_t x1 = nx * (c + 1) / in_chunks;
-    VGT_CUDA_TRY(cudaMemcpyAsync(d_in.get() + x0 * plane, h_in + x0 * plane,
-                                 sizeof(In) * (x1 - x0) * plane, cudaMemcpyHostToDevice,
-                                 copy_in.stream),
-                 "copy grid slab to device");
+    {
+      const size_t slab_bytes = sizeof(In) * static_cast<size_t>((x1 - x0) * plane);
+      VGT_CUDA_TRY(transfer.ToDevice(reinterpret_cast<char*>(d_in.get() + x0 * plane), slab_bytes,
+                                     reinterpret_cast<const char*>(h_in + x0 * plane), slab_bytes,
+                                     slab_bytes, 1, copy_in.stream),
+                   "copy grid slab to device");
+    }
     VGT_CUDA_TRY(cudaEventCreateWithFlags(&arrived[c].event, cudaEventDisableTiming), "event");
     VGT_CUDA_TRY(cudaEventRecord(arrived[c].event, copy_in.stream), "event record");
     VGT_CUDA_TRY(cudaStreamWaitEvent(compute.stream, arrived[c].event, 0), "stream wait");
@@ -631,6 +637,8 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
   }
   const int out_chunks = static_cast<int>(ny < kPipelineChunks ? ny : kPipelineChunks);
   EventGuard finished[kPipelineChunks];
+  // every y-slab of the final pass is enqueued first (the compute stream never waits for the
+  // host), then the slabs are copied out in order, each as soon as its pass has finished
   for (int c = 0; c < out_chunks && status == VGT_B200_OK; c++)
   {
     const int64_t y0 = ny * c / out_chunks;
@@ -644,12 +652,6 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
     }
     VGT_CUDA_TRY(cudaEventCreateWithFlags(&finished[c].event, cudaEventDisableTiming), "event");
     VGT_CUDA_TRY(cudaEventRecord(finished[c].event, compute.stream), "event record");
-    VGT_CUDA_TRY(cudaStreamWaitEvent(copy_out.stream, finished[c].event, 0), "stream wait");
-    VGT_CUDA_TRY(cudaMemcpy2DAsync(h_out + y0 * nz, sizeof(Out) * plane, d_out.get() + y0 * nz,
-                                   sizeof(Out) * plane, sizeof(Out) * (y1 - y0) * nz,
-                                   static_cast<size_t>(nx), cudaMemcpyDeviceToHost,
-                                   copy_out.stream),
-                 "copy SDF slab to host");
   }
   Out min_max[2];
   if (status == VGT_B200_OK)
@@ -657,6 +659,18 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
     DecodeMinMaxKernel<Out, Key><<<1, 1, 0, compute.stream>>>(keys.get(), d_min_max.get());
     cudaMemcpyAsync(min_max, d_min_max.get(), sizeof(Out) * 2, cudaMemcpyDeviceToHost,
                     compute.stream);
+  }
+  for (int c = 0; c < out_chunks && status == VGT_B200_OK; c++)
+  {
+    const int64_t y0 = ny * c / out_chunks;
+    const int64_t y1 = ny * (c + 1) / out_chunks;
+    VGT_CUDA_TRY(cudaStreamWaitEvent(copy_out.stream, finished[c].event, 0), "stream wait");
+    // rows = x planes, one row = the slab's (y1 - y0) * nz values (a strided 2-D copy)
+    VGT_CUDA_TRY(transfer.ToHost(reinterpret_cast<char*>(h_out + y0 * nz), sizeof(Out) * plane,
+                                 reinterpret_cast<const char*>(d_out.get() + y0 * nz),
+                                 sizeof(Out) * plane, sizeof(Out) * (y1 - y0) * nz,
+                                 static_cast<size_t>(nx), copy_out.stream),
+                 "copy SDF slab to host");
   }
   const cudaError_t sync_in = cudaStreamSynchronize(copy_in.stream);
   const cudaError_t sync_compute = cudaStreamSynchronize(compute.stream);
