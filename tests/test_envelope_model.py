@@ -270,3 +270,116 @@ def test_smooth_distance_like_lines():
         assert kernel_line(classes, values) == brute_line(classes, values)
         assert lean_line(classes, values) == brute_line(classes, values)
 
+
+
+# ------------------------------------------------------------------------------------------------
+# Window kernel (csrc/edt_envelope_window.cuh): per voxel a class-agnostic min over the rows
+# within R of it plus the nearest opposite-class row from a class-bit window; a result below
+# (R + 1)^2 is exact by construction (every row outside the window costs at least (R + 1)^2),
+# anything else takes the extended search. Mirrors the kernel's chunking and bit arithmetic.
+# ------------------------------------------------------------------------------------------------
+def clz32(x):
+    return 32 - x.bit_length()
+
+
+def brev32(x):
+    return int(format(x & 0xFFFFFFFF, "032b")[::-1], 2)
+
+
+def window_line(classes, values, radius, step_budget=None):
+    """Returns (out, steps) or (None, steps) when the extended search ran past its budget."""
+    n = len(classes)
+    chunk = radius
+    far = (radius + 1) ** 2
+    steps = 0
+
+    def load_chunk(k):
+        # rows k*chunk .. k*chunk+chunk-1; out-of-range rows: NONE with the class of the clamped row
+        vals, bits = [], 0
+        for i in range(chunk):
+            r = k * chunk + i
+            rc = min(max(r, 0), n - 1)
+            vals.append(values[rc] if 0 <= r < n else NONE)
+            bits = ((bits << 1) | classes[rc]) & 0xFFFFFFFF
+        return vals, bits
+
+    def extended(q, best):
+        # four distances per round, rows clamped to the line, no class / range predicates:
+        # a clamped row was already seen at its true, smaller distance
+        nonlocal steps
+        d = radius + 1
+        reach = max(q, n - 1 - q)
+        while d * d < best and d <= reach:
+            steps += 4
+            for u in range(4):
+                for r in (max(q - d - u, 0), min(q + d + u, n - 1)):
+                    height = values[r] if classes[r] == classes[q] else 0
+                    best = min(best, height + (d + u) ** 2)
+            d += 4
+        return best
+
+    out = [0] * n
+    num_chunks = (n + chunk - 1) // chunk
+    a, ca = load_chunk(-1)
+    b, cb = load_chunk(0)
+    nx, cn = load_chunk(1)
+    mask_r = (1 << radius) - 1
+    for k in range(num_chunks):
+        composite = (ca << (2 * chunk)) | (cb << chunk) | cn
+        rows = a + b + nx  # chunk-relative row r at index r + chunk
+        for j in range(chunk):
+            q = k * chunk + j
+            if q >= n:
+                break
+            acc = b[j]
+            for d in range(1, radius + 1):
+                acc = min(acc, rows[chunk + j - d] + d * d)
+                acc = min(acc, rows[chunk + j + d] + d * d)
+            x = (composite >> (chunk - 1 - j)) & 0xFFFFFFFF
+            query_class = (x >> radius) & 1
+            assert query_class == classes[q]
+            diff = x ^ (0xFFFFFFFF if query_class else 0)
+            both = ((diff & mask_r) | (brev32(diff) >> (31 - 2 * radius))) & mask_r
+            e = radius - 31 + clz32(both)
+            w = min(acc, e * e)
+            if w >= far:
+                # (then no opposite-class row is inside the window and e was the "none" value,
+                # so the search starts from the window minimum alone)
+                assert both == 0
+                w = extended(q, min(acc, NONE))
+                if step_budget is not None and steps > step_budget:
+                    return None, steps
+            out[q] = min(w, NONE)
+        a, ca = b, cb
+        b, cb = nx, cn
+        nx, cn = load_chunk(k + 2)
+    return out, steps
+
+
+def test_window_line_model_matches_brute_force():
+    rng = random.Random(3)
+    for _ in range(4000):
+        n = rng.choice([1, 2, 3, 4, 5, 7, 12, 13, 24, 25, 31, 32, 33, 36, 40, 64, 65, 97])
+        classes, values = random_line(rng, n)
+        want = brute_line(classes, values)
+        for radius in (4, 8, 12, 15):
+            got, _ = window_line(classes, values, radius)
+            assert got == want, (radius, classes, values)
+
+
+def test_window_line_smooth_and_budget():
+    rng = random.Random(4)
+    for _ in range(200):
+        n = rng.choice([64, 100, 130])
+        centre, offset = rng.uniform(0, n), rng.randint(1, 50)
+        classes = [1 if abs(i - n / 3) < 4 else 0 for i in range(n)]
+        values = [int((i - centre) ** 2) + offset for i in range(n)]
+        want = brute_line(classes, values)
+        got, steps = window_line(classes, values, 8)
+        assert got == want
+        # a budget below the steps taken reports the line for the stack kernel instead
+        if steps > 0:
+            assert window_line(classes, values, 8, step_budget=steps - 4)[0] is None
+    # one class, no values at all: every result is NONE and the search stops at the line ends
+    got, steps = window_line([0] * 50, [NONE] * 50, 8)
+    assert got == [NONE] * 50 and steps <= 50 * 50

@@ -1,0 +1,75 @@
+"""GPU: the window kernel (csrc/edt_envelope_window.cuh) on each of its three routes - rows that
+certify inside the register window, rows that take the extended search, tiles handed to the stack
+kernel - against the oracle, bit for bit. The routes are forced with the library's A/B switches
+(read at every call): VGT_B200_WINDOW_BUDGET (extended-search steps a warp may spend per 100 rows of
+its tile; 0 sends every tile with an uncertain row to the stack kernel, a huge value
+keeps everything in the window kernel) and VGT_B200_ENVELOPE=lean (no window kernel at all)."""
+import os
+
+import numpy as np
+import pytest
+
+from voxelized_geometry_tools_b200 import synthetic
+
+from .conftest import random_occupancy
+from .test_gpu_sdf import assert_matches_oracle
+
+pytestmark = pytest.mark.gpu
+
+ROUTES = [{"VGT_B200_WINDOW_BUDGET": "0"}, {"VGT_B200_WINDOW_BUDGET": "1000000"},
+          {"VGT_B200_WINDOW_BUDGET": "25"}, {"VGT_B200_ENVELOPE": "lean"}, {}]
+
+
+@pytest.fixture(params=ROUTES, ids=lambda route: ",".join(f"{k}={v}" for k, v in route.items())
+                or "default")
+def route(request):
+    saved = {key: os.environ.get(key) for key in ("VGT_B200_WINDOW_BUDGET", "VGT_B200_ENVELOPE")}
+    for key in saved:
+        os.environ.pop(key, None)
+    os.environ.update(request.param)
+    yield request.param
+    for key, value in saved.items():
+        os.environ.pop(key, None)
+        if value is not None:
+            os.environ[key] = value
+
+
+def test_cluttered_grid(shared_library, oracle, route):
+    # distances of a few voxels nearly everywhere: the certified route
+    occupancy = synthetic.clustered_spheres_occupancy((96, 80, 72))
+    assert_matches_oracle(oracle, occupancy, 0.02)
+    assert_matches_oracle(oracle, occupancy, 0.02, add_virtual_border=True)
+    assert_matches_oracle(oracle, occupancy, 0.02, dtype=np.float64)
+
+
+def test_sparse_and_empty_grids(shared_library, oracle, route):
+    # distances far beyond the window: extended search or the stack kernel; an empty and a full
+    # grid (no opposite class anywhere: every value is infinite)
+    rng = np.random.default_rng(5)
+    occupancy = np.zeros((70, 45, 50), dtype=np.float32)
+    occupancy[rng.integers(0, 70, 6), rng.integers(0, 45, 6), rng.integers(0, 50, 6)] = 1.0
+    assert_matches_oracle(oracle, occupancy, 0.05)
+    assert_matches_oracle(oracle, 1.0 - occupancy, 0.05, add_virtual_border=True)
+    assert_matches_oracle(oracle, np.zeros((13, 30, 17), dtype=np.float32), 0.05)
+    assert_matches_oracle(oracle, np.ones((13, 30, 17), dtype=np.float32), 0.05,
+                          add_virtual_border=True)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 5), (2, 3, 4), (7, 1, 33), (1, 13, 40), (12, 24, 36),
+                                   (13, 25, 37), (11, 23, 35), (8, 16, 33), (9, 17, 31),
+                                   (40, 100, 31), (100, 37, 65)])
+def test_line_lengths_around_the_chunk_size(shared_library, oracle, route, shape):
+    # chunk sizes are 12 (y) and 8 (x): lengths below, at and just past multiples of them,
+    # column counts that are not multiples of 32 (shadow lanes)
+    rng = np.random.default_rng(sum(shape))
+    for fill in (0.03, 0.4):
+        occupancy = random_occupancy(rng, shape, fill)
+        assert_matches_oracle(oracle, occupancy, 0.1)
+        assert_matches_oracle(oracle, occupancy, 0.1, add_virtual_border=True, dtype=np.float64)
+
+
+def test_box_scene_and_blobs(shared_library, oracle, route):
+    assert_matches_oracle(oracle, synthetic.box_scene(64), 0.02)
+    rng = np.random.default_rng(11)
+    occupancy = random_occupancy(rng, (60, 130, 90), 0.08, blobs=True)
+    assert_matches_oracle(oracle, occupancy, 0.02)

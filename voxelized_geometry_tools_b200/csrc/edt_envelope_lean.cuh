@@ -93,7 +93,8 @@ template <int kMode, bool kNarrow, bool kSend, bool kBorder, bool kSplit, int kB
 __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     EnvelopeAxisLeanKernel(uint32_t* in, typename OutputOf<kMode>::Type* out, uint16_t* positions,
                            uint32_t* class_scratch, LineFamily family, FinalizeParams finalize,
-                           typename OutputOf<kMode>::Key* min_max_keys)
+                           typename OutputOf<kMode>::Key* min_max_keys,
+                           const uint32_t* redo_list)
 {
   using Out = typename OutputOf<kMode>::Type;
   const int warp = threadIdx.x >> 5;
@@ -103,8 +104,18 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
 
   // (the launcher guarantees that tile, line and column counts fit 31 bits)
   const uint32_t tiles_per_outer = static_cast<uint32_t>((family.inner_count + kWarp - 1) / kWarp);
-  const uint32_t tile_index = blockIdx.x * kLineWarpsPerBlock + warp;
-  if (tile_index >= tiles_per_outer * static_cast<uint32_t>(family.num_outer))
+  uint32_t tile_index = blockIdx.x * kLineWarpsPerBlock + warp;
+  if (redo_list != nullptr)
+  {
+    // second launch after the window kernel (edt_envelope_window.cuh): only the tiles it gave up
+    // on; word 0 = how many, words 1.. = their indices
+    if (tile_index >= redo_list[0])
+    {
+      return;  // warp-uniform
+    }
+    tile_index = redo_list[1 + tile_index];
+  }
+  else if (tile_index >= tiles_per_outer * static_cast<uint32_t>(family.num_outer))
   {
     return;  // warp-uniform
   }

@@ -1,0 +1,407 @@
+// The strided-axis WINDOW kernel (sm_100a): the common case of the y / x passes without a stack.
+// Included by edt_kernels.cu after edt_envelope_lean.cuh.
+//
+// The 1-D transform of a line is D(q) = min over rows i of G(i) + (q - i)^2, where G(i) is the
+// partial squared distance of row i when it has the class of row q and 0 when it has the other
+// class (sdfgen.cpp:85-226 computes exactly this for each of the reference's two fields). Two
+// observations make most of it a fixed, branch-free amount of work:
+//   * the class-agnostic minimum T(q) = min_i g(i) + (q - i)^2 over ALL rows differs from D(q)
+//     only by the opposite-class rows, and those enter D(q) as (q - i)^2, whose minimum is e^2
+//     with e the distance to the NEAREST opposite-class row: D(q) = min(T(q), e^2);
+//   * a row further than R from q contributes at least (R + 1)^2. So the minimum W(q) over the
+//     rows within R of q is the exact D(q) whenever W(q) < (R + 1)^2 - it certifies itself.
+// Here one lane owns one line (a warp = 32 adjacent lines, every row access is one 128-byte
+// segment, as in the stack kernels) and keeps the 3 R rows around the current chunk of R rows in
+// registers, so T costs one VIADDMNMX per candidate row (2 R per voxel, the squared offsets are
+// immediates) and e comes from a class-bit window with one BREV and one FLO. No shared memory,
+// no scratch, the input is read once and not modified: 4 B in + 4 B out per voxel.
+//
+// Rows that do not certify (distance to the opposite class > R voxels) continue the same search
+// outwards, row pair by row pair, until d^2 reaches the best value so far - exact for any input
+// but O(distance) per voxel, so the warp counts those steps and, past its budget, hands its tile
+// to the stack kernel (EnvelopeAxisLeanKernel over the redo list) instead. Distance fields of
+// cluttered maps (distances of a few voxels nearly everywhere) stay on the fast path; open
+// terrain goes to the stack kernel after a bounded amount of wasted work.
+//
+// Replaces the same reference loops as the stack kernels: the X / Y loops of
+// ComputeDistanceFieldTransformInPlace (sdfgen.cpp:276-351) with the 1-D transforms
+// (sdfgen.cpp:85-226) for both fields at once; in finalize mode also the combine loop
+// (sdfgen.hpp:85-108) and Lock()'s min/max (sdf.hpp:765-787).
+#pragma once
+
+#include "edt_device.cuh"
+#include "edt_envelope_lean.cuh"
+
+namespace vgt_b200
+{
+namespace edt
+{
+namespace
+{
+// Window radius and resident blocks (of 4 warps) per SM for the packed (y) pass and the
+// finalizing (x) pass: the in-plane distances the y pass sees are larger than the final ones.
+constexpr int kWindowRadiusPacked = 12;
+constexpr int kWindowBlocksPacked = 6;
+constexpr int kWindowRadiusFinal = 8;
+constexpr int kWindowBlocksFinal = 8;
+// A row whose search passes this distance is in open space, where the stack kernel is the better
+// tool: its tile is given up at once, whatever the step allowance says.
+constexpr int kDeepestSearch = 64;
+
+// Continues the search of one row beyond the register window: rows q - d and q + d for
+// d = first_d, first_d + 1, ... while d^2 can still improve on `best`. Convergent and branch-free
+// inside: EVERY lane of the warp evaluates every candidate, four distances per vote. That is
+// harmless for the lanes that need nothing: a candidate at distance d is at least d^2, and a lane
+// is only done once d^2 >= its best (a certified lane's best is below first_d^2 from the start),
+// so such a candidate never wins. Rows past the ends of the line are clamped to the end rows:
+// the end row was already seen at its true, smaller distance, so the clamped candidate never
+// wins either. Gives up (returns with the step counter past the budget, the caller then hands
+// the tile to the stack kernel) once the counter passes the budget or d passes kDeepestSearch.
+__device__ __noinline__ uint32_t ExtendedRowSearch(const char* line, uint32_t stride_bytes, int q,
+                                                   int last_row, uint32_t class_bit, uint32_t best,
+                                                   bool uncertain, int first_d, uint32_t budget,
+                                                   uint32_t* steps)
+{
+  constexpr int kUnroll = 4;
+  int d = first_d;
+  uint32_t used = *steps;
+  // the furthest row of the line from q: nothing to find beyond it
+  const int reach = max(q, last_row - q);
+  while (true)
+  {
+    const bool need = uncertain && static_cast<uint32_t>(d * d) < best && d <= reach;
+    if (!__any_sync(0xffffffffu, need))
+    {
+      break;
+    }
+    if (used > budget || d > kDeepestSearch)
+    {
+      used = max(used, budget + 1u);  // the caller gives the tile up
+      break;
+    }
+    used += kUnroll;
+    uint32_t words_below[kUnroll], words_above[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++)
+    {
+      const int below = __viaddmax_s32(q, -(d + u), 0);
+      const int above = __viaddmin_s32(q, d + u, last_row);
+      words_below[u] = *reinterpret_cast<const uint32_t*>(
+          line + static_cast<uint64_t>(static_cast<uint32_t>(below)) * stride_bytes);
+      words_above[u] = *reinterpret_cast<const uint32_t*>(
+          line + static_cast<uint64_t>(static_cast<uint32_t>(above)) * stride_bytes);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++)
+    {
+      const uint32_t dd = static_cast<uint32_t>((d + u) * (d + u));
+      const uint32_t height_below =
+          static_cast<uint32_t>(max(static_cast<int32_t>(words_below[u] ^ class_bit), 0));
+      const uint32_t height_above =
+          static_cast<uint32_t>(max(static_cast<int32_t>(words_above[u] ^ class_bit), 0));
+      best = __viaddmin_u32(height_below, dd, best);
+      best = __viaddmin_u32(height_above, dd, best);
+    }
+    d += kUnroll;
+  }
+  *steps = used;
+  return best;
+}
+
+// Work split: blockIdx.x = group of 4 tiles, blockIdx.y = segment of segment_rows rows (a
+// multiple of R) of their lines. Redo list layout: word 0 = number of tiles, words 1 .. T = tile
+// indices, words T + 1 .. 2 T = per-tile "already listed" flags (T = number of tiles); the
+// launcher zeroes word 0 and the flags.
+template <int kMode, int kR, bool kBorder, int kBlocksPerSm>
+__global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
+    EnvelopeAxisWindowKernel(const uint32_t* __restrict__ in,
+                             typename OutputOf<kMode>::Type* __restrict__ out, LineFamily family,
+                             FinalizeParams finalize, typename OutputOf<kMode>::Key* min_max_keys,
+                             uint32_t* redo, uint32_t step_rate, int segment_rows)
+{
+  using Out = typename OutputOf<kMode>::Type;
+  static_assert(kR >= 2 && kR <= 15, "the class window is one 32-bit word: 2 R + 1 <= 31 bits");
+  constexpr uint32_t kFar = static_cast<uint32_t>((kR + 1) * (kR + 1));
+  constexpr uint32_t kSideMask = (1u << kR) - 1u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int length = family.length;
+  const int last_row = static_cast<int>(family.last_row);
+
+  const uint32_t tiles_per_outer = static_cast<uint32_t>((family.inner_count + kWarp - 1) / kWarp);
+  const uint32_t tile_index = blockIdx.x * kLineWarpsPerBlock + warp;
+  if (tile_index >= tiles_per_outer * static_cast<uint32_t>(family.num_outer))
+  {
+    return;  // warp-uniform
+  }
+  const uint32_t outer = tile_index / tiles_per_outer;
+  const uint32_t wanted_column = (tile_index - outer * tiles_per_outer) * kWarp + lane;
+  const bool active = wanted_column < static_cast<uint32_t>(family.inner_count);
+  // Lanes past the last column shadow the last one (loads only), so that the whole warp stays
+  // converged for the votes.
+  const uint32_t column = active ? wanted_column : static_cast<uint32_t>(family.inner_count - 1);
+  const int64_t first = static_cast<int64_t>(outer) * family.outer_stride + column;
+  const uint32_t stride_bytes = family.stride_bytes;
+  // (pinned in registers: the compiler otherwise re-derives both from the kernel parameters at
+  // every use inside the unrolled chunk bodies)
+  const char* line = reinterpret_cast<const char*>(in + first);
+  asm volatile("" : "+l"(line));
+  const auto load_row = [&](int row)
+  {
+    return *reinterpret_cast<const uint32_t*>(
+        line + static_cast<uint64_t>(static_cast<uint32_t>(row)) * stride_bytes);
+  };
+  char* write_origin = reinterpret_cast<char*>(out + first);
+  asm volatile("" : "+l"(write_origin));
+  const uint32_t out_stride_bytes = family.out_stride_bytes;
+
+  Out lane_min = PositiveInfinity<Out>();
+  Out lane_max = -PositiveInfinity<Out>();
+  int32_t border_yz = 0x7fffffff;
+  if constexpr (kBorder)
+  {
+    const int32_t y = finalize.y_offset + static_cast<int32_t>(column / finalize.nz);
+    const int32_t z = static_cast<int32_t>(column % finalize.nz);
+    if (finalize.ny_total > 1)
+    {
+      border_yz = min(border_yz, min(y + 1, finalize.ny_total - y));
+    }
+    if (finalize.nz_total > 1)
+    {
+      border_yz = min(border_yz, min(z + 1, finalize.nz_total - z));
+    }
+  }
+
+  // The three chunks of R rows around the rows being computed: values with the class bit
+  // stripped (kNone = no distance yet, also used for rows outside the line). Rows outside the
+  // line repeat the class of the nearest row of the line, so they never read as the nearest
+  // opposite-class row.
+  uint32_t previous_values[kR], current_values[kR], next_values[kR];
+  // Class bits of the three chunks: bit 3 R - 1 - r' = class of row r' counted from the first
+  // row of the previous chunk. The bits of the next chunk enter row by row (see below); bits
+  // above 3 R are leftovers of older chunks and never reach a window.
+  uint64_t classes = 0;
+  // The rows of the next chunk as loaded. Row j of it is needed from row j of the current chunk
+  // on, so it is absorbed (stripped, class bit filed) right there and its register reloaded with
+  // the row one chunk further at once: every load has a whole chunk of work to land.
+  uint32_t raw[kR];
+
+  const auto load_clamped = [&](const int row) { return load_row(min(max(row, 0), last_row)); };
+
+  // Extended-search steps of this warp so far (warp-uniform) and whether they have passed the
+  // allowance of step_rate / 128 steps per row done (plus a credit of a quarter segment), or a
+  // row turned out deeper than kDeepestSearch: the tile then goes to the stack kernel.
+  uint32_t steps = 0;
+  bool over_budget = false;
+  const int first_row = static_cast<int>(blockIdx.y) * segment_rows;
+  const int end_row = min(first_row + segment_rows, length);
+  if (first_row >= length)
+  {
+    return;  // warp-uniform
+  }
+  const uint32_t credit_rows = static_cast<uint32_t>(segment_rows >> 2) + 16u;
+
+  // one row of the output; write_base = address of the chunk's first output row
+  const auto emit_row = [&](const int q, const int j, char* const write_base, const uint32_t filled,
+                            uint32_t squared)
+  {
+    char* const write_at = write_base + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(j);
+    if constexpr (kMode == kEmitPacked)
+    {
+      if (active)
+      {
+        __stcs(reinterpret_cast<uint32_t*>(write_at), (filled << 31) | squared);
+      }
+    }
+    else
+    {
+      if constexpr (kBorder)
+      {
+        int32_t border = border_yz;
+        if (finalize.nx_total > 1)
+        {
+          border = min(border, min(q + 1, finalize.nx_total - q));
+        }
+        if (border != 0x7fffffff)
+        {
+          squared = min(squared, static_cast<uint32_t>(border * border));
+        }
+      }
+      const Out value = SignedDistanceFromTable<Out>(
+          filled, squared, finalize.resolution, static_cast<const Out*>(finalize.magnitude_table),
+          finalize.magnitude_table_size);
+      if (active)
+      {
+        __stcs(reinterpret_cast<Out*>(write_at), value);
+      }
+      lane_min = (value < lane_min) ? value : lane_min;
+      lane_max = (value > lane_max) ? value : lane_max;
+    }
+  };
+
+  // The rows base .. base + R - 1 (kEdge: only those inside the line), and the loads of the rows
+  // base + 2 R .. base + 3 R - 1 (kEdge: clamped to the line) into `raw`.
+  const auto compute_chunk = [&](const int base, auto edge)
+  {
+    constexpr bool kEdge = decltype(edge)::value;
+    const char* const read_base =
+        line + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(base);
+    char* const write_base =
+        write_origin + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(base);
+#pragma unroll
+    for (int j = 0; j < kR; j++)
+    {
+      const int q = base + j;
+      {
+        // row j of the next chunk (row q + R of the line): needed from here on
+        uint32_t value = raw[j] & kNone;
+        if constexpr (kEdge)
+        {
+          value = (q + kR > last_row) ? kNone : value;
+        }
+        next_values[j] = value;
+        classes |= static_cast<uint64_t>(raw[j] >> 31) << (kR - 1 - j);
+      }
+      if (!kEdge || q <= last_row)  // warp-uniform
+      {
+        uint32_t best = current_values[j];
+#pragma unroll
+        for (int d = 1; d <= kR; d++)
+        {
+          const uint32_t offset = static_cast<uint32_t>(d * d);
+          const uint32_t before = (j - d >= 0) ? current_values[(j - d >= 0) ? j - d : 0]
+                                               : previous_values[(j - d >= 0) ? 0 : kR + j - d];
+          const uint32_t after = (j + d < kR) ? current_values[(j + d < kR) ? j + d : 0]
+                                              : next_values[(j + d < kR) ? 0 : j + d - kR];
+          best = __viaddmin_u32(before, offset, best);
+          best = __viaddmin_u32(after, offset, best);
+        }
+        // class window of row q: bit R = row q, bit R - d = row q + d, bit R + d = row q - d
+        const uint32_t window = static_cast<uint32_t>(classes >> (kR - 1 - j));
+        const uint32_t same =
+            static_cast<uint32_t>(static_cast<int32_t>(window << (31 - kR)) >> 31);
+        const uint32_t differs = window ^ same;
+        // rows at distance d on either side folded onto bit R - d; the highest set bit = nearest
+        const uint32_t folded = (differs | (__brev(differs) >> (31 - 2 * kR))) & kSideMask;
+        const int nearest = kR - 31 + __clz(static_cast<int>(folded));  // R + 1: there is none
+        const uint32_t window_best = best;
+        best = min(best, static_cast<uint32_t>(nearest * nearest));
+        const bool uncertain = best >= kFar;
+        if (__any_sync(0xffffffffu, uncertain))
+        {
+          // (an uncertain row has no opposite-class row inside the window, so its search starts
+          // from the window minimum alone; the other lanes only vote)
+          const uint32_t allowance =
+              (step_rate * (static_cast<uint32_t>(q - first_row) + credit_rows)) >> 7;
+          best = ExtendedRowSearch(line, stride_bytes, q, last_row, same & kClassBit,
+                                   uncertain ? min(window_best, kNone) : best, uncertain, kR + 1,
+                                   allowance, &steps);
+          over_budget = over_budget || steps > allowance;
+        }
+        emit_row(q, j, write_base, same & 1u, best);
+      }
+      // previous_values[j] is dead from here on, raw[j] was absorbed: reload it
+      if constexpr (kEdge)
+      {
+        raw[j] = load_clamped(base + 2 * kR + j);
+      }
+      else
+      {
+        raw[j] = *reinterpret_cast<const uint32_t*>(
+            read_base + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(2 * kR + j));
+      }
+    }
+    // the next chunk becomes the current one
+#pragma unroll
+    for (int i = 0; i < kR; i++)
+    {
+      previous_values[i] = current_values[i];
+      current_values[i] = next_values[i];
+    }
+    classes <<= kR;
+  };
+
+  {
+    using Edge = std::true_type;
+    using Interior = std::false_type;
+    // previous and current chunk of the segment's first row (a segment that does not start the
+    // line reads its neighbour's rows), and the raw rows of the chunk after
+#pragma unroll
+    for (int i = 0; i < kR; i++)
+    {
+      const int row = first_row - kR + i;
+      const uint32_t word = load_clamped(row);
+      previous_values[i] = (row < 0) ? kNone : (word & kNone);
+      classes = (classes << 1) | (word >> 31);
+    }
+#pragma unroll
+    for (int i = 0; i < kR; i++)
+    {
+      const int row = first_row + i;
+      const uint32_t word = load_clamped(row);
+      current_values[i] = (row > last_row) ? kNone : (word & kNone);
+      classes = (classes << 1) | (word >> 31);
+    }
+    classes <<= kR;
+#pragma unroll
+    for (int i = 0; i < kR; i++)
+    {
+      raw[i] = load_clamped(first_row + kR + i);
+    }
+    int base = first_row;
+    // chunks whose own rows and whose prefetched chunk (rows base + 2 R ..) lie inside the line
+#pragma unroll 1
+    for (; base + 3 * kR <= length && base < end_row && !over_budget; base += kR)
+    {
+      compute_chunk(base, Interior{});
+    }
+#pragma unroll 1
+    for (; base < end_row && !over_budget; base += kR)
+    {
+      compute_chunk(base, Edge{});
+    }
+  }
+
+  if (over_budget)
+  {
+    // The stack kernel redoes this tile (it overwrites whatever was stored here). Several
+    // segments of one tile may give up: the flag words after the list keep the entry unique.
+    if (lane == 0)
+    {
+      const uint32_t num_tiles = tiles_per_outer * static_cast<uint32_t>(family.num_outer);
+      if (atomicExch(redo + 1 + num_tiles + tile_index, 1u) == 0u)
+      {
+        const uint32_t at = atomicAdd(redo, 1u);
+        redo[1 + at] = tile_index;
+      }
+    }
+    return;
+  }
+
+  if constexpr (kMode != kEmitPacked)
+  {
+    if (min_max_keys == nullptr)
+    {
+      return;
+    }
+    using Key = typename OutputOf<kMode>::Key;
+    Key key_min = OrderedKey(lane_min);
+    Key key_max = OrderedKey(lane_max);
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1)
+    {
+      const Key other_min = __shfl_xor_sync(0xffffffffu, key_min, offset);
+      const Key other_max = __shfl_xor_sync(0xffffffffu, key_max, offset);
+      key_min = (other_min < key_min) ? other_min : key_min;
+      key_max = (other_max > key_max) ? other_max : key_max;
+    }
+    if (lane == 0)
+    {
+      atomicMin(min_max_keys + 0, key_min);
+      atomicMax(min_max_keys + 1, key_max);
+    }
+  }
+}
+}  // namespace
+}  // namespace edt
+}  // namespace vgt_b200

@@ -13,6 +13,7 @@
 #include "edt_device.cuh"
 #include "edt_envelope_inplace.cuh"
 #include "edt_envelope_lean.cuh"
+#include "edt_envelope_window.cuh"
 #include "edt_scan_registers.cuh"
 #include "edt_cells.cuh"
 
@@ -133,7 +134,8 @@ template <int kMode, bool kNarrow, bool kSend, bool kBorder, bool kSplit>
 int LaunchEnvelopeLeanKernel(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
                              uint16_t* d_positions, const LineFamily& family,
                              const FinalizeParams& finalize,
-                             typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
+                             typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream,
+                             const uint32_t* d_redo_list)
 {
   const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
   const int64_t blocks = (tiles + kLineWarpsPerBlock - 1) / kLineWarpsPerBlock;
@@ -156,7 +158,7 @@ int LaunchEnvelopeLeanKernel(uint32_t* d_in, typename OutputOf<kMode>::Type* d_o
   const auto launch = [&](auto kernel)
   {
     kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, 0, stream>>>(
-        d_in, d_out, d_positions, class_scratch.get(), derived, finalize, d_keys);
+        d_in, d_out, d_positions, class_scratch.get(), derived, finalize, d_keys, d_redo_list);
   };
   if constexpr (kMode == kEmitPacked)
   {
@@ -187,17 +189,17 @@ template <int kMode, bool kNarrow, bool kSplit>
 int LaunchEnvelopeLean(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
                        uint16_t* d_positions, const LineFamily& family,
                        const FinalizeParams& finalize, typename OutputOf<kMode>::Key* d_keys,
-                       cudaStream_t stream)
+                       cudaStream_t stream, const uint32_t* d_redo_list)
 {
   if constexpr (kMode == kEmitPacked)
   {
     if (family.out_parts > 0)
     {
       return LaunchEnvelopeLeanKernel<kMode, kNarrow, true, false, kSplit>(
-          d_in, d_out, d_positions, family, finalize, d_keys, stream);
+          d_in, d_out, d_positions, family, finalize, d_keys, stream, d_redo_list);
     }
     return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, false, kSplit>(
-        d_in, d_out, d_positions, family, finalize, d_keys, stream);
+        d_in, d_out, d_positions, family, finalize, d_keys, stream, d_redo_list);
   }
   else
   {
@@ -208,22 +210,41 @@ int LaunchEnvelopeLean(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
     if (finalize.add_virtual_border != 0)
     {
       return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, true, kSplit>(
-          d_in, d_out, d_positions, family, finalize, d_keys, stream);
+          d_in, d_out, d_positions, family, finalize, d_keys, stream, d_redo_list);
     }
     return LaunchEnvelopeLeanKernel<kMode, kNarrow, false, false, kSplit>(
-        d_in, d_out, d_positions, family, finalize, d_keys, stream);
+        d_in, d_out, d_positions, family, finalize, d_keys, stream, d_redo_list);
   }
 }
 
-// Debug / A-B switch: VGT_B200_ENVELOPE=inplace forces the round-1 kernel.
+// Debug / A-B switch: VGT_B200_ENVELOPE=inplace forces the round-1 kernel, =lean the stack kernel
+// without the window kernel in front of it.
+// (read at every call, so a test can flip it inside one process)
+inline const char* EnvelopeChoice()
+{
+  const char* value = std::getenv("VGT_B200_ENVELOPE");
+  return value == nullptr ? "" : value;
+}
+
 inline bool LeanEnvelopeEnabled()
 {
-  static const bool enabled = []()
-  {
-    const char* choice = std::getenv("VGT_B200_ENVELOPE");
-    return choice == nullptr || std::strcmp(choice, "inplace") != 0;
-  }();
-  return enabled;
+  return std::strcmp(EnvelopeChoice(), "inplace") != 0;
+}
+
+inline bool WindowEnvelopeEnabled()
+{
+  return LeanEnvelopeEnabled() && std::strcmp(EnvelopeChoice(), "lean") != 0;
+}
+
+// Extended-search steps a warp of the window kernel may spend per row of its tile before it
+// hands the tile to the stack kernel, in 1/128 steps (VGT_B200_WINDOW_BUDGET overrides, in
+// percent: 2400 = 24 steps per row on average; 0 = no extended search at all). Rows deeper than
+// kDeepestSearch give their tile up at once, whatever the rate.
+inline uint32_t WindowStepRate()
+{
+  const char* value = std::getenv("VGT_B200_WINDOW_BUDGET");
+  const long percent = value == nullptr ? 2400L : std::strtol(value, nullptr, 10);
+  return static_cast<uint32_t>(std::min(std::max(0L, percent), 1000000L) * 128 / 100);
 }
 
 // Largest finite partial squared distance the lean kernel's 32-bit sentinels leave room for
@@ -231,9 +252,86 @@ inline bool LeanEnvelopeEnabled()
 // VGT_B200_MAX_AXIS stays below it: 2 * 8191^2 < 2^28.
 constexpr int64_t kLeanMaxInput = (int64_t{1} << 29) - 1;
 
+// The window kernel over every tile of the family; tiles it gives up on are appended to
+// d_redo_list (word 0 = count, zeroed here).
+template <int kMode>
+int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
+                         const LineFamily& family, const FinalizeParams& finalize,
+                         typename OutputOf<kMode>::Key* d_keys, uint32_t* d_redo_list,
+                         cudaStream_t stream)
+{
+  const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
+  const int64_t blocks = (tiles + kLineWarpsPerBlock - 1) / kLineWarpsPerBlock;
+  if (blocks > 0x7fffffffLL)
+  {
+    return FailInvalid("grid too large for one launch");
+  }
+  VGT_CUDA_TRY(cudaMemsetAsync(d_redo_list, 0, sizeof(uint32_t), stream), "redo list reset");
+  VGT_CUDA_TRY(cudaMemsetAsync(d_redo_list + 1 + tiles, 0, sizeof(uint32_t) * tiles, stream),
+               "redo flags reset");
+  LineFamily derived = family;
+  derived.stride_bytes = static_cast<uint32_t>(family.line_stride * 4);
+  derived.out_stride_bytes = static_cast<uint32_t>(
+      family.line_stride * static_cast<int64_t>(sizeof(typename OutputOf<kMode>::Type)));
+  derived.last_row = static_cast<uint32_t>(family.length - 1);
+  derived.num_words = static_cast<uint32_t>((family.length + 31) >> 5);
+  const uint32_t step_rate = WindowStepRate();
+  // Lines are cut into segments of about 128 rows (shorter when the grid has few tiles), so that
+  // the blocks are many and short: the block scheduler then balances tiles of uneven depth and
+  // the last wave is thin. A segment re-reads 2 R rows of its neighbours.
+  constexpr int kRadius = (kMode == kEmitPacked) ? kWindowRadiusPacked : kWindowRadiusFinal;
+  const int64_t chunks = (family.length + kRadius - 1) / kRadius;
+  const int64_t wanted_blocks = MultiprocessorCount() * 32;
+  int64_t segments = std::max<int64_t>((family.length + 64) / 128,
+                                       (wanted_blocks + blocks - 1) / blocks);
+  segments = std::max<int64_t>(1, std::min<int64_t>(segments, chunks / 3));
+  const int segment_rows = static_cast<int>((chunks + segments - 1) / segments) * kRadius;
+  segments = (family.length + segment_rows - 1) / segment_rows;
+  const auto launch = [&](auto kernel)
+  {
+    kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)),
+             kLineWarpsPerBlock * kWarp, 0, stream>>>(d_in, d_out, derived, finalize, d_keys,
+                                                      d_redo_list, step_rate, segment_rows);
+  };
+  // (tuning switch: VGT_B200_WINDOW_BLOCKS=6 / 8 picks the 80- / 64-register builds)
+  const char* blocks_choice = std::getenv("VGT_B200_WINDOW_BLOCKS");
+  const bool roomy = blocks_choice != nullptr && std::strcmp(blocks_choice, "6") == 0;
+  const bool tight = blocks_choice != nullptr && std::strcmp(blocks_choice, "8") == 0;
+  if constexpr (kMode == kEmitPacked)
+  {
+    if (tight)
+    {
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, 8>);
+    }
+    else
+    {
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, kWindowBlocksPacked>);
+    }
+  }
+  else if (finalize.add_virtual_border != 0)
+  {
+    launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, kWindowBlocksFinal>);
+  }
+  else
+  {
+    if (roomy)
+    {
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, 6>);
+    }
+    else
+    {
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, kWindowBlocksFinal>);
+    }
+  }
+  VGT_CUDA_TRY(cudaGetLastError(), "EnvelopeAxisWindowKernel launch");
+  return VGT_B200_OK;
+}
+
 // One strided-axis pass. d_in is DESTROYED and must not alias d_out.
 // max_input: largest finite partial squared distance the pass can see. Short axes use packed
 // 32-bit stack entries; longer ones keep the site positions in a stream-ordered uint16 side array.
+// Unless the output goes out in send layout, the window kernel runs first and the stack kernel
+// only redoes the tiles it gave up on.
 
 template <int kMode>
 int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
@@ -247,6 +345,20 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
   const bool packed = family.length <= kInPlaceMaxLength && max_input <= kInPlaceMaxInput;
   const bool lean = LeanEnvelopeEnabled() && family.line_stride * 8 <= 0xffffffffLL
       && max_input <= kLeanMaxInput;
+  StreamScratch<uint32_t> redo;
+  const uint32_t* d_redo_list = nullptr;
+  if (lean && WindowEnvelopeEnabled() && family.out_parts == 0)
+  {
+    const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
+    VGT_CUDA_TRY(redo.Allocate(2 * tiles + 1, stream), "envelope redo list");
+    const int status = LaunchEnvelopeWindow<kMode>(d_in, d_out, family, finalize, d_keys,
+                                                   redo.get(), stream);
+    if (status != VGT_B200_OK)
+    {
+      return status;
+    }
+    d_redo_list = redo.get();
+  }
   if (lean && packed)
   {
     // 32-bit pop test when no product of an h difference and a position difference can overflow.
@@ -254,10 +366,10 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
     if (max_h * family.length < (int64_t{1} << 31))
     {
       return LaunchEnvelopeLean<kMode, true, false>(d_in, d_out, nullptr, family, finalize,
-                                                    d_keys, stream);
+                                                    d_keys, stream, d_redo_list);
     }
     return LaunchEnvelopeLean<kMode, false, false>(d_in, d_out, nullptr, family, finalize, d_keys,
-                                                   stream);
+                                                   stream, d_redo_list);
   }
   if (packed)
   {
@@ -273,7 +385,7 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
   if (lean)
   {
     return LaunchEnvelopeLean<kMode, false, true>(d_in, d_out, positions.get(), family, finalize,
-                                                  d_keys, stream);
+                                                  d_keys, stream, d_redo_list);
   }
   return LaunchEnvelopeInPlaceStack<kMode, true>(d_in, d_out, positions.get(), family, finalize,
                                                  d_keys, stream);
