@@ -6,7 +6,5 @@ for n in ${SIZES:-512 256}; do
   echo "lean:"; VGT_B200_ENVELOPE=lean python profiles/time_passes.py $n 10
   echo "window default:"; python profiles/time_passes.py $n 10
   echo "window 6 blocks:"; VGT_B200_WINDOW_BLOCKS=6 python profiles/time_passes.py $n 10
-  for budget in ${BUDGETS:-1000000 1600}; do
-    echo "window budget $budget:"; VGT_B200_WINDOW_BUDGET=$budget python profiles/time_passes.py $n 10
-  done
+  echo "window 8 blocks:"; VGT_B200_WINDOW_BLOCKS=8 python profiles/time_passes.py $n 10
 done

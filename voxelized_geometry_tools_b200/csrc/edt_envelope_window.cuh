@@ -41,12 +41,14 @@ namespace
 // Window radius and resident blocks (of 4 warps) per SM for the packed (y) pass and the
 // finalizing (x) pass: the in-plane distances the y pass sees are larger than the final ones.
 constexpr int kWindowRadiusPacked = 12;
-constexpr int kWindowBlocksPacked = 6;
+constexpr int kWindowBlocksPacked = 8;
 constexpr int kWindowRadiusFinal = 8;
 constexpr int kWindowBlocksFinal = 8;
 // A row whose search passes this distance is in open space, where the stack kernel is the better
 // tool: its tile is given up at once, whatever the step allowance says.
 constexpr int kDeepestSearch = 64;
+// Values in the register window are clamped to this (16-bit halves; + (R + 1)^2 must fit).
+constexpr uint32_t kSaturated = 0x3fffu;
 
 // Continues the search of one row beyond the register window: rows q - d and q + d for
 // d = first_d, first_d + 1, ... while d^2 can still improve on `best`. Convergent and branch-free
@@ -120,7 +122,9 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
                              uint32_t* redo, uint32_t step_rate, int segment_rows)
 {
   using Out = typename OutputOf<kMode>::Type;
-  static_assert(kR >= 2 && kR <= 15, "the class window is one 32-bit word: 2 R + 1 <= 31 bits");
+  static_assert(kR >= 2 && kR <= 14 && kR % 2 == 0,
+                "the class window is one 32-bit word (2 R + 1 <= 31 bits); rows are kept in pairs");
+  static_assert((kR + 1) * (kR + 1) <= static_cast<int>(kSaturated), "kSaturated >= kFar");
   constexpr uint32_t kFar = static_cast<uint32_t>((kR + 1) * (kR + 1));
   constexpr uint32_t kSideMask = (1u << kR) - 1u;
   const int warp = threadIdx.x >> 5;
@@ -172,21 +176,27 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     }
   }
 
-  // The three chunks of R rows around the rows being computed: values with the class bit
-  // stripped (kNone = no distance yet, also used for rows outside the line). Rows outside the
-  // line repeat the class of the nearest row of the line, so they never read as the nearest
+  // The three chunks of R rows around the rows being computed, two rows per register: 16-bit
+  // halves, low half = the even row of the pair, so that one VIADDMNMX.U16x2 handles two
+  // candidates. Values are clamped to kSaturated: a candidate that large cannot certify anything
+  // (kSaturated >= kFar), and as long as the window minimum stays below kSaturated it was taken
+  // over unclamped values only, i.e. it is exact. Rows outside the line hold kSaturated and
+  // repeat the class of the nearest row of the line, so they never read as the nearest
   // opposite-class row.
-  uint32_t previous_values[kR], current_values[kR], next_values[kR];
+  constexpr int kPairs = kR / 2;
+  uint32_t previous_pairs[kPairs], current_pairs[kPairs], next_pairs[kPairs];
   // Class bits of the three chunks: bit 3 R - 1 - r' = class of row r' counted from the first
-  // row of the previous chunk. The bits of the next chunk enter row by row (see below); bits
+  // row of the previous chunk. The bits of the next chunk enter pair by pair (see below); bits
   // above 3 R are leftovers of older chunks and never reach a window.
   uint64_t classes = 0;
-  // The rows of the next chunk as loaded. Row j of it is needed from row j of the current chunk
-  // on, so it is absorbed (stripped, class bit filed) right there and its register reloaded with
-  // the row one chunk further at once: every load has a whole chunk of work to land.
+  // The rows of the next chunk as loaded. Rows j, j + 1 (j even) of it are needed from row j of
+  // the current chunk on, so they are absorbed (clamped, packed, class bits filed) right there,
+  // and each register is reloaded with the row one chunk further after its own row: every load
+  // has about a chunk of work to land.
   uint32_t raw[kR];
 
   const auto load_clamped = [&](const int row) { return load_row(min(max(row, 0), last_row)); };
+  const auto clamped_value = [&](const uint32_t word) { return min(word & kNone, kSaturated); };
 
   // Extended-search steps of this warp so far (warp-uniform) and whether they have passed the
   // allowance of step_rate / 128 steps per row done (plus a credit of a quarter segment), or a
@@ -200,6 +210,29 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     return;  // warp-uniform
   }
   const uint32_t credit_rows = static_cast<uint32_t>(segment_rows >> 2) + 16u;
+
+  // Finalize mode: the magnitude of row q comes from a table load; it is consumed (signed,
+  // stored, folded into min / max) one row later, behind the next row's window work.
+  Out pending_magnitude = Out(0);
+  char* pending_at = nullptr;
+  uint32_t pending_filled = 0;
+  bool pending = false;
+  const auto flush_pending = [&]()
+  {
+    if constexpr (kMode != kEmitPacked)
+    {
+      if (pending)
+      {
+        const Out value = pending_filled ? -pending_magnitude : pending_magnitude;
+        if (active)
+        {
+          __stcs(reinterpret_cast<Out*>(pending_at), value);
+        }
+        lane_min = (value < lane_min) ? value : lane_min;
+        lane_max = (value > lane_max) ? value : lane_max;
+      }
+    }
+  };
 
   // one row of the output; write_base = address of the chunk's first output row
   const auto emit_row = [&](const int q, const int j, char* const write_base, const uint32_t filled,
@@ -227,15 +260,21 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
           squared = min(squared, static_cast<uint32_t>(border * border));
         }
       }
-      const Out value = SignedDistanceFromTable<Out>(
-          filled, squared, finalize.resolution, static_cast<const Out*>(finalize.magnitude_table),
-          finalize.magnitude_table_size);
-      if (active)
+      // this row's magnitude is requested first, then the previous row is finished
+      Out magnitude;
+      if (squared < finalize.magnitude_table_size)
       {
-        __stcs(reinterpret_cast<Out*>(write_at), value);
+        magnitude = __ldg(static_cast<const Out*>(finalize.magnitude_table) + squared);
       }
-      lane_min = (value < lane_min) ? value : lane_min;
-      lane_max = (value > lane_max) ? value : lane_max;
+      else
+      {
+        magnitude = SignedDistanceOf<Out>(0u, squared, finalize.resolution);
+      }
+      flush_pending();
+      pending_magnitude = magnitude;
+      pending_at = write_at;
+      pending_filled = filled;
+      pending = true;
     }
   };
 
@@ -252,30 +291,41 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     for (int j = 0; j < kR; j++)
     {
       const int q = base + j;
+      if ((j & 1) == 0)
       {
-        // row j of the next chunk (row q + R of the line): needed from here on
-        uint32_t value = raw[j] & kNone;
+        // rows j, j + 1 of the next chunk (rows q + R, q + R + 1 of the line): needed from here on
+        uint32_t low = clamped_value(raw[j]);
+        uint32_t high = clamped_value(raw[j + 1]);
         if constexpr (kEdge)
         {
-          value = (q + kR > last_row) ? kNone : value;
+          low = (q + kR > last_row) ? kSaturated : low;
+          high = (q + kR + 1 > last_row) ? kSaturated : high;
         }
-        next_values[j] = value;
-        classes |= static_cast<uint64_t>(raw[j] >> 31) << (kR - 1 - j);
+        next_pairs[j >> 1] = __byte_perm(low, high, 0x5410);
+        classes |= (static_cast<uint64_t>(raw[j] >> 31) << (kR - 1 - j))
+            | (static_cast<uint64_t>(raw[j + 1] >> 31) << (kR - 2 - j));
       }
       if (!kEdge || q <= last_row)  // warp-uniform
       {
-        uint32_t best = current_values[j];
+        // Pairs g = (j >> 1) .. (j >> 1) + R of the 3 R / 2 pairs in registers cover the rows
+        // q - R .. q + R plus one row at distance R + 1 (a true candidate like the others).
+        uint32_t best_pair = 0xffffffffu;
 #pragma unroll
-        for (int d = 1; d <= kR; d++)
+        for (int t = 0; t <= kR; t++)
         {
-          const uint32_t offset = static_cast<uint32_t>(d * d);
-          const uint32_t before = (j - d >= 0) ? current_values[(j - d >= 0) ? j - d : 0]
-                                               : previous_values[(j - d >= 0) ? 0 : kR + j - d];
-          const uint32_t after = (j + d < kR) ? current_values[(j + d < kR) ? j + d : 0]
-                                              : next_values[(j + d < kR) ? 0 : j + d - kR];
-          best = __viaddmin_u32(before, offset, best);
-          best = __viaddmin_u32(after, offset, best);
+          const int g = (j >> 1) + t;                 // pair index, 0 .. 3 R / 2 - 1
+          const int low_row = 2 * g - kR;             // chunk-relative row of the low half
+          const int d_low = (j > low_row) ? j - low_row : low_row - j;
+          const int d_high = (j > low_row + 1) ? j - low_row - 1 : low_row + 1 - j;
+          const uint32_t offsets =
+              static_cast<uint32_t>(d_low * d_low) | (static_cast<uint32_t>(d_high * d_high) << 16);
+          const uint32_t pair = (g < kPairs)
+              ? previous_pairs[(g < kPairs) ? g : 0]
+              : ((g < 2 * kPairs) ? current_pairs[(g >= kPairs && g < 2 * kPairs) ? g - kPairs : 0]
+                                  : next_pairs[(g >= 2 * kPairs) ? g - 2 * kPairs : 0]);
+          best_pair = __viaddmin_u16x2(pair, offsets, best_pair);
         }
+        const uint32_t window_best = min(best_pair & 0xffffu, best_pair >> 16);
         // class window of row q: bit R = row q, bit R - d = row q + d, bit R + d = row q - d
         const uint32_t window = static_cast<uint32_t>(classes >> (kR - 1 - j));
         const uint32_t same =
@@ -284,23 +334,30 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
         // rows at distance d on either side folded onto bit R - d; the highest set bit = nearest
         const uint32_t folded = (differs | (__brev(differs) >> (31 - 2 * kR))) & kSideMask;
         const int nearest = kR - 31 + __clz(static_cast<int>(folded));  // R + 1: there is none
-        const uint32_t window_best = best;
-        best = min(best, static_cast<uint32_t>(nearest * nearest));
+        uint32_t best = min(window_best, static_cast<uint32_t>(nearest * nearest));
         const bool uncertain = best >= kFar;
         if (__any_sync(0xffffffffu, uncertain))
         {
           // (an uncertain row has no opposite-class row inside the window, so its search starts
-          // from the window minimum alone; the other lanes only vote)
-          const uint32_t allowance =
-              (step_rate * (static_cast<uint32_t>(q - first_row) + credit_rows)) >> 7;
-          best = ExtendedRowSearch(line, stride_bytes, q, last_row, same & kClassBit,
-                                   uncertain ? min(window_best, kNone) : best, uncertain, kR + 1,
-                                   allowance, &steps);
-          over_budget = over_budget || steps > allowance;
+          // from the window minimum alone; the other lanes only vote). A saturated window
+          // minimum says nothing: open space, the tile is given up.
+          if (__any_sync(0xffffffffu, uncertain && window_best >= kSaturated))
+          {
+            over_budget = true;
+          }
+          else
+          {
+            const uint32_t allowance =
+                (step_rate * (static_cast<uint32_t>(q - first_row) + credit_rows)) >> 7;
+            best = ExtendedRowSearch(line, stride_bytes, q, last_row, same & kClassBit,
+                                     uncertain ? window_best : best, uncertain, kR + 1, allowance,
+                                     &steps);
+            over_budget = over_budget || steps > allowance;
+          }
         }
         emit_row(q, j, write_base, same & 1u, best);
       }
-      // previous_values[j] is dead from here on, raw[j] was absorbed: reload it
+      // raw[j] was absorbed (at row j or j - 1): reload it
       if constexpr (kEdge)
       {
         raw[j] = load_clamped(base + 2 * kR + j);
@@ -313,10 +370,10 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     }
     // the next chunk becomes the current one
 #pragma unroll
-    for (int i = 0; i < kR; i++)
+    for (int i = 0; i < kPairs; i++)
     {
-      previous_values[i] = current_values[i];
-      current_values[i] = next_values[i];
+      previous_pairs[i] = current_pairs[i];
+      current_pairs[i] = next_pairs[i];
     }
     classes <<= kR;
   };
@@ -327,20 +384,26 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     // previous and current chunk of the segment's first row (a segment that does not start the
     // line reads its neighbour's rows), and the raw rows of the chunk after
 #pragma unroll
-    for (int i = 0; i < kR; i++)
+    for (int i = 0; i < kR; i += 2)
     {
       const int row = first_row - kR + i;
-      const uint32_t word = load_clamped(row);
-      previous_values[i] = (row < 0) ? kNone : (word & kNone);
-      classes = (classes << 1) | (word >> 31);
+      const uint32_t low_word = load_clamped(row);
+      const uint32_t high_word = load_clamped(row + 1);
+      const uint32_t low = (row < 0) ? kSaturated : clamped_value(low_word);
+      const uint32_t high = (row + 1 < 0) ? kSaturated : clamped_value(high_word);
+      previous_pairs[i >> 1] = __byte_perm(low, high, 0x5410);
+      classes = (classes << 2) | ((low_word >> 31) << 1) | (high_word >> 31);
     }
 #pragma unroll
-    for (int i = 0; i < kR; i++)
+    for (int i = 0; i < kR; i += 2)
     {
       const int row = first_row + i;
-      const uint32_t word = load_clamped(row);
-      current_values[i] = (row > last_row) ? kNone : (word & kNone);
-      classes = (classes << 1) | (word >> 31);
+      const uint32_t low_word = load_clamped(row);
+      const uint32_t high_word = load_clamped(row + 1);
+      const uint32_t low = (row > last_row) ? kSaturated : clamped_value(low_word);
+      const uint32_t high = (row + 1 > last_row) ? kSaturated : clamped_value(high_word);
+      current_pairs[i >> 1] = __byte_perm(low, high, 0x5410);
+      classes = (classes << 2) | ((low_word >> 31) << 1) | (high_word >> 31);
     }
     classes <<= kR;
 #pragma unroll
@@ -360,6 +423,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     {
       compute_chunk(base, Edge{});
     }
+    flush_pending();
   }
 
   if (over_budget)
