@@ -15,7 +15,7 @@ needed between iterations.
 value  = voxels / s with the occupancy already resident in HBM (CUDA events, max over ranks).
 e2e    = the same through the drop-in host entry point vgt_b200_sdf_f32 (host buffers in, host
          buffers out; H2D + D2H inside the timed region), per rank on its slab at N>1.
-roofline: the dominant kernel (x pass + finalize), algorithmic 8 B/voxel, timed with CUDA events
+roofline: the dominant kernel (the slowest of the three passes, normally x + finalize), algorithmic 8 B/voxel, timed with CUDA events
          between the kernels on the launching stream (vgt_b200_sdf_f32_dev_profile).
 cpu_baseline / --impl reference: the CPU oracle (our restatement of the reference CPU path, or
          the reference's own EDT source when oracle/_ref was built) on a bounded 256^3 sample.
@@ -40,10 +40,12 @@ if str(REPO) not in sys.path:
 RESOLUTION = 0.02
 SDF_BYTES_PER_VOXEL = 24           # 3 passes x (4 B in + 4 B out), SURVEY.md section 8d
 PASS_BYTES_PER_VOXEL = 8
-KERNELS_PER_STEP = 5               # scan, y envelope, key reset, x envelope + finalize, key decode
+# scan, y window + stack redo (exits at once when the redo list is empty), key reset, magnitude
+# table, x window + finalize, its stack redo, key decode
+KERNELS_PER_STEP = 8
 CPU_SAMPLE_DIMS = (256, 256, 256)
-PASS_NAMES = ["ScanContiguousAxisRegistersKernel (z)", "EnvelopeAxisLeanKernel (y)",
-              "EnvelopeAxisLeanKernel (x + finalize)"]
+PASS_NAMES = ["ScanContiguousAxisRegistersKernel (z)", "EnvelopeAxisWindowKernel (y)",
+              "EnvelopeAxisWindowKernel (x + finalize)"]
 NCU_TRAFFIC_FILE = REPO / "profiles" / "ncu_traffic.json"
 
 

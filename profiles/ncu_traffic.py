@@ -21,8 +21,8 @@ def value(row, name):
 
 
 labels = {"ScanContiguousAxis": "ScanContiguousAxisRegistersKernel (z)",
-          "EnvelopeAxisLeanKernel<0": "EnvelopeAxisLeanKernel (y)",
-          "EnvelopeAxisLeanKernel<1": "EnvelopeAxisLeanKernel (x + finalize)"}
+          "EnvelopeAxisWindowKernel<0": "EnvelopeAxisWindowKernel (y)",
+          "EnvelopeAxisWindowKernel<1": "EnvelopeAxisWindowKernel (x + finalize)"}
 out = {}
 for row in rows[2:]:
     name = row[header.index("Kernel Name")]

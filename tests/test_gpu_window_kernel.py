@@ -73,3 +73,26 @@ def test_box_scene_and_blobs(shared_library, oracle, route):
     rng = np.random.default_rng(11)
     occupancy = random_occupancy(rng, (60, 130, 90), 0.08, blobs=True)
     assert_matches_oracle(oracle, occupancy, 0.02)
+
+
+@pytest.mark.parametrize("shape,world", [((20, 38, 70), 4), ((9, 130, 40), 3), ((6, 61, 33), 8)])
+def test_send_layout_output(shared_library, route, shape, world):
+    # the slab-local y pass writing the all-to-all's send layout (multi-GPU path) must hold the
+    # packed result of the plain pass, part by part
+    import torch
+    from voxelized_geometry_tools_b200 import device as vdev
+    from voxelized_geometry_tools_b200.sharded import split_range
+    rng = np.random.default_rng(world)
+    for fill in (0.02, 0.3):
+        occupancy = random_occupancy(rng, shape, fill, blobs=True)
+        slab = torch.from_numpy(occupancy).to(torch.device("cuda", 0))
+        packed = vdev.edt_local_passes(slab)
+        send = vdev.edt_local_passes(slab, send_parts=world).view(-1)
+        blocks, offset = [], 0
+        for peer in range(world):
+            y0, y1 = split_range(shape[1], world, peer)
+            count = shape[0] * (y1 - y0) * shape[2]
+            blocks.append(send[offset:offset + count].view(shape[0], y1 - y0, shape[2]))
+            offset += count
+        assert offset == send.numel()
+        assert torch.equal(packed, torch.cat(blocks, dim=1))

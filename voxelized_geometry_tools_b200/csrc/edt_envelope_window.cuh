@@ -41,7 +41,7 @@ namespace
 // Window radius and resident blocks (of 4 warps) per SM for the packed (y) pass and the
 // finalizing (x) pass: the in-plane distances the y pass sees are larger than the final ones.
 constexpr int kWindowRadiusPacked = 12;
-constexpr int kWindowBlocksPacked = 8;
+constexpr int kWindowBlocksPacked = 7;
 constexpr int kWindowRadiusFinal = 8;
 constexpr int kWindowBlocksFinal = 8;
 // A row whose search passes this distance is in open space, where the stack kernel is the better
@@ -114,7 +114,7 @@ __device__ __noinline__ uint32_t ExtendedRowSearch(const char* line, uint32_t st
 // multiple of R) of their lines. Redo list layout: word 0 = number of tiles, words 1 .. T = tile
 // indices, words T + 1 .. 2 T = per-tile "already listed" flags (T = number of tiles); the
 // launcher zeroes word 0 and the flags.
-template <int kMode, int kR, bool kBorder, int kBlocksPerSm>
+template <int kMode, int kR, bool kBorder, bool kSend, int kBlocksPerSm>
 __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     EnvelopeAxisWindowKernel(const uint32_t* __restrict__ in,
                              typename OutputOf<kMode>::Type* __restrict__ out, LineFamily family,
@@ -211,6 +211,11 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
   }
   const uint32_t credit_rows = static_cast<uint32_t>(segment_rows >> 2) + 16u;
 
+  // Send layout only: the virtual origin of the current part and the row at which the next
+  // part starts (the segment's first row forces the first look-up).
+  char* send_origin = nullptr;
+  int next_part_start = first_row;
+
   // Finalize mode: the magnitude of row q comes from a table load; it is consumed (signed,
   // stored, folded into min / max) one row later, behind the next row's window work.
   Out pending_magnitude = Out(0);
@@ -238,7 +243,58 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
   const auto emit_row = [&](const int q, const int j, char* const write_base, const uint32_t filled,
                             uint32_t squared)
   {
-    char* const write_at = write_base + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(j);
+    char* write_at = write_base + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(j);
+    if constexpr (kSend)
+    {
+      // Send layout (see LineFamily): row q is at send_origin + q * out_stride_bytes; the origin
+      // jumps at part boundaries, which are the same for every lane (warp-uniform branch).
+      if (q == next_part_start)
+      {
+        // Part h covers rows [y0, y0 + rows); its block starts at inner * num_outer * y0.
+        const int wide = family.out_base + 1;
+        const int wide_rows = family.out_extra * wide;
+        int y0;
+        int rows;
+        if (q < wide_rows)
+        {
+          y0 = (q / wide) * wide;
+          rows = wide;
+        }
+        else
+        {
+          y0 = wide_rows + ((q - wide_rows) / family.out_base) * family.out_base;
+          rows = family.out_base;
+        }
+        next_part_start = y0 + rows;
+        Out* part_row;
+        if (family.scatter_base[0] != nullptr)
+        {
+          // this part goes straight to its owner's receive buffer over NVLink
+          const int part = (q < wide_rows)
+              ? (q / wide)
+              : (family.out_extra + (q - wide_rows) / family.out_base);
+          // (selected with compares: indexing the kernel-parameter array with a register
+          // would force a local-memory copy of the whole parameter struct)
+          uint32_t* target = family.scatter_base[0];
+#pragma unroll
+          for (int i = 1; i < 8; i++)
+          {
+            target = (part == i) ? family.scatter_base[i] : target;
+          }
+          part_row = reinterpret_cast<Out*>(target)
+              + family.inner_count * ((family.scatter_row_offset + outer) * rows + (q - y0))
+              + column;
+        }
+        else
+        {
+          part_row = out + family.inner_count * (family.num_outer * y0 + outer * rows + (q - y0))
+              + column;
+        }
+        send_origin = reinterpret_cast<char*>(part_row)
+            - static_cast<uint64_t>(static_cast<uint32_t>(q)) * out_stride_bytes;
+      }
+      write_at = send_origin + static_cast<uint64_t>(static_cast<uint32_t>(q)) * out_stride_bytes;
+    }
     if constexpr (kMode == kEmitPacked)
     {
       if (active)
@@ -283,8 +339,8 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
   const auto compute_chunk = [&](const int base, auto edge)
   {
     constexpr bool kEdge = decltype(edge)::value;
-    const char* const read_base =
-        line + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(base);
+    const char* const read_next =
+        line + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(base + 2 * kR);
     char* const write_base =
         write_origin + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(base);
 #pragma unroll
@@ -365,7 +421,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
       else
       {
         raw[j] = *reinterpret_cast<const uint32_t*>(
-            read_base + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(2 * kR + j));
+            read_next + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(j));
       }
     }
     // the next chunk becomes the current one

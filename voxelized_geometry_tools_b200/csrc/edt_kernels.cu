@@ -276,14 +276,14 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   derived.last_row = static_cast<uint32_t>(family.length - 1);
   derived.num_words = static_cast<uint32_t>((family.length + 31) >> 5);
   const uint32_t step_rate = WindowStepRate();
-  // Lines are cut into segments of about 128 rows (shorter when the grid has few tiles), so that
-  // the blocks are many and short: the block scheduler then balances tiles of uneven depth and
-  // the last wave is thin. A segment re-reads 2 R rows of its neighbours.
+  // Lines are cut into segments so that there are about six waves of blocks (and never
+  // segments shorter than three chunks; measured at 512^3: 1.68 ms with one segment per line,
+  // 1.49 ms with four): the block scheduler then balances tiles of uneven depth
+  // and the last wave is thin. A segment re-reads 2 R rows of its neighbours.
   constexpr int kRadius = (kMode == kEmitPacked) ? kWindowRadiusPacked : kWindowRadiusFinal;
   const int64_t chunks = (family.length + kRadius - 1) / kRadius;
-  const int64_t wanted_blocks = MultiprocessorCount() * 32;
-  int64_t segments = std::max<int64_t>((family.length + 64) / 128,
-                                       (wanted_blocks + blocks - 1) / blocks);
+  const int64_t wanted_blocks = MultiprocessorCount() * 48;
+  int64_t segments = (wanted_blocks + blocks - 1) / blocks;
   segments = std::max<int64_t>(1, std::min<int64_t>(segments, chunks / 3));
   const int segment_rows = static_cast<int>((chunks + segments - 1) / segments) * kRadius;
   segments = (family.length + segment_rows - 1) / segment_rows;
@@ -293,35 +293,28 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
              kLineWarpsPerBlock * kWarp, 0, stream>>>(d_in, d_out, derived, finalize, d_keys,
                                                       d_redo_list, step_rate, segment_rows);
   };
-  // (tuning switch: VGT_B200_WINDOW_BLOCKS=6 / 8 picks the 80- / 64-register builds)
-  const char* blocks_choice = std::getenv("VGT_B200_WINDOW_BLOCKS");
-  const bool roomy = blocks_choice != nullptr && std::strcmp(blocks_choice, "6") == 0;
-  const bool tight = blocks_choice != nullptr && std::strcmp(blocks_choice, "8") == 0;
   if constexpr (kMode == kEmitPacked)
   {
-    if (tight)
+    if (family.out_parts > 0)
     {
-      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, 8>);
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, true, kWindowBlocksPacked>);
     }
     else
     {
-      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, kWindowBlocksPacked>);
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, false, kWindowBlocksPacked>);
     }
+  }
+  else if (family.out_parts > 0)
+  {
+    return FailInvalid("send layout is only available for the packed intermediate");
   }
   else if (finalize.add_virtual_border != 0)
   {
-    launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, kWindowBlocksFinal>);
+    launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, false, kWindowBlocksFinal>);
   }
   else
   {
-    if (roomy)
-    {
-      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, 6>);
-    }
-    else
-    {
-      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, kWindowBlocksFinal>);
-    }
+    launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, false, kWindowBlocksFinal>);
   }
   VGT_CUDA_TRY(cudaGetLastError(), "EnvelopeAxisWindowKernel launch");
   return VGT_B200_OK;
@@ -330,8 +323,7 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
 // One strided-axis pass. d_in is DESTROYED and must not alias d_out.
 // max_input: largest finite partial squared distance the pass can see. Short axes use packed
 // 32-bit stack entries; longer ones keep the site positions in a stream-ordered uint16 side array.
-// Unless the output goes out in send layout, the window kernel runs first and the stack kernel
-// only redoes the tiles it gave up on.
+// The window kernel runs first and the stack kernel only redoes the tiles it gave up on.
 
 template <int kMode>
 int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
@@ -347,7 +339,7 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
       && max_input <= kLeanMaxInput;
   StreamScratch<uint32_t> redo;
   const uint32_t* d_redo_list = nullptr;
-  if (lean && WindowEnvelopeEnabled() && family.out_parts == 0)
+  if (lean && WindowEnvelopeEnabled())
   {
     const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
     VGT_CUDA_TRY(redo.Allocate(2 * tiles + 1, stream), "envelope redo list");
