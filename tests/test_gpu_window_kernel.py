@@ -3,7 +3,9 @@ certify inside the register window, rows that take the extended search, tiles ha
 kernel - against the oracle, bit for bit. The routes are forced with the library's A/B switches
 (read at every call): VGT_B200_WINDOW_BUDGET (extended-search steps a warp may spend per 100 rows of
 its tile; 0 sends every tile with an uncertain row to the stack kernel, a huge value
-keeps everything in the window kernel) and VGT_B200_ENVELOPE=lean (no window kernel at all)."""
+keeps everything in the window kernel), VGT_B200_WINDOW_PILOT=0 (no pilot launch: the window
+kernel takes every tile whatever the map looks like) and VGT_B200_ENVELOPE=lean (no window kernel
+at all)."""
 import os
 
 import numpy as np
@@ -17,13 +19,15 @@ from .test_gpu_sdf import assert_matches_oracle
 pytestmark = pytest.mark.gpu
 
 ROUTES = [{"VGT_B200_WINDOW_BUDGET": "0"}, {"VGT_B200_WINDOW_BUDGET": "1000000"},
-          {"VGT_B200_WINDOW_BUDGET": "25"}, {"VGT_B200_ENVELOPE": "lean"}, {}]
+          {"VGT_B200_WINDOW_BUDGET": "25"}, {"VGT_B200_ENVELOPE": "lean"},
+          {"VGT_B200_WINDOW_PILOT": "0"}, {}]
 
 
 @pytest.fixture(params=ROUTES, ids=lambda route: ",".join(f"{k}={v}" for k, v in route.items())
                 or "default")
 def route(request):
-    saved = {key: os.environ.get(key) for key in ("VGT_B200_WINDOW_BUDGET", "VGT_B200_ENVELOPE")}
+    saved = {key: os.environ.get(key) for key in ("VGT_B200_WINDOW_BUDGET", "VGT_B200_ENVELOPE",
+                                                  "VGT_B200_WINDOW_PILOT")}
     for key in saved:
         os.environ.pop(key, None)
     os.environ.update(request.param)
@@ -96,3 +100,19 @@ def test_send_layout_output(shared_library, route, shape, world):
             offset += count
         assert offset == send.numel()
         assert torch.equal(packed, torch.cat(blocks, dim=1))
+
+
+def test_grids_with_enough_tiles_for_the_pilot(shared_library, oracle, route):
+    # >= 64 groups of 4 tiles in both passes: the pilot launch decides between "cluttered" (the
+    # rest of the window launch runs) and "deep" (the stack kernel takes every tile)
+    shape = (40, 100, 256)
+    cluttered = synthetic.clustered_spheres_occupancy(shape)
+    assert_matches_oracle(oracle, cluttered, 0.02)
+    rng = np.random.default_rng(3)
+    deep = np.zeros(shape, dtype=np.float32)
+    deep[rng.integers(0, 40, 5), rng.integers(0, 100, 5), rng.integers(0, 256, 5)] = 1.0
+    deep[:, 60:, 200:] = 1.0
+    assert_matches_oracle(oracle, deep, 0.02, add_virtual_border=True)
+    mixed = cluttered.copy()
+    mixed[:, :50, :] = 0.0
+    assert_matches_oracle(oracle, mixed, 0.02)

@@ -107,15 +107,19 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
   uint32_t tile_index = blockIdx.x * kLineWarpsPerBlock + warp;
   if (redo_list != nullptr)
   {
-    // second launch after the window kernel (edt_envelope_window.cuh): only the tiles it gave up
-    // on; word 0 = how many, words 1.. = their indices
-    if (tile_index >= redo_list[0])
+    // Launch after the window kernel (edt_envelope_window.cuh; buffer layout there): either
+    // only the tiles it gave up on (word 0 = how many, words 4.. = their indices), or, when its
+    // pilot found the map deep (word 1), every tile.
+    if (redo_list[1] == 0u)
     {
-      return;  // warp-uniform
+      if (tile_index >= redo_list[0])
+      {
+        return;  // warp-uniform
+      }
+      tile_index = redo_list[4 + tile_index];
     }
-    tile_index = redo_list[1 + tile_index];
   }
-  else if (tile_index >= tiles_per_outer * static_cast<uint32_t>(family.num_outer))
+  if (tile_index >= tiles_per_outer * static_cast<uint32_t>(family.num_outer))
   {
     return;  // warp-uniform
   }

@@ -44,6 +44,24 @@ constexpr int kWindowRadiusPacked = 12;
 constexpr int kWindowBlocksPacked = 7;
 constexpr int kWindowRadiusFinal = 8;
 constexpr int kWindowBlocksFinal = 8;
+// Hand-over buffer between the window kernel and the stack kernel ("redo list"), T = number of
+// tiles: word 0 = number of listed tiles, word 1 = mode (0: the stack kernel redoes the listed
+// tiles; 1: the pilot found the map deep, the stack kernel does every tile), word 2 = extended-
+// search steps of the pilot's warps, word 3 unused, words 4 .. 4 + T = tile indices, then T
+// per-tile "already listed" flags. The launcher zeroes everything but the list.
+constexpr uint32_t kRedoCount = 0;
+constexpr uint32_t kRedoMode = 1;
+constexpr uint32_t kRedoPilotSteps = 2;
+constexpr uint32_t kRedoList = 4;
+// What a launch is: the plain pass over every tile; the pilot, a probe that computes two chunks
+// of rows out of every kPilotSpacing rows of every kPilotStride-th group of 4 tiles, stores
+// nothing and only reports its search effort (words 0 and 2), from which the mode is decided;
+// or the pass after the pilot, which stands down when the mode is "deep".
+constexpr uint32_t kSelectAll = 0;
+constexpr uint32_t kSelectPilot = 1;
+constexpr uint32_t kSelectAfterPilot = 2;
+constexpr uint32_t kPilotStride = 8;
+constexpr int kPilotSpacing = 256;
 // A row whose search passes this distance is in open space, where the stack kernel is the better
 // tool: its tile is given up at once, whatever the step allowance says.
 constexpr int kDeepestSearch = 64;
@@ -110,16 +128,30 @@ __device__ __noinline__ uint32_t ExtendedRowSearch(const char* line, uint32_t st
   return best;
 }
 
-// Work split: blockIdx.x = group of 4 tiles, blockIdx.y = segment of segment_rows rows (a
-// multiple of R) of their lines. Redo list layout: word 0 = number of tiles, words 1 .. T = tile
-// indices, words T + 1 .. 2 T = per-tile "already listed" flags (T = number of tiles); the
-// launcher zeroes word 0 and the flags.
+// Work split: blockIdx.x = group of 4 tiles (the pilot launch: group blockIdx.x * kPilotStride),
+// blockIdx.y = segment: rows [blockIdx.y * segment_spacing, + segment_rows) of their lines
+// (segment_rows a multiple of R; spacing == rows except for the pilot's probes).
+
+// After the pilot, whose probes run on a tight allowance (kPilotStepRate: two search steps per
+// row, so that a probe in open space gives up at its first or second deep row instead of
+// searching for 100 microseconds): the map is "deep" when 40 % of the probes gave up. Then the
+// window launch stands down and the stack kernel takes every tile. Resets the count for the real
+// pass.
+constexpr uint32_t kPilotStepRate = 2u * 128u;
+__global__ void DecideWindowModeKernel(uint32_t* redo, uint32_t pilot_probes)
+{
+  const bool deep = 5u * redo[kRedoCount] > 2u * pilot_probes;
+  redo[kRedoMode] = deep ? 1u : 0u;
+  redo[kRedoCount] = 0u;
+}
+
 template <int kMode, int kR, bool kBorder, bool kSend, int kBlocksPerSm>
 __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     EnvelopeAxisWindowKernel(const uint32_t* __restrict__ in,
                              typename OutputOf<kMode>::Type* __restrict__ out, LineFamily family,
                              FinalizeParams finalize, typename OutputOf<kMode>::Key* min_max_keys,
-                             uint32_t* redo, uint32_t step_rate, int segment_rows)
+                             uint32_t* redo, uint32_t step_rate, int segment_rows,
+                             int segment_spacing, uint32_t block_select)
 {
   using Out = typename OutputOf<kMode>::Type;
   static_assert(kR >= 2 && kR <= 14 && kR % 2 == 0,
@@ -133,14 +165,21 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
   const int last_row = static_cast<int>(family.last_row);
 
   const uint32_t tiles_per_outer = static_cast<uint32_t>((family.inner_count + kWarp - 1) / kWarp);
-  const uint32_t tile_index = blockIdx.x * kLineWarpsPerBlock + warp;
+  const uint32_t block_index = (block_select == kSelectPilot) ? blockIdx.x * kPilotStride : blockIdx.x;
+  if (block_select == kSelectAfterPilot && redo[kRedoMode] != 0u)
+  {
+    return;  // a deep map: the stack kernel does it all
+  }
+  const uint32_t tile_index = block_index * kLineWarpsPerBlock + warp;
   if (tile_index >= tiles_per_outer * static_cast<uint32_t>(family.num_outer))
   {
     return;  // warp-uniform
   }
   const uint32_t outer = tile_index / tiles_per_outer;
   const uint32_t wanted_column = (tile_index - outer * tiles_per_outer) * kWarp + lane;
-  const bool active = wanted_column < static_cast<uint32_t>(family.inner_count);
+  // (the pilot stores nothing)
+  const bool active = wanted_column < static_cast<uint32_t>(family.inner_count)
+      && block_select != kSelectPilot;
   // Lanes past the last column shadow the last one (loads only), so that the whole warp stays
   // converged for the votes.
   const uint32_t column = active ? wanted_column : static_cast<uint32_t>(family.inner_count - 1);
@@ -203,7 +242,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
   // row turned out deeper than kDeepestSearch: the tile then goes to the stack kernel.
   uint32_t steps = 0;
   bool over_budget = false;
-  const int first_row = static_cast<int>(blockIdx.y) * segment_rows;
+  const int first_row = static_cast<int>(blockIdx.y) * segment_spacing;
   const int end_row = min(first_row + segment_rows, length);
   if (first_row >= length)
   {
@@ -482,6 +521,18 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     flush_pending();
   }
 
+  if (block_select == kSelectPilot)
+  {
+    if (lane == 0 && steps != 0u)
+    {
+      atomicAdd(redo + kRedoPilotSteps, steps);
+    }
+    if (lane == 0 && over_budget)
+    {
+      atomicAdd(redo + kRedoCount, 1u);
+    }
+    return;
+  }
   if (over_budget)
   {
     // The stack kernel redoes this tile (it overwrites whatever was stored here). Several
@@ -489,10 +540,10 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     if (lane == 0)
     {
       const uint32_t num_tiles = tiles_per_outer * static_cast<uint32_t>(family.num_outer);
-      if (atomicExch(redo + 1 + num_tiles + tile_index, 1u) == 0u)
+      if (atomicExch(redo + kRedoList + num_tiles + tile_index, 1u) == 0u)
       {
-        const uint32_t at = atomicAdd(redo, 1u);
-        redo[1 + at] = tile_index;
+        const uint32_t at = atomicAdd(redo + kRedoCount, 1u);
+        redo[kRedoList + at] = tile_index;
       }
     }
     return;

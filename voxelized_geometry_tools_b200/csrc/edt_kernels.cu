@@ -253,7 +253,11 @@ inline uint32_t WindowStepRate()
 constexpr int64_t kLeanMaxInput = (int64_t{1} << 29) - 1;
 
 // The window kernel over every tile of the family; tiles it gives up on are appended to
-// d_redo_list (word 0 = count, zeroed here).
+// d_redo_list (layout in edt_envelope_window.cuh; header and flags zeroed here). With enough tiles
+// a pilot launch goes first: it probes two chunks of rows out of every 256 of every 8th group of
+// tiles and decides, on the device, whether the window kernel runs at all. On maps with large
+// open spaces nearly every tile would end up with the stack kernel anyway, and the window
+// kernel's searches would only be wasted.
 template <int kMode>
 int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
                          const LineFamily& family, const FinalizeParams& finalize,
@@ -266,8 +270,10 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   {
     return FailInvalid("grid too large for one launch");
   }
-  VGT_CUDA_TRY(cudaMemsetAsync(d_redo_list, 0, sizeof(uint32_t), stream), "redo list reset");
-  VGT_CUDA_TRY(cudaMemsetAsync(d_redo_list + 1 + tiles, 0, sizeof(uint32_t) * tiles, stream),
+  VGT_CUDA_TRY(cudaMemsetAsync(d_redo_list, 0, sizeof(uint32_t) * kRedoList, stream),
+               "redo list reset");
+  VGT_CUDA_TRY(cudaMemsetAsync(d_redo_list + kRedoList + tiles, 0, sizeof(uint32_t) * tiles,
+                               stream),
                "redo flags reset");
   LineFamily derived = family;
   derived.stride_bytes = static_cast<uint32_t>(family.line_stride * 4);
@@ -287,11 +293,32 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   segments = std::max<int64_t>(1, std::min<int64_t>(segments, chunks / 3));
   const int segment_rows = static_cast<int>((chunks + segments - 1) / segments) * kRadius;
   segments = (family.length + segment_rows - 1) / segment_rows;
+  // (VGT_B200_WINDOW_PILOT=0: no pilot, the window kernel works on every tile)
+  const char* pilot_choice = std::getenv("VGT_B200_WINDOW_PILOT");
+  const bool pilot = blocks >= 4 * static_cast<int64_t>(kPilotStride)
+      && !(pilot_choice != nullptr && std::strcmp(pilot_choice, "0") == 0);
   const auto launch = [&](auto kernel)
   {
-    kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)),
-             kLineWarpsPerBlock * kWarp, 0, stream>>>(d_in, d_out, derived, finalize, d_keys,
-                                                      d_redo_list, step_rate, segment_rows);
+    const dim3 threads(kLineWarpsPerBlock * kWarp);
+    if (!pilot)
+    {
+      kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)), threads, 0,
+               stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list, step_rate,
+                         segment_rows, segment_rows, kSelectAll);
+      return;
+    }
+    const int64_t pilot_blocks = (blocks + kPilotStride - 1) / kPilotStride;
+    const int64_t probes_per_line = (family.length + kPilotSpacing - 1) / kPilotSpacing;
+    const int64_t pilot_probes =
+        std::min<int64_t>(pilot_blocks * kLineWarpsPerBlock, tiles) * probes_per_line;
+    kernel<<<dim3(static_cast<unsigned>(pilot_blocks), static_cast<unsigned>(probes_per_line)),
+             threads, 0, stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list,
+                                   std::min(step_rate, kPilotStepRate), 2 * kRadius, kPilotSpacing,
+                                   kSelectPilot);
+    DecideWindowModeKernel<<<1, 1, 0, stream>>>(d_redo_list, static_cast<uint32_t>(pilot_probes));
+    kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)), threads, 0,
+             stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list, step_rate,
+                       segment_rows, segment_rows, kSelectAfterPilot);
   };
   if constexpr (kMode == kEmitPacked)
   {
@@ -342,7 +369,7 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
   if (lean && WindowEnvelopeEnabled())
   {
     const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
-    VGT_CUDA_TRY(redo.Allocate(2 * tiles + 1, stream), "envelope redo list");
+    VGT_CUDA_TRY(redo.Allocate(2 * tiles + kRedoList, stream), "envelope redo list");
     const int status = LaunchEnvelopeWindow<kMode>(d_in, d_out, family, finalize, d_keys,
                                                    redo.get(), stream);
     if (status != VGT_B200_OK)
