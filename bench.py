@@ -40,9 +40,10 @@ if str(REPO) not in sys.path:
 RESOLUTION = 0.02
 SDF_BYTES_PER_VOXEL = 24           # 3 passes x (4 B in + 4 B out), SURVEY.md section 8d
 PASS_BYTES_PER_VOXEL = 8
-# scan, y window + stack redo (exits at once when the redo list is empty), key reset, magnitude
-# table, x window + finalize, its stack redo, key decode
-KERNELS_PER_STEP = 8
+# scan; y pass: pilot probe, mode decision, window kernel, stack kernel over the hand-over list
+# (exits at once when the list is empty); key reset, magnitude table; x pass: the same four with
+# the finalize fused; key decode
+KERNELS_PER_STEP = 12
 CPU_SAMPLE_DIMS = (256, 256, 256)
 PASS_NAMES = ["ScanContiguousAxisRegistersKernel (z)", "EnvelopeAxisWindowKernel (y)",
               "EnvelopeAxisWindowKernel (x + finalize)"]
