@@ -62,9 +62,12 @@ constexpr uint32_t kSelectPilot = 1;
 constexpr uint32_t kSelectAfterPilot = 2;
 constexpr uint32_t kPilotStride = 8;
 constexpr int kPilotSpacing = 256;
-// A row whose search passes this distance is in open space, where the stack kernel is the better
-// tool: its tile is given up at once, whatever the step allowance says.
-constexpr int kDeepestSearch = 64;
+// A row whose search passes max(this, line length / 8) is in open space, where the stack kernel
+// is the better tool: its tile is given up at once, whatever the step allowance says. The bound
+// grows with the line because so does the price of handing a tile over (one warp walking the
+// whole line alone): at 1024^3 the clustered-spheres workload has pockets 86 voxels deep, and
+// with a bound of 64 the few tiles through them cost both strided passes 0.2-0.5 ms each.
+constexpr int kDeepestSearchFloor = 64;
 // Values in the register window are clamped to this (16-bit halves; + (R + 1)^2 must fit).
 constexpr uint32_t kSaturated = 0x3fffu;
 
@@ -76,11 +79,11 @@ constexpr uint32_t kSaturated = 0x3fffu;
 // so such a candidate never wins. Rows past the ends of the line are clamped to the end rows:
 // the end row was already seen at its true, smaller distance, so the clamped candidate never
 // wins either. Gives up (returns with the step counter past the budget, the caller then hands
-// the tile to the stack kernel) once the counter passes the budget or d passes kDeepestSearch.
+// the tile to the stack kernel) once the counter passes the budget or d passes `deepest`.
 __device__ __noinline__ uint32_t ExtendedRowSearch(const char* line, uint32_t stride_bytes, int q,
                                                    int last_row, uint32_t class_bit, uint32_t best,
-                                                   bool uncertain, int first_d, uint32_t budget,
-                                                   uint32_t* steps)
+                                                   bool uncertain, int first_d, int deepest,
+                                                   uint32_t budget, uint32_t* steps)
 {
   constexpr int kUnroll = 4;
   int d = first_d;
@@ -94,7 +97,7 @@ __device__ __noinline__ uint32_t ExtendedRowSearch(const char* line, uint32_t st
     {
       break;
     }
-    if (used > budget || d > kDeepestSearch)
+    if (used > budget || d > deepest)
     {
       used = max(used, budget + 1u);  // the caller gives the tile up
       break;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
 
   // Extended-search steps of this warp so far (warp-uniform) and whether they have passed the
   // allowance of step_rate / 128 steps per row done (plus a credit of a quarter segment), or a
-  // row turned out deeper than kDeepestSearch: the tile then goes to the stack kernel.
+  // row turned out deeper than deepest_search: the tile then goes to the stack kernel.
   uint32_t steps = 0;
   bool over_budget = false;
   const int first_row = static_cast<int>(blockIdx.y) * segment_spacing;
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
     return;  // warp-uniform
   }
   const uint32_t credit_rows = static_cast<uint32_t>(segment_rows >> 2) + 16u;
+  const int deepest_search = max(kDeepestSearchFloor, length >> 3);
 
   // Send layout only: the virtual origin of the current part and the row at which the next
   // part starts (the segment's first row forces the first look-up).
@@ -445,8 +449,8 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
             const uint32_t allowance =
                 (step_rate * (static_cast<uint32_t>(q - first_row) + credit_rows)) >> 7;
             best = ExtendedRowSearch(line, stride_bytes, q, last_row, same & kClassBit,
-                                     uncertain ? window_best : best, uncertain, kR + 1, allowance,
-                                     &steps);
+                                     uncertain ? window_best : best, uncertain, kR + 1,
+                                     deepest_search, allowance, &steps);
             over_budget = over_budget || steps > allowance;
           }
         }

@@ -239,7 +239,7 @@ inline bool WindowEnvelopeEnabled()
 // Extended-search steps a warp of the window kernel may spend per row of its tile before it
 // hands the tile to the stack kernel, in 1/128 steps (VGT_B200_WINDOW_BUDGET overrides, in
 // percent: 2400 = 24 steps per row on average; 0 = no extended search at all). Rows deeper than
-// kDeepestSearch give their tile up at once, whatever the rate.
+// max(64, line length / 8) give their tile up at once, whatever the rate.
 inline uint32_t WindowStepRate()
 {
   const char* value = std::getenv("VGT_B200_WINDOW_BUDGET");
