@@ -18,7 +18,7 @@ from .test_gpu_sdf import assert_matches_oracle
 
 pytestmark = pytest.mark.gpu
 
-ROUTES = [{"VGT_B200_WINDOW_BUDGET": "0"}, {"VGT_B200_WINDOW_BUDGET": "1000000"},
+ROUTES = [{"VGT_B200_WINDOW_BUDGET": "0"}, {"VGT_B200_WINDOW_BUDGET": "100000"},
           {"VGT_B200_WINDOW_BUDGET": "25"}, {"VGT_B200_ENVELOPE": "lean"},
           {"VGT_B200_WINDOW_PILOT": "0"}, {}]
 

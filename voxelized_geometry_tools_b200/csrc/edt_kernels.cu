@@ -244,7 +244,8 @@ inline uint32_t WindowStepRate()
 {
   const char* value = std::getenv("VGT_B200_WINDOW_BUDGET");
   const long percent = value == nullptr ? 2400L : std::strtol(value, nullptr, 10);
-  return static_cast<uint32_t>(std::min(std::max(0L, percent), 1000000L) * 128 / 100);
+  // (capped so that rate x rows of the longest segment stays inside 32 bits)
+  return static_cast<uint32_t>(std::min(std::max(0L, percent), 100000L) * 128 / 100);
 }
 
 // Largest finite partial squared distance the lean kernel's 32-bit sentinels leave room for
