@@ -27,7 +27,11 @@ out = {}
 for row in rows[2:]:
     name = row[header.index("Kernel Name")]
     for key, label in labels.items():
-        if key in name and label not in out:
+        # (the window kernels launch twice per pass: the short pilot probe first, then the pass
+        # itself; keep the longer launch)
+        duration = float(row[header.index("gpu__time_duration.sum")]) \
+            * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[units[header.index("gpu__time_duration.sum")]]
+        if key in name and (label not in out or duration > out[label]["gpu_time_ms_under_ncu"]):
             out[label] = {"dram_bytes_read": value(row, "dram__bytes_read.sum"),
                           "dram_bytes_write": value(row, "dram__bytes_write.sum"),
                           "gpu_time_ms_under_ncu": float(row[header.index("gpu__time_duration.sum")])
