@@ -38,12 +38,17 @@ namespace edt
 {
 namespace
 {
-// Window radius and resident blocks (of 4 warps) per SM for the packed (y) pass and the
+// One warp (one tile) per block: warps finish at very different times (a tile through a deep
+// pocket searches far longer than its neighbours), and a block's slot is only free again when
+// its slowest warp is done. With 4-warp blocks the SMs held 25 warps on average out of the 32
+// the registers allow.
+constexpr int kWindowWarpsPerBlock = 1;
+// Window radius and resident warps per SM (72 / 64 registers) for the packed (y) pass and the
 // finalizing (x) pass: the in-plane distances the y pass sees are larger than the final ones.
 constexpr int kWindowRadiusPacked = 12;
-constexpr int kWindowBlocksPacked = 7;
+constexpr int kWindowBlocksPacked = 28;
 constexpr int kWindowRadiusFinal = 8;
-constexpr int kWindowBlocksFinal = 8;
+constexpr int kWindowBlocksFinal = 32;
 // Hand-over buffer between the window kernel and the stack kernel ("redo list"), T = number of
 // tiles: word 0 = number of listed tiles, word 1 = mode (0: the stack kernel redoes the listed
 // tiles; 1: the pilot found the map deep, the stack kernel does every tile), word 2 = extended-
@@ -54,7 +59,7 @@ constexpr uint32_t kRedoMode = 1;
 constexpr uint32_t kRedoPilotSteps = 2;
 constexpr uint32_t kRedoList = 4;
 // What a launch is: the plain pass over every tile; the pilot, a probe that computes two chunks
-// of rows out of every kPilotSpacing rows of every kPilotStride-th group of 4 tiles, stores
+// of rows out of every kPilotSpacing rows of every kPilotStride-th tile, stores
 // nothing and only reports its search effort (words 0 and 2), from which the mode is decided;
 // or the pass after the pilot, which stands down when the mode is "deep".
 constexpr uint32_t kSelectAll = 0;
@@ -131,7 +136,7 @@ __device__ __noinline__ uint32_t ExtendedRowSearch(const char* line, uint32_t st
   return best;
 }
 
-// Work split: blockIdx.x = group of 4 tiles (the pilot launch: group blockIdx.x * kPilotStride),
+// Work split: blockIdx.x = tile (the pilot launch: tile blockIdx.x * kPilotStride),
 // blockIdx.y = segment: rows [blockIdx.y * segment_spacing, + segment_rows) of their lines
 // (segment_rows a multiple of R; spacing == rows except for the pilot's probes).
 
@@ -149,7 +154,7 @@ __global__ void DecideWindowModeKernel(uint32_t* redo, uint32_t pilot_probes)
 }
 
 template <int kMode, int kR, bool kBorder, bool kSend, int kBlocksPerSm>
-__global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
+__global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     EnvelopeAxisWindowKernel(const uint32_t* __restrict__ in,
                              typename OutputOf<kMode>::Type* __restrict__ out, LineFamily family,
                              FinalizeParams finalize, typename OutputOf<kMode>::Key* min_max_keys,
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(kLineWarpsPerBlock* kWarp, kBlocksPerSm)
   {
     return;  // a deep map: the stack kernel does it all
   }
-  const uint32_t tile_index = block_index * kLineWarpsPerBlock + warp;
+  const uint32_t tile_index = block_index * kWindowWarpsPerBlock + warp;
   if (tile_index >= tiles_per_outer * static_cast<uint32_t>(family.num_outer))
   {
     return;  // warp-uniform

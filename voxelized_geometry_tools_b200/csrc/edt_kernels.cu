@@ -255,8 +255,8 @@ constexpr int64_t kLeanMaxInput = (int64_t{1} << 29) - 1;
 
 // The window kernel over every tile of the family; tiles it gives up on are appended to
 // d_redo_list (layout in edt_envelope_window.cuh; header and flags zeroed here). With enough tiles
-// a pilot launch goes first: it probes two chunks of rows out of every 256 of every 8th group of
-// tiles and decides, on the device, whether the window kernel runs at all. On maps with large
+// a pilot launch goes first: it probes two chunks of rows out of every 256 of every 8th tile
+// and decides, on the device, whether the window kernel runs at all. On maps with large
 // open spaces nearly every tile would end up with the stack kernel anyway, and the window
 // kernel's searches would only be wasted.
 template <int kMode>
@@ -266,7 +266,7 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
                          cudaStream_t stream)
 {
   const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
-  const int64_t blocks = (tiles + kLineWarpsPerBlock - 1) / kLineWarpsPerBlock;
+  const int64_t blocks = (tiles + kWindowWarpsPerBlock - 1) / kWindowWarpsPerBlock;
   if (blocks > 0x7fffffffLL)
   {
     return FailInvalid("grid too large for one launch");
@@ -289,18 +289,18 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   // and the last wave is thin. A segment re-reads 2 R rows of its neighbours.
   constexpr int kRadius = (kMode == kEmitPacked) ? kWindowRadiusPacked : kWindowRadiusFinal;
   const int64_t chunks = (family.length + kRadius - 1) / kRadius;
-  const int64_t wanted_blocks = MultiprocessorCount() * 48;
+  const int64_t wanted_blocks = MultiprocessorCount() * 192 / kWindowWarpsPerBlock;
   int64_t segments = (wanted_blocks + blocks - 1) / blocks;
   segments = std::max<int64_t>(1, std::min<int64_t>(segments, chunks / 3));
   const int segment_rows = static_cast<int>((chunks + segments - 1) / segments) * kRadius;
   segments = (family.length + segment_rows - 1) / segment_rows;
   // (VGT_B200_WINDOW_PILOT=0: no pilot, the window kernel works on every tile)
   const char* pilot_choice = std::getenv("VGT_B200_WINDOW_PILOT");
-  const bool pilot = blocks >= 4 * static_cast<int64_t>(kPilotStride)
+  const bool pilot = tiles >= 16 * static_cast<int64_t>(kPilotStride)
       && !(pilot_choice != nullptr && std::strcmp(pilot_choice, "0") == 0);
   const auto launch = [&](auto kernel)
   {
-    const dim3 threads(kLineWarpsPerBlock * kWarp);
+    const dim3 threads(kWindowWarpsPerBlock * kWarp);
     if (!pilot)
     {
       kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)), threads, 0,
@@ -311,7 +311,7 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
     const int64_t pilot_blocks = (blocks + kPilotStride - 1) / kPilotStride;
     const int64_t probes_per_line = (family.length + kPilotSpacing - 1) / kPilotSpacing;
     const int64_t pilot_probes =
-        std::min<int64_t>(pilot_blocks * kLineWarpsPerBlock, tiles) * probes_per_line;
+        std::min<int64_t>(pilot_blocks * kWindowWarpsPerBlock, tiles) * probes_per_line;
     kernel<<<dim3(static_cast<unsigned>(pilot_blocks), static_cast<unsigned>(probes_per_line)),
              threads, 0, stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list,
                                    std::min(step_rate, kPilotStepRate), 2 * kRadius, kPilotSpacing,
