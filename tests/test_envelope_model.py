@@ -289,9 +289,11 @@ def brev32(x):
 SATURATED = 0x3FFF
 
 
-def window_line(classes, values, radius, step_budget=None):
+def window_line(classes, values, radius, step_budget=None, segment_rows=None):
     """Returns (out, steps), or (None, steps) when the line is given up: the extended search ran
-    past its budget, or an uncertain row's window minimum was saturated."""
+    past its budget, or an uncertain row's window minimum was saturated. segment_rows (a multiple
+    of the radius): the line is cut into segments computed independently, as the kernel's
+    grid.y does; a segment that does not start the line reads its neighbour's rows."""
     n = len(classes)
     chunk = radius
     assert radius % 2 == 0
@@ -325,44 +327,60 @@ def window_line(classes, values, radius, step_budget=None):
         return best
 
     out = [0] * n
-    num_chunks = (n + chunk - 1) // chunk
-    a, ca = load_chunk(-1)
-    b, cb = load_chunk(0)
-    nx, cn = load_chunk(1)
     mask_r = (1 << radius) - 1
-    for k in range(num_chunks):
-        composite = (ca << (2 * chunk)) | (cb << chunk) | cn
-        rows = a + b + nx  # chunk-relative row r at index r + chunk
-        for j in range(chunk):
-            q = k * chunk + j
-            if q >= n:
-                break
-            # pairs (j >> 1) .. (j >> 1) + radius of the row pairs in registers: the rows within
-            # the radius plus one more at distance radius + 1
-            acc = 0xFFFF
-            for g in range(j >> 1, (j >> 1) + radius + 1):
-                for index in (2 * g, 2 * g + 1):
-                    acc = min(acc, rows[index] + (index - chunk - j) ** 2)
-            x = (composite >> (chunk - 1 - j)) & 0xFFFFFFFF
-            query_class = (x >> radius) & 1
-            assert query_class == classes[q]
-            diff = x ^ (0xFFFFFFFF if query_class else 0)
-            both = ((diff & mask_r) | (brev32(diff) >> (31 - 2 * radius))) & mask_r
-            e = radius - 31 + clz32(both)
-            w = min(acc, e * e)
-            if w >= far:
-                # (then no opposite-class row is inside the window and e was the "none" value,
-                # so the search starts from the window minimum alone - unless that is saturated)
-                assert both == 0
-                if acc >= SATURATED:
-                    return None, steps
-                w = extended(q, acc)
-                if step_budget is not None and steps > step_budget:
-                    return None, steps
-            out[q] = min(w, NONE)
-        a, ca = b, cb
-        b, cb = nx, cn
-        nx, cn = load_chunk(k + 2)
+    if segment_rows is None:
+        segment_rows = ((n + chunk - 1) // chunk) * chunk
+    assert segment_rows % chunk == 0
+    for first_row in range(0, n, segment_rows):
+        end_row = min(first_row + segment_rows, n)
+
+        def load_rows(start):
+            # rows start .. start + chunk - 1 (load_chunk with an arbitrary first row)
+            vals, bits = [], 0
+            for i in range(chunk):
+                r = start + i
+                rc = min(max(r, 0), n - 1)
+                vals.append(min(values[rc], SATURATED) if 0 <= r < n else SATURATED)
+                bits = ((bits << 1) | classes[rc]) & 0xFFFFFFFF
+            return vals, bits
+
+        a, ca = load_rows(first_row - chunk)
+        b, cb = load_rows(first_row)
+        nx, cn = load_rows(first_row + chunk)
+        for base in range(first_row, end_row, chunk):
+            composite = (ca << (2 * chunk)) | (cb << chunk) | cn
+            rows = a + b + nx  # chunk-relative row r at index r + chunk
+            for j in range(chunk):
+                q = base + j
+                if q >= n:
+                    break
+                # pairs (j >> 1) .. (j >> 1) + radius of the row pairs in registers: the rows
+                # within the radius plus one more at distance radius + 1
+                acc = 0xFFFF
+                for g in range(j >> 1, (j >> 1) + radius + 1):
+                    for index in (2 * g, 2 * g + 1):
+                        acc = min(acc, rows[index] + (index - chunk - j) ** 2)
+                x = (composite >> (chunk - 1 - j)) & 0xFFFFFFFF
+                query_class = (x >> radius) & 1
+                assert query_class == classes[q]
+                diff = x ^ (0xFFFFFFFF if query_class else 0)
+                both = ((diff & mask_r) | (brev32(diff) >> (31 - 2 * radius))) & mask_r
+                e = radius - 31 + clz32(both)
+                w = min(acc, e * e)
+                if w >= far:
+                    # (then no opposite-class row is inside the window and e was the "none"
+                    # value, so the search starts from the window minimum alone - unless that
+                    # is saturated)
+                    assert both == 0
+                    if acc >= SATURATED:
+                        return None, steps
+                    w = extended(q, acc)
+                    if step_budget is not None and steps > step_budget:
+                        return None, steps
+                out[q] = min(w, NONE)
+            a, ca = b, cb
+            b, cb = nx, cn
+            nx, cn = load_rows(base + 2 * chunk)
     return out, steps
 
 
@@ -376,8 +394,13 @@ def test_window_line_model_matches_brute_force():
             got, _ = window_line(classes, values, radius)
             # (None: a saturated window, the line goes to the stack kernel)
             assert got is None or got == want, (radius, classes, values)
-            if max(v for v in values if v != NONE or True) < SATURATED:
+            if max(values) < SATURATED:
                 assert got == want
+            # the same line cut into segments of one and of three chunks
+            for segment_chunks in (1, 3):
+                cut, _ = window_line(classes, values, radius, segment_rows=segment_chunks * radius)
+                assert cut is None or cut == want, (radius, segment_chunks, classes, values)
+                assert (cut is None) == (got is None)
 
 
 def test_window_line_smooth_and_budget():
