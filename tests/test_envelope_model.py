@@ -300,17 +300,6 @@ def window_line(classes, values, radius, step_budget=None, segment_rows=None):
     far = (radius + 1) ** 2
     steps = 0
 
-    def load_chunk(k):
-        # rows k*chunk .. k*chunk+chunk-1, clamped to SATURATED; out-of-range rows: SATURATED
-        # with the class of the clamped row
-        vals, bits = [], 0
-        for i in range(chunk):
-            r = k * chunk + i
-            rc = min(max(r, 0), n - 1)
-            vals.append(min(values[rc], SATURATED) if 0 <= r < n else SATURATED)
-            bits = ((bits << 1) | classes[rc]) & 0xFFFFFFFF
-        return vals, bits
-
     def extended(q, best):
         # four distances per round, rows clamped to the line, no class / range predicates:
         # a clamped row was already seen at its true, smaller distance

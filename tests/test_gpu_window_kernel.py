@@ -4,8 +4,9 @@ kernel - against the oracle, bit for bit. The routes are forced with the library
 (read at every call): VGT_B200_WINDOW_BUDGET (extended-search steps a warp may spend per 100 rows of
 its tile; 0 sends every tile with an uncertain row to the stack kernel, a huge value
 keeps everything in the window kernel), VGT_B200_WINDOW_PILOT=0 (no pilot launch: the window
-kernel takes every tile whatever the map looks like) and VGT_B200_ENVELOPE=lean (no window kernel
-at all)."""
+kernel takes every tile whatever the map looks like), VGT_B200_WINDOW_STAGE=0 / 1 (rows prefetched
+into registers / staged through shared memory with cp.async, for both passes) and VGT_B200_ENVELOPE=lean (no
+window kernel at all)."""
 import os
 
 import numpy as np
@@ -20,14 +21,15 @@ pytestmark = pytest.mark.gpu
 
 ROUTES = [{"VGT_B200_WINDOW_BUDGET": "0"}, {"VGT_B200_WINDOW_BUDGET": "100000"},
           {"VGT_B200_WINDOW_BUDGET": "25"}, {"VGT_B200_ENVELOPE": "lean"},
-          {"VGT_B200_WINDOW_PILOT": "0"}, {}]
+          {"VGT_B200_WINDOW_PILOT": "0"}, {"VGT_B200_WINDOW_STAGE": "1"},
+          {"VGT_B200_WINDOW_STAGE": "0", "VGT_B200_WINDOW_PILOT": "0"}, {}]
 
 
 @pytest.fixture(params=ROUTES, ids=lambda route: ",".join(f"{k}={v}" for k, v in route.items())
                 or "default")
 def route(request):
     saved = {key: os.environ.get(key) for key in ("VGT_B200_WINDOW_BUDGET", "VGT_B200_ENVELOPE",
-                                                  "VGT_B200_WINDOW_PILOT")}
+                                                  "VGT_B200_WINDOW_PILOT", "VGT_B200_WINDOW_STAGE")}
     for key in saved:
         os.environ.pop(key, None)
     os.environ.update(request.param)

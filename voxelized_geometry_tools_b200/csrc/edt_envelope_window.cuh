@@ -76,6 +76,27 @@ constexpr int kDeepestSearchFloor = 64;
 // Values in the register window are clamped to this (16-bit halves; + (R + 1)^2 must fit).
 constexpr uint32_t kSaturated = 0x3fffu;
 
+// Staged variant (kStage): the rows of the chunks ahead travel global -> shared memory with
+// cp.async (4 bytes per lane and row, each lane later reads back only what it copied itself, so
+// no barrier is needed), two chunks ahead, tracked by cp.async groups instead of the load
+// scoreboards the register prefetch shares between its 12 loads in flight.
+__device__ __forceinline__ void CopyRowAsync(uint32_t* shared_word, const void* global_word)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(shared_word))),
+               "l"(global_word)
+               : "memory");
+}
+__device__ __forceinline__ void CommitAsyncCopies()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void WaitForAsyncCopies()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
 // Continues the search of one row beyond the register window: rows q - d and q + d for
 // d = first_d, first_d + 1, ... while d^2 can still improve on `best`. Convergent and branch-free
 // inside: EVERY lane of the warp evaluates every candidate, four distances per vote. That is
@@ -153,7 +174,7 @@ __global__ void DecideWindowModeKernel(uint32_t* redo, uint32_t pilot_probes)
   redo[kRedoCount] = 0u;
 }
 
-template <int kMode, int kR, bool kBorder, bool kSend, int kBlocksPerSm>
+template <int kMode, int kR, bool kBorder, bool kSend, int kBlocksPerSm, bool kStage = false>
 __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     EnvelopeAxisWindowKernel(const uint32_t* __restrict__ in,
                              typename OutputOf<kMode>::Type* __restrict__ out, LineFamily family,
@@ -240,7 +261,15 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   // the current chunk on, so they are absorbed (clamped, packed, class bits filed) right there,
   // and each register is reloaded with the row one chunk further after its own row: every load
   // has about a chunk of work to land.
-  uint32_t raw[kR];
+  uint32_t raw[kStage ? 1 : kR];
+  // kStage: three chunk buffers of R rows x 32 lanes in shared memory instead (one warp per
+  // block); absorb_buffer holds the next chunk, the one after it is in flight, fill_buffer takes
+  // the chunk three ahead.
+  __shared__ uint32_t stage[kStage ? 3 * kR * kWarp : 1];
+  static_assert(!kStage || kWindowWarpsPerBlock == 1, "the stage buffers are per block");
+  uint32_t* const stage_lane = stage + lane;
+  int absorb_buffer = 0;
+  int fill_buffer = 2;
 
   const auto load_clamped = [&](const int row) { return load_row(min(max(row, 0), last_row)); };
   const auto clamped_value = [&](const uint32_t word) { return min(word & kNone, kSaturated); };
@@ -387,8 +416,14 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   const auto compute_chunk = [&](const int base, auto edge)
   {
     constexpr bool kEdge = decltype(edge)::value;
+    // (kStage: the chunk three ahead is fetched, else the chunk two ahead)
+    constexpr int kAhead = kStage ? 3 : 2;
     const char* const read_next =
-        line + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(base + 2 * kR);
+        line + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(base + kAhead * kR);
+    if constexpr (kStage)
+    {
+      WaitForAsyncCopies<1>();  // everything but the newest group: the next chunk has landed
+    }
     char* const write_base =
         write_origin + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(base);
 #pragma unroll
@@ -398,16 +433,20 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       if ((j & 1) == 0)
       {
         // rows j, j + 1 of the next chunk (rows q + R, q + R + 1 of the line): needed from here on
-        uint32_t low = clamped_value(raw[j]);
-        uint32_t high = clamped_value(raw[j + 1]);
+        const uint32_t low_word =
+            kStage ? stage_lane[(absorb_buffer * kR + j) * kWarp] : raw[kStage ? 0 : j];
+        const uint32_t high_word =
+            kStage ? stage_lane[(absorb_buffer * kR + j + 1) * kWarp] : raw[kStage ? 0 : j + 1];
+        uint32_t low = clamped_value(low_word);
+        uint32_t high = clamped_value(high_word);
         if constexpr (kEdge)
         {
           low = (q + kR > last_row) ? kSaturated : low;
           high = (q + kR + 1 > last_row) ? kSaturated : high;
         }
         next_pairs[j >> 1] = __byte_perm(low, high, 0x5410);
-        classes |= (static_cast<uint64_t>(raw[j] >> 31) << (kR - 1 - j))
-            | (static_cast<uint64_t>(raw[j + 1] >> 31) << (kR - 2 - j));
+        classes |= (static_cast<uint64_t>(low_word >> 31) << (kR - 1 - j))
+            | (static_cast<uint64_t>(high_word >> 31) << (kR - 2 - j));
       }
       if (!kEdge || q <= last_row)  // warp-uniform
       {
@@ -461,16 +500,26 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
         }
         emit_row(q, j, write_base, same & 1u, best);
       }
-      // raw[j] was absorbed (at row j or j - 1): reload it
-      if constexpr (kEdge)
+      // raw[j] was absorbed (at row j or j - 1): reload it (kStage: fetch row j of the chunk
+      // three ahead into the buffer whose rows were absorbed during the previous chunk)
+      const char* const next_row = kEdge
+          ? line + static_cast<uint64_t>(stride_bytes)
+              * static_cast<uint32_t>(min(base + kAhead * kR + j, last_row))
+          : read_next + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(j);
+      if constexpr (kStage)
       {
-        raw[j] = load_clamped(base + 2 * kR + j);
+        CopyRowAsync(stage_lane + (fill_buffer * kR + j) * kWarp, next_row);
       }
       else
       {
-        raw[j] = *reinterpret_cast<const uint32_t*>(
-            read_next + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(j));
+        raw[j] = *reinterpret_cast<const uint32_t*>(next_row);
       }
+    }
+    if constexpr (kStage)
+    {
+      CommitAsyncCopies();
+      fill_buffer = absorb_buffer;
+      absorb_buffer = (absorb_buffer == 2) ? 0 : absorb_buffer + 1;
     }
     // the next chunk becomes the current one
 #pragma unroll
@@ -510,15 +559,36 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       classes = (classes << 2) | ((low_word >> 31) << 1) | (high_word >> 31);
     }
     classes <<= kR;
-#pragma unroll
-    for (int i = 0; i < kR; i++)
+    if constexpr (kStage)
     {
-      raw[i] = load_clamped(first_row + kR + i);
+      // the next chunk into buffer 0, the one after it into buffer 1, one group each
+#pragma unroll
+      for (int ahead = 0; ahead < 2; ahead++)
+      {
+#pragma unroll
+        for (int i = 0; i < kR; i++)
+        {
+          const int row = min(first_row + (1 + ahead) * kR + i, last_row);
+          CopyRowAsync(stage_lane + (ahead * kR + i) * kWarp,
+                       line + static_cast<uint64_t>(static_cast<uint32_t>(row)) * stride_bytes);
+        }
+        CommitAsyncCopies();
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < kR; i++)
+      {
+        raw[i] = load_clamped(first_row + kR + i);
+      }
     }
     int base = first_row;
-    // chunks whose own rows and whose prefetched chunk (rows base + 2 R ..) lie inside the line
+    // chunks whose own rows and whose prefetched chunk (rows base + 2 R .., kStage: + 3 R ..) lie
+    // inside the line
+    constexpr int kInteriorSpan = kStage ? 4 : 3;
 #pragma unroll 1
-    for (; base + 3 * kR <= length && base < end_row && !over_budget; base += kR)
+    for (; base + kInteriorSpan * kR <= length && base < end_row && !over_budget; base += kR)
     {
       compute_chunk(base, Interior{});
     }
@@ -528,6 +598,10 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       compute_chunk(base, Edge{});
     }
     flush_pending();
+    if constexpr (kStage)
+    {
+      WaitForAsyncCopies<0>();  // nothing of this warp may still be in flight when it exits
+    }
   }
 
   if (block_select == kSelectPilot)

@@ -321,11 +321,22 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
              stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list, step_rate,
                        segment_rows, segment_rows, kSelectAfterPilot);
   };
+  // Rows reach the registers either by plain loads one chunk ahead (the y pass: 0.59 ms against
+  // 0.61 staged at 512^3) or through shared memory with cp.async two chunks ahead (the finalizing
+  // x pass: 0.62 ms against 0.66). VGT_B200_WINDOW_STAGE=0 / 1 forces one variant for both.
+  const char* stage_choice = std::getenv("VGT_B200_WINDOW_STAGE");
+  const bool forced = stage_choice != nullptr
+      && (std::strcmp(stage_choice, "0") == 0 || std::strcmp(stage_choice, "1") == 0);
+  const bool staged = forced ? stage_choice[0] == '1' : kMode != kEmitPacked;
   if constexpr (kMode == kEmitPacked)
   {
     if (family.out_parts > 0)
     {
       launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, true, kWindowBlocksPacked>);
+    }
+    else if (staged)
+    {
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, false, 32, true>);
     }
     else
     {
@@ -338,7 +349,18 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   }
   else if (finalize.add_virtual_border != 0)
   {
-    launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, false, kWindowBlocksFinal>);
+    if (staged)
+    {
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, false, 32, true>);
+    }
+    else
+    {
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, false, kWindowBlocksFinal>);
+    }
+  }
+  else if (staged)
+  {
+    launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, false, 32, true>);
   }
   else
   {
