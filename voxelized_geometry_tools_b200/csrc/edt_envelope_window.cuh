@@ -12,16 +12,19 @@
 //     rows within R of q is the exact D(q) whenever W(q) < (R + 1)^2 - it certifies itself.
 // Here one lane owns one line (a warp = 32 adjacent lines, every row access is one 128-byte
 // segment, as in the stack kernels) and keeps the 3 R rows around the current chunk of R rows in
-// registers, so T costs one VIADDMNMX per candidate row (2 R per voxel, the squared offsets are
-// immediates) and e comes from a class-bit window with one BREV and one FLO. No shared memory,
-// no scratch, the input is read once and not modified: 4 B in + 4 B out per voxel.
+// registers, two rows per register as 16-bit halves, so T costs one VIADDMNMX.U16x2 per two
+// candidate rows (R + 1 per voxel, the squared offsets are immediates) and e comes from a
+// class-bit window with one BREV and one FLO. The rows ahead arrive by plain loads one chunk
+// ahead (y pass) or through shared memory with cp.async two chunks ahead (x pass). No scratch,
+// the input is read once and not modified: 4 B in + 4 B out per voxel.
 //
 // Rows that do not certify (distance to the opposite class > R voxels) continue the same search
-// outwards, row pair by row pair, until d^2 reaches the best value so far - exact for any input
-// but O(distance) per voxel, so the warp counts those steps and, past its budget, hands its tile
-// to the stack kernel (EnvelopeAxisLeanKernel over the redo list) instead. Distance fields of
-// cluttered maps (distances of a few voxels nearly everywhere) stay on the fast path; open
-// terrain goes to the stack kernel after a bounded amount of wasted work.
+// outwards, four row pairs per vote, until d^2 reaches the best value so far - exact for any
+// input but O(distance) per voxel, so the warp counts those steps and, past its allowance (or at
+// a row in open space), hands its tile to the stack kernel (EnvelopeAxisLeanKernel over the redo
+// list) instead. Distance fields of cluttered maps (distances of a few voxels nearly everywhere)
+// stay on the fast path; for maps of open space a pilot launch (a probe over a sample of rows)
+// decides on the device that the stack kernel takes every tile and this kernel stands down.
 //
 // Replaces the same reference loops as the stack kernels: the X / Y loops of
 // ComputeDistanceFieldTransformInPlace (sdfgen.cpp:276-351) with the 1-D transforms
