@@ -1,0 +1,87 @@
+"""CPU: the SASS of the built library carries the instructions the design relies on (cuobjdump
+reads the sm_100a cubin without a GPU). A regression here means the compiler no longer emits what
+DESIGN.md section 3 describes, whatever the timings say later:
+  * the window kernels' candidate search is VIADDMNMX.U16x2 (two rows per instruction) and the
+    extended search VIADDMNMX.U32, no integer min emulation;
+  * the staged window kernels fetch their rows with LDGSTS (cp.async) and wait on LDGDEPBAR /
+    DEPBAR groups, the others with plain loads;
+  * the z scan moves 16 bytes per lane and instruction;
+  * the voxelizer's counters are RED atomics (no return value) and its arithmetic keeps separate
+    double multiplies and adds (-fmad=false: the DDA must reproduce the CPU's double-precision
+    steps; the DFMAs that remain belong to the correctly rounded division sequences)."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def sass_by_function(shared_library):
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    result = subprocess.run([cuobjdump, "-sass", str(shared_library)], capture_output=True,
+                            text=True, timeout=300)
+    assert result.returncode == 0, result.stderr[-2000:]
+    functions, name = {}, None
+    for line in result.stdout.splitlines():
+        match = re.search(r"Function : (\S+)", line)
+        if match:
+            name = match.group(1)
+            functions[name] = []
+        elif name is not None:
+            functions[name].append(line)
+    assert functions, "no device functions found in the library"
+    return {key: "\n".join(lines) for key, lines in functions.items()}
+
+
+def functions_named(sass_by_function, fragment):
+    found = {k: v for k, v in sass_by_function.items() if fragment in k}
+    assert found, f"no kernel named *{fragment}* in the library"
+    return found
+
+
+def test_library_is_sm_100a_only(shared_library):
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    listing = subprocess.run([cuobjdump, "-lelf", str(shared_library)], capture_output=True,
+                             text=True, timeout=120).stdout
+    archs = set(re.findall(r"sm_\d+a?", listing))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_window_kernels_use_the_packed_add_min(sass_by_function):
+    kernels = functions_named(sass_by_function, "EnvelopeAxisWindowKernel")
+    for name, sass in kernels.items():
+        radius = int(re.search(r"EnvelopeAxisWindowKernelILi\dELi(\d+)E", name).group(1))
+        packed = sass.count("VIADDMNMX.U16x2")
+        # two unrolled chunk bodies (interior / edge) x R rows x (R + 1) pairs
+        assert packed >= 2 * radius * (radius + 1), (name, packed)
+        assert "VIADDMNMX.U32" in sass, name          # the extended search
+        assert "BREV" in sass and "FLO" in sass, name  # nearest opposite-class row
+
+
+def test_staged_window_kernels_use_async_copies(sass_by_function):
+    kernels = functions_named(sass_by_function, "EnvelopeAxisWindowKernel")
+    staged = {k: v for k, v in kernels.items() if k.rstrip("_").find("ELb1EEEv") != -1
+              and re.search(r"ELi\d+ELb1EEEv", k)}
+    assert staged, "no staged (kStage = true) window kernel was instantiated"
+    for name, sass in kernels.items():
+        if name in staged:
+            assert "LDGSTS" in sass, name
+            assert "LDGDEPBAR" in sass or "DEPBAR" in sass, name
+        else:
+            assert "LDGSTS" not in sass, name
+
+
+def test_z_scan_moves_sixteen_bytes_per_lane(sass_by_function):
+    for name, sass in functions_named(sass_by_function, "ScanContiguousAxisRegistersKernel").items():
+        if "Float4Source" in name or "12Float4Source" in name:
+            assert re.search(r"LDG\.E(\.[A-Z]+)*\.128", sass), name
+        assert re.search(r"STG\.E(\.[A-Z]+)*\.128", sass), name
+
+
+def test_voxelizer_uses_reductions_and_separate_multiplies(sass_by_function):
+    raycast = functions_named(sass_by_function, "RaycastCloudKernel")
+    for name, sass in raycast.items():
+        assert re.search(r"\bRED(G)?\.", sass), name
+        assert "ATOMG" not in sass, name              # no atomic that returns a value
+        assert sass.count("DMUL") >= 10 and sass.count("DADD") >= 10, name
