@@ -114,3 +114,21 @@ def test_synthetic_generators_are_deterministic_and_consistent():
     assert 0.05 < (a == 1.0).mean() < 0.16 and 0.005 < (a == 0.5).mean() < 0.015
     rng = synthetic.Mt19937_64(5489)
     assert rng.next_u64() == 14514284786278117030     # the published first output of mt19937_64
+
+
+def test_bench_finds_the_ncu_traffic_of_every_pass():
+    # bench.py reports roofline.traffic from profiles/ncu_traffic.json; a renamed kernel label
+    # would silently turn it into null
+    import importlib.util
+    from pathlib import Path
+    repo = Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("bench_module", repo / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    dims = bench.workload_dims(1)
+    for name in bench.PASS_NAMES:
+        traffic = bench.ncu_dram_bytes_per_launch(dims, name)
+        assert traffic is not None, name
+        voxels = dims[0] * dims[1] * dims[2]
+        # between the algorithmic 8 B/voxel (minus what L2 keeps) and twice that
+        assert 0.9 * bench.PASS_BYTES_PER_VOXEL * voxels < traffic < 2 * bench.PASS_BYTES_PER_VOXEL * voxels
