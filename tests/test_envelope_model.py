@@ -289,31 +289,32 @@ def brev32(x):
 SATURATED = 0x3FFF
 
 
-def window_line(classes, values, radius, step_budget=None, segment_rows=None):
-    """Returns (out, steps), or (None, steps) when the line is given up: the extended search ran
-    past its budget, or an uncertain row's window minimum was saturated. segment_rows (a multiple
-    of the radius): the line is cut into segments computed independently, as the kernel's
-    grid.y does; a segment that does not start the line reads its neighbour's rows."""
+DEEPEST_CAP = 120
+
+
+def window_line(classes, values, radius, step_budget=None, segment_rows=None, deepest=None):
+    """Returns (out, steps), or (None, steps) when the line is given up: the joint search ran
+    past its budget or its depth cap, or a row that needs it has a saturated minimum.
+    segment_rows (a multiple of the radius): the line is cut into segments computed
+    independently, as the kernel's grid.y does; a segment that does not start the line reads its
+    neighbour's rows.
+
+    Per chunk of R rows, as the kernel: phase A = window minimum + nearest opposite-class row
+    inside the window for every row (16-bit results); phase B, only when some row is not
+    certified = the rows of the register window beyond each row's own window (class-agnostic,
+    plus the nearest opposite-class row of the neighbouring chunks), then rows loaded from memory
+    that serve ALL rows of the chunk at once, four per side and round; phase C = emit."""
     n = len(classes)
     chunk = radius
     assert radius % 2 == 0
     far = (radius + 1) ** 2
     steps = 0
+    if deepest is None:
+        deepest = min(DEEPEST_CAP, max(64, n >> 3))
 
-    def extended(q, best):
-        # four distances per round, rows clamped to the line, no class / range predicates:
-        # a clamped row was already seen at its true, smaller distance
-        nonlocal steps
-        d = radius + 1
-        reach = max(q, n - 1 - q)
-        while d * d < best and d <= reach:
-            steps += 4
-            for u in range(4):
-                for r in (max(q - d - u, 0), min(q + d + u, n - 1)):
-                    height = values[r] if classes[r] == classes[q] else 0
-                    best = min(best, height + (d + u) ** 2)
-            d += 4
-        return best
+    def u16(x):
+        assert 0 <= x < 65536, x
+        return x
 
     out = [0] * n
     mask_r = (1 << radius) - 1
@@ -339,34 +340,83 @@ def window_line(classes, values, radius, step_budget=None, segment_rows=None):
         for base in range(first_row, end_row, chunk):
             composite = (ca << (2 * chunk)) | (cb << chunk) | cn
             rows = a + b + nx  # chunk-relative row r at index r + chunk
+            # ---- phase A
+            best = [0] * chunk
             for j in range(chunk):
                 q = base + j
                 if q >= n:
                     break
-                # pairs (j >> 1) .. (j >> 1) + radius of the row pairs in registers: the rows
-                # within the radius plus one more at distance radius + 1
                 acc = 0xFFFF
                 for g in range(j >> 1, (j >> 1) + radius + 1):
                     for index in (2 * g, 2 * g + 1):
-                        acc = min(acc, rows[index] + (index - chunk - j) ** 2)
+                        acc = min(acc, u16(rows[index] + (index - chunk - j) ** 2))
                 x = (composite >> (chunk - 1 - j)) & 0xFFFFFFFF
                 query_class = (x >> radius) & 1
                 assert query_class == classes[q]
                 diff = x ^ (0xFFFFFFFF if query_class else 0)
                 both = ((diff & mask_r) | (brev32(diff) >> (31 - 2 * radius))) & mask_r
                 e = radius - 31 + clz32(both)
-                w = min(acc, e * e)
-                if w >= far:
-                    # (then no opposite-class row is inside the window and e was the "none"
-                    # value, so the search starts from the window minimum alone - unless that
-                    # is saturated)
-                    assert both == 0
-                    if acc >= SATURATED:
+                # (no opposite-class row inside the window: no such candidate)
+                best[j] = min(acc, e * e) if both else acc
+            # ---- phase B
+            if max(best) >= far:
+                chunk_class = (cb >> (chunk - 1)) & 1
+                uniform = cb == (mask_r if chunk_class else 0)
+                flip = mask_r if chunk_class else 0
+                # nearest opposite-class row of the previous / next chunk (lanes whose chunk is
+                # of one class only; 200 = none)
+                d_prev = (ca ^ flip) & mask_r
+                d_next = (cn ^ flip) & mask_r
+                c_below = 200
+                c_above = 200
+                if uniform and d_prev:
+                    c_below = 1 + ((d_prev & -d_prev).bit_length() - 1)
+                if uniform and d_next:
+                    c_above = 1 + (chunk - 1 - (d_next.bit_length() - 1))
+                for j in range(chunk):
+                    best[j] = min(best[j], u16((c_below + j) ** 2))
+                    best[j] = min(best[j], u16((c_above + chunk - 1 - j) ** 2))
+                # class-agnostic candidates: the rows of the register window a row's own window
+                # did not reach (pairs of output rows: the low row may see a row twice)
+                for k in range(chunk - 1):          # row base - R + k
+                    for pair in range(chunk // 2):
+                        if 2 * pair + 1 > k:
+                            for j in (2 * pair, 2 * pair + 1):
+                                best[j] = min(best[j], u16(a[k] + (j + chunk - k) ** 2))
+                for m in range(1, chunk):           # row base + R + m
+                    for pair in range(chunk // 2):
+                        if 2 * pair < m:
+                            for j in (2 * pair, 2 * pair + 1):
+                                best[j] = min(best[j], u16(nx[m] + (chunk + m - j) ** 2))
+                if max(best) >= SATURATED:
+                    return None, steps
+                t = 0
+                while True:
+                    worst = max(best)
+                    below_open = base - chunk - 1 - t >= 0
+                    above_open = base + 2 * chunk + t <= n - 1
+                    if not ((chunk + 1 + t) ** 2 < worst and (below_open or above_open)):
+                        break
+                    if (step_budget is not None and steps > step_budget) \
+                            or chunk + 1 + t + 3 > deepest:
                         return None, steps
-                    w = extended(q, acc)
-                    if step_budget is not None and steps > step_budget:
-                        return None, steps
-                out[q] = min(w, NONE)
+                    steps += 4
+                    for u in range(4):
+                        for row, distance in ((max(base - chunk - 1 - t - u, 0),
+                                               lambda j: j + chunk + 1 + t + u),
+                                              (min(base + 2 * chunk + t + u, n - 1),
+                                               lambda j: 2 * chunk + t + u - j)):
+                            height = min(values[row], SATURATED) \
+                                if classes[row] == chunk_class else 0
+                            for j in range(chunk):
+                                best[j] = min(best[j], u16(height + distance(j) ** 2))
+                    t += 4
+                if max(best) >= SATURATED:
+                    return None, steps
+            # ---- phase C
+            for j in range(chunk):
+                if base + j < n:
+                    out[base + j] = min(best[j], NONE)
             a, ca = b, cb
             b, cb = nx, cn
             nx, cn = load_rows(base + 2 * chunk)
@@ -394,16 +444,21 @@ def test_window_line_model_matches_brute_force():
 
 def test_window_line_smooth_and_budget():
     rng = random.Random(4)
+    solved = 0
     for _ in range(200):
         n = rng.choice([64, 100, 130])
         centre, offset = rng.uniform(0, n), rng.randint(1, 50)
         classes = [1 if abs(i - n / 3) < 4 else 0 for i in range(n)]
         values = [int((i - centre) ** 2) + offset for i in range(n)]
         want = brute_line(classes, values)
-        got, steps = window_line(classes, values, 8)
-        assert got == want
+        got, steps = window_line(classes, values, 8, deepest=DEEPEST_CAP)
+        # (None: some row needs rows further away than the depth cap of the 16-bit search)
+        assert got is None or got == want
+        solved += got is not None
         # a budget below the steps taken reports the line for the stack kernel instead
-        if steps > 0:
-            assert window_line(classes, values, 8, step_budget=steps - 4)[0] is None
+        if got is not None and steps > 0:
+            assert window_line(classes, values, 8, step_budget=steps - 5,
+                               deepest=DEEPEST_CAP)[0] is None
+    assert solved > 100
     # one class, no values at all: the window is saturated, the line is given up
     assert window_line([0] * 50, [NONE] * 50, 8)[0] is None

@@ -100,64 +100,33 @@ __device__ __forceinline__ void WaitForAsyncCopies()
   asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
-// Continues the search of one row beyond the register window: rows q - d and q + d for
-// d = first_d, first_d + 1, ... while d^2 can still improve on `best`. Convergent and branch-free
-// inside: EVERY lane of the warp evaluates every candidate, four distances per vote. That is
-// harmless for the lanes that need nothing: a candidate at distance d is at least d^2, and a lane
-// is only done once d^2 >= its best (a certified lane's best is below first_d^2 from the start),
-// so such a candidate never wins. Rows past the ends of the line are clamped to the end rows:
-// the end row was already seen at its true, smaller distance, so the clamped candidate never
-// wins either. Gives up (returns with the step counter past the budget, the caller then hands
-// the tile to the stack kernel) once the counter passes the budget or d passes `deepest`.
-__device__ __noinline__ uint32_t ExtendedRowSearch(const char* line, uint32_t stride_bytes, int q,
-                                                   int last_row, uint32_t class_bit, uint32_t best,
-                                                   bool uncertain, int first_d, int deepest,
-                                                   uint32_t budget, uint32_t* steps)
+// Deepest row distance the 16-bit joint search looks at: clamped values (0x3fff) plus squared
+// offsets must fit 16 bits and a result is only exact below kSaturated, i.e. up to 127 voxels.
+constexpr int kJointDeepestCap = 120;
+// "No opposite-class row in the neighbouring chunk" for the joint search: far enough that its
+// square beats no real candidate, small enough that (kNoRow + R)^2 fits 16 bits.
+constexpr uint32_t kNoRow = 200u;
+
+// Calls f(std::integral_constant<int, 0>{}) ... f(std::integral_constant<int, kCount - 1>{}).
+template <int kCount, int kIndex = 0, typename F>
+__device__ __forceinline__ void StaticFor(F&& f)
 {
-  constexpr int kUnroll = 4;
-  int d = first_d;
-  uint32_t used = *steps;
-  // the furthest row of the line from q: nothing to find beyond it
-  const int reach = max(q, last_row - q);
-  while (true)
+  if constexpr (kIndex < kCount)
   {
-    const bool need = uncertain && static_cast<uint32_t>(d * d) < best && d <= reach;
-    if (!__any_sync(0xffffffffu, need))
-    {
-      break;
-    }
-    if (used > budget || d > deepest)
-    {
-      used = max(used, budget + 1u);  // the caller gives the tile up
-      break;
-    }
-    used += kUnroll;
-    uint32_t words_below[kUnroll], words_above[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; u++)
-    {
-      const int below = __viaddmax_s32(q, -(d + u), 0);
-      const int above = __viaddmin_s32(q, d + u, last_row);
-      words_below[u] = *reinterpret_cast<const uint32_t*>(
-          line + static_cast<uint64_t>(static_cast<uint32_t>(below)) * stride_bytes);
-      words_above[u] = *reinterpret_cast<const uint32_t*>(
-          line + static_cast<uint64_t>(static_cast<uint32_t>(above)) * stride_bytes);
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; u++)
-    {
-      const uint32_t dd = static_cast<uint32_t>((d + u) * (d + u));
-      const uint32_t height_below =
-          static_cast<uint32_t>(max(static_cast<int32_t>(words_below[u] ^ class_bit), 0));
-      const uint32_t height_above =
-          static_cast<uint32_t>(max(static_cast<int32_t>(words_above[u] ^ class_bit), 0));
-      best = __viaddmin_u32(height_below, dd, best);
-      best = __viaddmin_u32(height_above, dd, best);
-    }
-    d += kUnroll;
+    f(std::integral_constant<int, kIndex>{});
+    StaticFor<kCount, kIndex + 1>(f);
   }
-  *steps = used;
-  return best;
+}
+
+// min(best, (c + a_low)^2 | (c + a_high)^2 << 16) per 16-bit half; c_squared = c * c * 0x10001.
+template <int kLow, int kHigh>
+__device__ __forceinline__ uint32_t FoldSquaredDistances(uint32_t best, uint32_t c,
+                                                         uint32_t c_squared)
+{
+  constexpr uint32_t kLinear = static_cast<uint32_t>(2 * kLow) | (static_cast<uint32_t>(2 * kHigh) << 16);
+  constexpr uint32_t kConstant =
+      static_cast<uint32_t>(kLow * kLow) | (static_cast<uint32_t>(kHigh * kHigh) << 16);
+  return __viaddmin_u16x2(c * kLinear + c_squared, kConstant, best);
 }
 
 // Work split: blockIdx.x = tile (the pilot launch: tile blockIdx.x * kPilotStride),
@@ -289,7 +258,7 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     return;  // warp-uniform
   }
   const uint32_t credit_rows = static_cast<uint32_t>(segment_rows >> 2) + 16u;
-  const int deepest_search = max(kDeepestSearchFloor, length >> 3);
+  const int deepest_search = min(kJointDeepestCap, max(kDeepestSearchFloor, length >> 3));
 
   // Send layout only: the virtual origin of the current part and the row at which the next
   // part starts (the segment's first row forces the first look-up).
@@ -414,8 +383,14 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     }
   };
 
-  // The rows base .. base + R - 1 (kEdge: only those inside the line), and the loads of the rows
-  // base + 2 R .. base + 3 R - 1 (kEdge: clamped to the line) into `raw`.
+  // One chunk: the rows base .. base + R - 1 (kEdge: only those inside the line), and the loads
+  // of the rows base + 2 R .. base + 3 R - 1 (kEdge: clamped to the line) into `raw`.
+  //   phase A  every row's window minimum and nearest opposite-class row inside the window,
+  //            results as 16-bit pairs (low half = the even row);
+  //   phase B  only when some lane holds a row that did not certify itself: first the rows of
+  //            the register window beyond each row's own window, then rows from memory, each
+  //            of which serves ALL rows of the chunk (one load, R / 2 paired add-mins);
+  //   phase C  the rows are emitted.
   const auto compute_chunk = [&](const int base, auto edge)
   {
     constexpr bool kEdge = decltype(edge)::value;
@@ -429,6 +404,9 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     }
     char* const write_base =
         write_origin + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(base);
+    uint32_t best_pairs[kPairs];
+    uint32_t even_best = 0;
+    // ---------------------------------------------------------------------------------- phase A
 #pragma unroll
     for (int j = 0; j < kR; j++)
     {
@@ -451,11 +429,14 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
         classes |= (static_cast<uint64_t>(low_word >> 31) << (kR - 1 - j))
             | (static_cast<uint64_t>(high_word >> 31) << (kR - 2 - j));
       }
+      // (a row past the end of the line: 0, so that it never asks for a search)
+      uint32_t best = 0;
       if (!kEdge || q <= last_row)  // warp-uniform
       {
         // Pairs g = (j >> 1) .. (j >> 1) + R of the 3 R / 2 pairs in registers cover the rows
         // q - R .. q + R plus one row at distance R + 1 (a true candidate like the others).
-        uint32_t best_pair = 0xffffffffu;
+        // Two accumulators: half the dependent chain.
+        uint32_t chains[2] = {0xffffffffu, 0xffffffffu};
 #pragma unroll
         for (int t = 0; t <= kR; t++)
         {
@@ -469,8 +450,9 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
               ? previous_pairs[(g < kPairs) ? g : 0]
               : ((g < 2 * kPairs) ? current_pairs[(g >= kPairs && g < 2 * kPairs) ? g - kPairs : 0]
                                   : next_pairs[(g >= 2 * kPairs) ? g - 2 * kPairs : 0]);
-          best_pair = __viaddmin_u16x2(pair, offsets, best_pair);
+          chains[t & 1] = __viaddmin_u16x2(pair, offsets, chains[t & 1]);
         }
+        const uint32_t best_pair = __vminu2(chains[0], chains[1]);
         const uint32_t window_best = min(best_pair & 0xffffu, best_pair >> 16);
         // class window of row q: bit R = row q, bit R - d = row q + d, bit R + d = row q - d
         const uint32_t window = static_cast<uint32_t>(classes >> (kR - 1 - j));
@@ -479,29 +461,19 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
         const uint32_t differs = window ^ same;
         // rows at distance d on either side folded onto bit R - d; the highest set bit = nearest
         const uint32_t folded = (differs | (__brev(differs) >> (31 - 2 * kR))) & kSideMask;
-        const int nearest = kR - 31 + __clz(static_cast<int>(folded));  // R + 1: there is none
-        uint32_t best = min(window_best, static_cast<uint32_t>(nearest * nearest));
-        const bool uncertain = best >= kFar;
-        if (__any_sync(0xffffffffu, uncertain))
-        {
-          // (an uncertain row has no opposite-class row inside the window, so its search starts
-          // from the window minimum alone; the other lanes only vote). A saturated window
-          // minimum says nothing: open space, the tile is given up.
-          if (__any_sync(0xffffffffu, uncertain && window_best >= kSaturated))
-          {
-            over_budget = true;
-          }
-          else
-          {
-            const uint32_t allowance =
-                (step_rate * (static_cast<uint32_t>(q - first_row) + credit_rows)) >> 7;
-            best = ExtendedRowSearch(line, stride_bytes, q, last_row, same & kClassBit,
-                                     uncertain ? window_best : best, uncertain, kR + 1,
-                                     deepest_search, allowance, &steps);
-            over_budget = over_budget || steps > allowance;
-          }
-        }
-        emit_row(q, j, write_base, same & 1u, best);
+        const int nearest = kR - 31 + __clz(static_cast<int>(folded));
+        // (no opposite-class row inside the window: no such candidate)
+        const uint32_t nearest_squared =
+            (folded != 0u) ? static_cast<uint32_t>(nearest * nearest) : 0xffffu;
+        best = min(window_best, nearest_squared);
+      }
+      if ((j & 1) == 0)
+      {
+        even_best = best;
+      }
+      else
+      {
+        best_pairs[j >> 1] = __byte_perm(even_best, best, 0x5410);
       }
       // raw[j] was absorbed (at row j or j - 1): reload it (kStage: fetch row j of the chunk
       // three ahead into the buffer whose rows were absorbed during the previous chunk)
@@ -523,6 +495,174 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       CommitAsyncCopies();
       fill_buffer = absorb_buffer;
       absorb_buffer = (absorb_buffer == 2) ? 0 : absorb_buffer + 1;
+    }
+    // ---------------------------------------------------------------------------------- phase B
+    // The largest result of this lane's rows: a row is certified iff its result is below kFar.
+    const auto worst_of_lane = [&]()
+    {
+      uint32_t worst_pair = best_pairs[0];
+#pragma unroll
+      for (int p = 1; p < kPairs; p++)
+      {
+        worst_pair = __vmaxu2(worst_pair, best_pairs[p]);
+      }
+      return max(worst_pair & 0xffffu, worst_pair >> 16);
+    };
+    uint32_t worst = worst_of_lane();
+    if (__any_sync(0xffffffffu, worst >= kFar))
+    {
+      // A lane with an uncertified row has no opposite-class row within R of that row, so all
+      // its rows of this chunk are of one class, the class of row `base`. (Lanes whose chunk is
+      // of both classes hold certified rows only - bounded by (R - 1)^2 - and no candidate
+      // below, at distance > R, can win against those.)
+      const uint32_t chunk_bits = static_cast<uint32_t>(classes >> kR) & kSideMask;
+      const uint32_t chunk_filled = (chunk_bits >> (kR - 1)) & 1u;
+      const uint32_t flip = chunk_filled ? kSideMask : 0u;
+      const bool one_class = chunk_bits == flip;
+      // Nearest opposite-class row of the previous chunk (distance c from row `base`) and of
+      // the next chunk (distance c from the chunk's last row): candidates (c + j)^2 and
+      // (c + R - 1 - j)^2 for row j.
+      {
+        const uint32_t differs_before = (static_cast<uint32_t>(classes >> (2 * kR)) ^ flip) & kSideMask;
+        const uint32_t differs_after = (static_cast<uint32_t>(classes) ^ flip) & kSideMask;
+        const uint32_t below = (one_class && differs_before != 0u)
+            ? static_cast<uint32_t>(__ffs(static_cast<int>(differs_before)))
+            : kNoRow;
+        const uint32_t above = (one_class && differs_after != 0u)
+            ? static_cast<uint32_t>(kR - 31 + __clz(static_cast<int>(differs_after)))
+            : kNoRow;
+        const uint32_t below_squared = below * below * 0x10001u;
+        const uint32_t above_squared = above * above * 0x10001u;
+        const auto fold = [&](auto pair_index)
+        {
+          constexpr int p = decltype(pair_index)::value;
+          best_pairs[p] = FoldSquaredDistances<2 * p, 2 * p + 1>(best_pairs[p], below, below_squared);
+          best_pairs[p] = FoldSquaredDistances<kR - 1 - 2 * p, kR - 2 - 2 * p>(best_pairs[p], above,
+                                                                             above_squared);
+        };
+        StaticFor<kPairs>(fold);
+      }
+      // Class-agnostic candidates: the rows of the register window a row's own window did not
+      // reach. Row k of the previous chunk is missing for the rows j > k, at distance j + R - k;
+      // row m of the next chunk for the rows j < m, at distance R + m - j.
+#pragma unroll
+      for (int k = 0; k < kR - 1; k++)
+      {
+        const uint32_t candidate = __byte_perm(previous_pairs[k >> 1], 0u, (k & 1) ? 0x3232 : 0x1010);
+#pragma unroll
+        for (int p = 0; p < kPairs; p++)
+        {
+          if (2 * p + 1 > k)
+          {
+            const int d_low = 2 * p + kR - k;
+            const uint32_t offsets = static_cast<uint32_t>(d_low * d_low)
+                | (static_cast<uint32_t>((d_low + 1) * (d_low + 1)) << 16);
+            best_pairs[p] = __viaddmin_u16x2(candidate, offsets, best_pairs[p]);
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 1; m < kR; m++)
+      {
+        const uint32_t candidate = __byte_perm(next_pairs[m >> 1], 0u, (m & 1) ? 0x3232 : 0x1010);
+#pragma unroll
+        for (int p = 0; p < kPairs; p++)
+        {
+          if (2 * p < m)
+          {
+            const int d_low = kR + m - 2 * p;
+            const uint32_t offsets = static_cast<uint32_t>(d_low * d_low)
+                | (static_cast<uint32_t>((d_low - 1) * (d_low - 1)) << 16);
+            best_pairs[p] = __viaddmin_u16x2(candidate, offsets, best_pairs[p]);
+          }
+        }
+      }
+      worst = worst_of_lane();
+      // A saturated result says nothing (open space): the tile is given up.
+      if (__any_sync(0xffffffffu, worst >= kSaturated))
+      {
+        over_budget = true;
+        worst = 0u;
+      }
+      // Rows from memory, four per side and round: row base - R - 1 - t below (distance
+      // j + R + 1 + t from row j) and row base + 2 R + t above (distance 2 R + t - j), clamped to
+      // the line (a clamped row was already seen at a smaller distance). Heights relative to the
+      // chunk's class: an opposite-class row counts 0. Convergent: every lane evaluates every
+      // candidate, which is harmless for certified rows (a candidate is at least (R + 1)^2).
+      // Past the step allowance or the depth the 16-bit arithmetic covers the tile is given up.
+      const uint32_t class_bit = chunk_filled << 31;
+      const uint32_t allowance =
+          (step_rate * (static_cast<uint32_t>(base - first_row) + credit_rows)) >> 7;
+      int t = 0;
+      while (true)
+      {
+        const int reach = kR + 1 + t;
+        const bool open = (base - kR - 1 - t >= 0) || (base + 2 * kR + t <= last_row);
+        const bool need = static_cast<uint32_t>(reach * reach) < worst && open;
+        if (!__any_sync(0xffffffffu, need))
+        {
+          break;
+        }
+        if (steps > allowance || reach + 3 > deepest_search)
+        {
+          over_budget = true;
+          break;
+        }
+        steps += 4u;
+        constexpr int kUnroll = 4;
+        uint32_t words_below[kUnroll], words_above[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++)
+        {
+          const int below = __viaddmax_s32(base - kR - 1 - u, -t, 0);
+          const int above = __viaddmin_s32(base + 2 * kR + u, t, last_row);
+          words_below[u] = *reinterpret_cast<const uint32_t*>(
+              line + static_cast<uint64_t>(static_cast<uint32_t>(below)) * stride_bytes);
+          words_above[u] = *reinterpret_cast<const uint32_t*>(
+              line + static_cast<uint64_t>(static_cast<uint32_t>(above)) * stride_bytes);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++)
+        {
+          const uint32_t tu = static_cast<uint32_t>(t + u);
+          const uint32_t tu_squared = tu * tu * 0x10001u;
+          const uint32_t height_below = min(
+              static_cast<uint32_t>(max(static_cast<int32_t>(words_below[u] ^ class_bit), 0)),
+              kSaturated);
+          const uint32_t height_above = min(
+              static_cast<uint32_t>(max(static_cast<int32_t>(words_above[u] ^ class_bit), 0)),
+              kSaturated);
+          const uint32_t from_below = height_below * 0x10001u + tu_squared;
+          const uint32_t from_above = height_above * 0x10001u + tu_squared;
+          const auto fold = [&](auto pair_index)
+          {
+            constexpr int p = decltype(pair_index)::value;
+            // (tu + a)^2 = tu^2 + 2 a tu + a^2 per half
+            best_pairs[p] = FoldSquaredDistances<2 * p + kR + 1, 2 * p + kR + 2>(
+                best_pairs[p], tu, from_below);
+            best_pairs[p] = FoldSquaredDistances<2 * kR - 2 * p, 2 * kR - 2 * p - 1>(
+                best_pairs[p], tu, from_above);
+          };
+          StaticFor<kPairs>(fold);
+        }
+        t += kUnroll;
+        worst = worst_of_lane();
+      }
+    }
+    // ---------------------------------------------------------------------------------- phase C
+    if (!over_budget)
+    {
+#pragma unroll
+      for (int j = 0; j < kR; j++)
+      {
+        const int q = base + j;
+        if (!kEdge || q <= last_row)  // warp-uniform
+        {
+          const uint32_t filled = static_cast<uint32_t>(classes >> (2 * kR - 1 - j)) & 1u;
+          const uint32_t squared = (j & 1) ? (best_pairs[j >> 1] >> 16) : (best_pairs[j >> 1] & 0xffffu);
+          emit_row(q, j, write_base, filled, squared);
+        }
+      }
     }
     // the next chunk becomes the current one
 #pragma unroll
