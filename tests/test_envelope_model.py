@@ -310,7 +310,7 @@ def window_line(classes, values, radius, step_budget=None, segment_rows=None, de
     far = (radius + 1) ** 2
     steps = 0
     if deepest is None:
-        deepest = min(DEEPEST_CAP, max(64, n >> 3))
+        deepest = DEEPEST_CAP
 
     def u16(x):
         assert 0 <= x < 65536, x
@@ -388,8 +388,6 @@ def window_line(classes, values, radius, step_budget=None, segment_rows=None, de
                         if 2 * pair < m:
                             for j in (2 * pair, 2 * pair + 1):
                                 best[j] = min(best[j], u16(nx[m] + (chunk + m - j) ** 2))
-                if max(best) >= SATURATED:
-                    return None, steps
                 t = 0
                 while True:
                     worst = max(best)

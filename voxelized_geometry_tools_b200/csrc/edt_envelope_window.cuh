@@ -70,12 +70,6 @@ constexpr uint32_t kSelectPilot = 1;
 constexpr uint32_t kSelectAfterPilot = 2;
 constexpr uint32_t kPilotStride = 8;
 constexpr int kPilotSpacing = 256;
-// A row whose search passes max(this, line length / 8) is in open space, where the stack kernel
-// is the better tool: its tile is given up at once, whatever the step allowance says. The bound
-// grows with the line because so does the price of handing a tile over (one warp walking the
-// whole line alone): at 1024^3 the clustered-spheres workload has pockets 86 voxels deep, and
-// with a bound of 64 the few tiles through them cost both strided passes 0.2-0.5 ms each.
-constexpr int kDeepestSearchFloor = 64;
 // Values in the register window are clamped to this (16-bit halves; + (R + 1)^2 must fit).
 constexpr uint32_t kSaturated = 0x3fffu;
 
@@ -258,7 +252,7 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     return;  // warp-uniform
   }
   const uint32_t credit_rows = static_cast<uint32_t>(segment_rows >> 2) + 16u;
-  const int deepest_search = min(kJointDeepestCap, max(kDeepestSearchFloor, length >> 3));
+  const int deepest_search = kJointDeepestCap;
 
   // Send layout only: the virtual origin of the current part and the row at which the next
   // part starts (the segment's first row forces the first look-up).
@@ -578,12 +572,6 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
         }
       }
       worst = worst_of_lane();
-      // A saturated result says nothing (open space): the tile is given up.
-      if (__any_sync(0xffffffffu, worst >= kSaturated))
-      {
-        over_budget = true;
-        worst = 0u;
-      }
       // Rows from memory, four per side and round: row base - R - 1 - t below (distance
       // j + R + 1 + t from row j) and row base + 2 R + t above (distance 2 R + t - j), clamped to
       // the line (a clamped row was already seen at a smaller distance). Heights relative to the
@@ -647,6 +635,11 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
         }
         t += kUnroll;
         worst = worst_of_lane();
+      }
+      // A result that is still saturated says nothing (values are clamped): the tile is given up.
+      if (__any_sync(0xffffffffu, worst >= kSaturated))
+      {
+        over_budget = true;
       }
     }
     // ---------------------------------------------------------------------------------- phase C
