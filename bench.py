@@ -17,8 +17,8 @@ e2e    = the same through the drop-in host entry point vgt_b200_sdf_f32 (host bu
          buffers out; H2D + D2H inside the timed region), per rank on its slab at N>1.
 roofline: the dominant kernel (the slowest of the three passes, normally x + finalize), algorithmic 8 B/voxel, timed with CUDA events
          between the kernels on the launching stream (vgt_b200_sdf_f32_dev_profile).
-cpu_baseline / --impl reference: the CPU oracle (our restatement of the reference CPU path, or
-         the reference's own EDT source when oracle/_ref was built) on a bounded 256^3 sample.
+cpu_baseline / --impl reference: the reference's own EDT source (oracle/_ref) when it was built,
+         else our restatement of it, on the host cores over the SAME grid (all host threads).
 """
 from __future__ import annotations
 
@@ -40,11 +40,6 @@ if str(REPO) not in sys.path:
 RESOLUTION = 0.02
 SDF_BYTES_PER_VOXEL = 24           # 3 passes x (4 B in + 4 B out), SURVEY.md section 8d
 PASS_BYTES_PER_VOXEL = 8
-# scan; y pass: pilot probe, mode decision, window kernel, stack kernel over the hand-over list
-# (exits at once when the list is empty); key reset, magnitude table; x pass: the same four with
-# the finalize fused; key decode
-KERNELS_PER_STEP = 12
-CPU_SAMPLE_DIMS = (256, 256, 256)
 PASS_NAMES = ["ScanContiguousAxisRegistersKernel (z)", "EnvelopeAxisWindowKernel (y)",
               "EnvelopeAxisWindowKernel (x + finalize)"]
 NCU_TRAFFIC_FILE = REPO / "profiles" / "ncu_traffic.json"
@@ -123,23 +118,60 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_reference_arm(steps: int, warmup: int):
-    """Times the CPU path on the host cores: kind 'reference' when oracle/_ref exists (the
-    reference's own signed_distance_field_generation.cpp), else 'port' (our restatement)."""
+def host_threads() -> int:
+    """The host threads this process may use. Passed explicitly to the CPU path: under
+    torch.distributed.run OMP_NUM_THREADS is forced to 1, which must not apply to it."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def available_host_bytes() -> int:
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 0
+
+
+def cpu_reference_arm(steps: int, warmup: int, dims):
+    """Times the CPU path on the host cores over the grid `dims`: kind 'reference' when
+    oracle/_ref exists (the reference's own signed_distance_field_generation.cpp), else 'port'
+    (our restatement). The grid is the workload itself when host memory allows (the reference
+    keeps two double fields: 24 B per voxel with occupancy and SDF), else the largest leading
+    part of it along x that fits; the result is per voxel either way."""
     import numpy as np
     from oracle import oracle
     from voxelized_geometry_tools_b200 import synthetic
-    occupancy = synthetic.clustered_spheres_occupancy(CPU_SAMPLE_DIMS)
+    dims = tuple(int(d) for d in dims)
+    wanted = dims
+    budget = available_host_bytes() * 0.6
+    while budget and 28.0 * float(np.prod(dims)) > budget and dims[0] > 64:
+        dims = (dims[0] // 2, dims[1], dims[2])
+    # (the x-range of the workload grid itself, not a smaller grid of another shape; generated
+    # with torch on the GPU when there is one - identical bits, seconds instead of a minute)
+    occupancy = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            occupancy = synthetic.clustered_spheres_occupancy_torch(
+                wanted, torch.device("cuda", 0), x_range=(0, dims[0])).cpu().numpy()
+            torch.cuda.empty_cache()
+    except Exception:
+        occupancy = None
+    if occupancy is None:
+        occupancy = synthetic.clustered_spheres_occupancy(wanted, x_range=(0, dims[0]))
+    threads = host_threads()
     kind = "port"
-    runner = lambda: oracle.sdf(occupancy, RESOLUTION, threads=0)  # noqa: E731
+    runner = lambda: oracle.sdf(occupancy, RESOLUTION, threads=threads)  # noqa: E731
     try:
         from oracle import reference_oracle
         if reference_oracle.available():
             kind = "reference"
-            runner = lambda: reference_oracle.sdf(occupancy, RESOLUTION, threads=0)  # noqa: E731
+            runner = lambda: reference_oracle.sdf(occupancy, RESOLUTION, threads=threads)  # noqa: E731
     except Exception:
         pass
-    cores = oracle.max_threads()
     for _ in range(warmup):
         runner()
     times = []
@@ -148,12 +180,16 @@ def cpu_reference_arm(steps: int, warmup: int):
         runner()
         times.append(time.perf_counter() - begin)
     seconds = sum(times) / len(times)
-    voxels = float(np.prod(CPU_SAMPLE_DIMS))
-    return {"value": voxels / seconds / 1e9, "unit": "Gvoxels/s", "cores": cores, "kind": kind,
-            "sample": f"{'x'.join(map(str, CPU_SAMPLE_DIMS))} clustered-spheres grid (1/8 of the "
-                      f"512^3 workload), ExtractSignedDistanceField<float>, {steps} run(s), "
-                      f"{seconds:.3f} s each",
-            "seconds_per_sample": seconds}
+    voxels = float(np.prod(dims))
+    same = dims == wanted
+    return {"value": voxels / seconds / 1e9, "unit": "Gvoxels/s", "cores": threads, "kind": kind,
+            "sample": f"{'x'.join(map(str, dims))} clustered-spheres grid ("
+                      + ("the whole workload" if same else
+                         f"the first {dims[0]} x-planes of the {'x'.join(map(str, wanted))} "
+                         "workload: host memory; per-voxel figure")
+                      + f"), ExtractSignedDistanceField<float>, {steps} run(s), "
+                      f"{seconds:.3f} s each, {threads} threads",
+            "seconds_per_sample": seconds, "same_config": same, "sample_dims": list(dims)}
 
 
 def run_reference(args):
@@ -162,8 +198,8 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 3))
     warmup = min(args.warmup, 1)
-    baseline = cpu_reference_arm(steps, warmup)
     dims = workload_dims(args.gpus)
+    baseline = cpu_reference_arm(steps, warmup, dims)
     line = {
         "impl": "reference", "metric": "sdf_gvoxels_per_s", "value": baseline["value"],
         "unit": "Gvoxels/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
@@ -171,13 +207,105 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{'x'.join(map(str, dims))} occupancy -> SDF<float> "
                                "(clustered spheres ~10% filled, 1% unknown)",
-                   "sample": baseline["sample"]},
+                   "sample": baseline["sample"], "same_config": baseline["same_config"]},
         "cpu_baseline": {k: baseline[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": baseline["value"], "unit": "Gvoxels/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def sharded_parity(sharded, vdev, synthetic, plan, result, dims, dev, rank, world):
+    """Outside the timed region: (1) the sharded SDF of the bench grid == the one-GPU SDF of the
+    same grid, bit for bit, slab by slab on rank 0 (plus min/max); (2) a 256^3 grid through the
+    same sharded path == the CPU oracle (the reference's own EDT source when oracle/_ref is
+    there). The oracle is only the checker here."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sdf, min_max = result
+    equal = True
+    if rank == 0:
+        whole = synthetic.clustered_spheres_occupancy_torch(dims, dev)
+        single, single_min_max = vdev.signed_distance_field(whole, RESOLUTION)
+        del whole
+        equal = single_min_max.tolist() == min_max.tolist()
+        for peer in range(world):
+            y0, y1 = sharded.split_range(dims[1], world, peer)
+            if peer == 0:
+                piece = sdf
+            else:
+                piece = torch.empty((dims[0], y1 - y0, dims[2]), dtype=torch.float32, device=dev)
+                dist.recv(piece, src=peer)
+            equal = equal and bool(torch.equal(piece, single[:, y0:y1, :]))
+        del single
+    else:
+        dist.send(sdf.contiguous(), dst=0)
+    torch.cuda.empty_cache()
+    small = (256, 256, 256)
+    small_plan = sharded.ShardedSignedDistanceField(small, rank=rank, world_size=world)
+    slab = synthetic.clustered_spheres_occupancy_torch(small, dev, x_range=small_plan.x_range)
+    small_sdf, _ = small_plan.extract(slab, RESOLUTION)
+    full = small_plan.gather_to_host(small_sdf)
+    oracle_ok, oracle_kind = None, None
+    if rank == 0:
+        from oracle import oracle
+        occupancy = synthetic.clustered_spheres_occupancy(small)
+        oracle_kind = "port"
+        want = None
+        try:
+            from oracle import reference_oracle
+            if reference_oracle.available():
+                want, _ = reference_oracle.sdf(occupancy, RESOLUTION, threads=host_threads())
+                oracle_kind = "reference"
+        except Exception:
+            want = None
+        if want is None:
+            want, _ = oracle.sdf(occupancy, RESOLUTION, threads=host_threads())
+        oracle_ok = bool(np.array_equal(full.numpy(), want))
+    return {"equals_single_gpu": bool(equal), "oracle_256": oracle_ok, "oracle_kind": oracle_kind,
+            "grid": "x".join(map(str, dims)), "exchange": plan.exchange_used}
+
+
+def strong_scaling_1024(sharded, vdev, synthetic, dev, rank, world, steps):
+    """BASELINE config 4: the SAME 1024^3 grid at every N (strong scaling), device-resident."""
+    import torch
+    import torch.distributed as dist
+    dims = (1024, 1024, 1024)
+    distributed = world > 1
+    if distributed:
+        plan = sharded.ShardedSignedDistanceField(dims, rank=rank, world_size=world)
+        occupancy = synthetic.clustered_spheres_occupancy_torch(dims, dev, x_range=plan.x_range)
+        step = lambda: plan.extract(occupancy, 0.01)  # noqa: E731
+    else:
+        occupancy = synthetic.clustered_spheres_occupancy_torch(dims, dev)
+        out = torch.empty_like(occupancy)
+        min_max = torch.empty(2, dtype=torch.float32, device=dev)
+        step = lambda: vdev.signed_distance_field(occupancy, 0.01, out=out, min_max=min_max)  # noqa: E731
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    if distributed:
+        dist.barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        step()
+    stop.record()
+    torch.cuda.synchronize(dev)
+    ms = start.elapsed_time(stop) / steps
+    if distributed:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    voxels = 1024.0 ** 3
+    peak, _ = measured_peaks()
+    return {"config": "1024^3 occupancy -> SDF<float> @0.01 m, the same grid at every N",
+            "scaling": "strong", "n_gpus": world, "ms_per_step": ms,
+            "value": voxels / (ms * 1e-3) / 1e9, "unit": "Gvoxels/s",
+            "hbm_roofline_frac_24B": SDF_BYTES_PER_VOXEL * voxels / (ms * 1e-3) / 1e9
+            / (peak * world)}
 
 
 def run_ours(args):
@@ -225,12 +353,15 @@ def run_ours(args):
         result = step()
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    count_launches = _capi.library().vgt_b200_kernel_launch_count
     with ClockSampler(local_rank) as sampler:
         barrier()
+        launches_before = count_launches()
         start.record()
         for _ in range(args.steps):
             result = step()
         stop.record()
+        launches = count_launches() - launches_before     # this rank's kernels, counted
         barrier()
     elapsed_ms = start.elapsed_time(stop)
     if distributed:
@@ -251,6 +382,10 @@ def run_ours(args):
             collected.append(plan.stage_ms())
         plan.profile = False
         stage_ms = {k: statistics.mean(c[k] for c in collected) for k in collected[0]}
+
+    parity = None
+    if distributed and not args.skip_parity:
+        parity = sharded_parity(sharded, vdev, synthetic, plan, result, dims, dev, rank, n_gpus)
 
     # ---- per-kernel timing for the roofline (rank-local grid, events between the kernels) ----
     pass_ms = None
@@ -397,9 +532,24 @@ def run_ours(args):
     if not distributed:
         other_map_types = bench_tagged_map(local_rank, include_cpu=not args.skip_cpu)
 
+    strong = None
+    if not args.skip_strong:
+        if n_gpus == 8:
+            # (the N = 8 bench grid IS the 1024^3 grid)
+            strong = {"config": "1024^3 occupancy -> SDF<float>, the same grid at every N",
+                      "scaling": "strong", "n_gpus": 8, "ms_per_step": ms_per_step,
+                      "value": value, "unit": "Gvoxels/s",
+                      "hbm_roofline_frac_24B": SDF_BYTES_PER_VOXEL * voxels
+                      / (ms_per_step * 1e-3) / 1e9 / (peak * n_gpus)}
+        else:
+            del occupancy
+            torch.cuda.empty_cache()
+            strong = strong_scaling_1024(sharded, vdev, synthetic, dev, rank, n_gpus,
+                                         max(3, min(args.steps, 10)))
+
     cpu_baseline = None
     if rank == 0 and not distributed and not args.skip_cpu:
-        full = cpu_reference_arm(1, 0)
+        full = cpu_reference_arm(2, 1, dims)
         cpu_baseline = {k: full[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -418,9 +568,13 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (>= 512 MiB per pass), no flush",
                        "sdf_min_max": sdf_min_max},
             "clocks": sampler.summary(), "e2e": e2e,
-            "gpu_launches": KERNELS_PER_STEP * args.steps, "roofline": roofline,
+            "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if strong is not None:
+            line["strong_scaling_1024"] = strong
         if voxelizer is not None:
             line["voxelizer"] = voxelizer
         if other_configs is not None:
@@ -572,6 +726,10 @@ def main():
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
     parser.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     parser.add_argument("--skip-voxelizer", action="store_true")
+    parser.add_argument("--skip-parity", action="store_true",
+                        help="N > 1: skip the sharded == single-GPU / oracle checks")
+    parser.add_argument("--skip-strong", action="store_true",
+                        help="skip the 1024^3 strong-scaling leg (BASELINE config 4)")
     parser.add_argument("--exchange", default="auto", choices=["auto", "peer_store", "nccl"])
     parser.add_argument("--chunks", type=int, default=2,
                         help="x-chunks per slab for overlapping the all-to-all (N > 1)")

@@ -50,6 +50,11 @@ enum
 VGT_B200_API const char* vgt_b200_last_error(void);
 VGT_B200_API const char* vgt_b200_version(void);
 
+/* Measurement aid (no reference counterpart): the number of CUDA kernels this library has
+ * launched in this process so far, over all threads and devices. bench.py reports the difference
+ * across its timed region as "gpu_launches". */
+VGT_B200_API uint64_t vgt_b200_kernel_launch_count(void);
+
 /* Replaces cuda_helpers::GetAvailableDevices() / IsAvailable()
  * (src/.../cuda_voxelization_helpers.cu:562-637, 769-822). Returns the number of usable
  * sm_100 devices (0 when there is none or the driver is missing; never an error). */
@@ -205,15 +210,22 @@ VGT_B200_API int vgt_b200_edt_local_passes_dev(
  * the kernel IS the all-to-all (the reference has no counterpart: SURVEY.md section 2.2). The
  * passes are the Z and Y loops of ComputeDistanceFieldTransformInPlace
  * (src/.../signed_distance_field_generation.cpp:315-390) on this rank's x-slab.
+ *   rank, num_ranks       this rank and the number of x-slabs (2..8). Rank g sweeps the parts of
+ *                         its lines starting with the part of rank g + 1, so that at any moment
+ *                         the ranks store into different peers.
+ *   x_offset, nx_total    first x row of this rank's slab inside the full grid, and its x size.
  *   peer_receive_buffers  host array of num_ranks device addresses, entry h = base of rank h's
  *                         receive buffer laid out [nx_total][rows_h][nz] (rows_h = rank h's share
  *                         of ny), mapped into this process (CUDA IPC / symmetric memory);
  *                         entry [own rank] is the local buffer.
- *   x_offset              first x row of this rank's slab inside the full grid.
+ *   receive_capacity_words  size of EVERY receive buffer in 32-bit words; the call fails with
+ *                         VGT_B200_ERR_INVALID_ARGUMENT when nx_total * ceil(ny / num_ranks) * nz
+ *                         words do not fit (a peer store must never land outside a buffer).
  * The caller synchronises the ranks (a barrier on `stream`) before any rank reads its buffer. */
 VGT_B200_API int vgt_b200_edt_local_passes_scatter_dev(
     const float* d_occupancy, int64_t nx_local, int64_t ny, int64_t nz, int unknown_is_filled,
-    int num_ranks, int64_t x_offset, const uint64_t* peer_receive_buffers, int device,
+    int num_ranks, int rank, int64_t x_offset, int64_t nx_total,
+    const uint64_t* peer_receive_buffers, int64_t receive_capacity_words, int device,
     void* stream);
 
 /* The remaining X pass (signed_distance_field_generation.cpp:276-312) fused with the combine loop

@@ -46,6 +46,7 @@ SIGNATURES = {
     "vgt_b200_last_error": (ctypes.c_char_p, []),
     "vgt_b200_version": (ctypes.c_char_p, []),
     "vgt_b200_device_count": (_int, []),
+    "vgt_b200_kernel_launch_count": (ctypes.c_uint64, []),
     "vgt_b200_sdf_f32": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _int, _vp, _f32p, _f32p]),
     "vgt_b200_sdf_f64": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _int, _vp, _f64p, _f64p]),
     "vgt_b200_sdf_from_mask_f32": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _vp, _f32p,
@@ -72,8 +73,9 @@ SIGNATURES = {
     "vgt_b200_sdf_from_mask_f32_dev": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _vp, _vp,
                                               _vp]),
     "vgt_b200_edt_local_passes_dev": (_int, [_vp, _i64, _i64, _i64, _int, _int, _int, _vp, _vp]),
-    "vgt_b200_edt_local_passes_scatter_dev": (_int, [_vp, _i64, _i64, _i64, _int, _int, _i64,
-                                                     ctypes.POINTER(ctypes.c_uint64), _int, _vp]),
+    "vgt_b200_edt_local_passes_scatter_dev": (_int, [_vp, _i64, _i64, _i64, _int, _int, _int, _i64,
+                                                     _i64, ctypes.POINTER(ctypes.c_uint64), _i64,
+                                                     _int, _vp]),
     "vgt_b200_edt_final_pass_f32_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _dbl, _int, _int,
                                                _vp, _vp, _vp]),
     "vgt_b200_voxelize_f64": (_int, [_vp, _i64, _i64, _i64, _dbl, ctypes.POINTER(Cloud),

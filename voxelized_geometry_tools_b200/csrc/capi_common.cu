@@ -1,6 +1,7 @@
 // Error text, version and device enumeration for the C-ABI (include/vgt_b200.h).
 #include "common.cuh"
 
+#include <atomic>
 #include <cstring>
 
 namespace vgt_b200
@@ -8,7 +9,12 @@ namespace vgt_b200
 namespace
 {
 thread_local char g_last_error[512] = "";
+// (a statistic, not state: nothing in the library reads it back)
+std::atomic<uint64_t> g_kernel_launches{0};
 }
+
+void NoteKernelLaunch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t KernelLaunchCount() { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 void SetLastError(const char* format, ...)
 {
@@ -45,6 +51,11 @@ extern "C"
 const char* vgt_b200_last_error(void)
 {
   return vgt_b200::LastErrorText();
+}
+
+uint64_t vgt_b200_kernel_launch_count(void)
+{
+  return vgt_b200::KernelLaunchCount();
 }
 
 const char* vgt_b200_version(void)

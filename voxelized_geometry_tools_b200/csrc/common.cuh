@@ -14,6 +14,8 @@
 namespace vgt_b200
 {
 // Defined in capi_common.cu.
+// Counts the kernels this library has launched (process-wide; vgt_b200_kernel_launch_count()).
+void NoteKernelLaunch();
 void SetLastError(const char* format, ...);
 int FailInvalid(const char* format, ...);
 int FailDevice(const char* what, cudaError_t error);

@@ -245,7 +245,18 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   // row turned out deeper than deepest_search: the tile then goes to the stack kernel.
   uint32_t steps = 0;
   bool over_budget = false;
-  const int first_row = static_cast<int>(blockIdx.y) * segment_spacing;
+  // Fused exchange: the segments are taken in an order rotated by the rank and by the line's
+  // outer index, so that the blocks in flight at any moment cover all parts of the lines and
+  // every rank stores into all its peers at once (see LineFamily::scatter_rank).
+  uint32_t segment = blockIdx.y;
+  if constexpr (kSend)
+  {
+    if (family.scatter_base[0] != nullptr)
+    {
+      segment = (segment + family.first_segment + outer) % gridDim.y;
+    }
+  }
+  const int first_row = static_cast<int>(segment) * segment_spacing;
   const int end_row = min(first_row + segment_rows, length);
   if (first_row >= length)
   {

@@ -48,7 +48,7 @@ int LaunchScan(const In* d_in, uint32_t* d_out, int64_t num_lines, int32_t lengt
     {
       kernel<<<static_cast<unsigned>(blocks), kScanWarpsPerBlock * kWarp, 0, stream>>>(
           reinterpret_cast<const typename Source::Vector*>(d_in), reinterpret_cast<uint4*>(d_out),
-          num_lines, length, unknown_is_filled);
+          num_lines, length, unknown_is_filled); NoteKernelLaunch();
     };
     if (length <= 128)
     {
@@ -74,12 +74,12 @@ int LaunchScan(const In* d_in, uint32_t* d_out, int64_t num_lines, int32_t lengt
     ScanContiguousAxisVec4Kernel<Source>
         <<<static_cast<unsigned>(blocks), kScanWarpsPerBlock * kWarp, smem, stream>>>(
             reinterpret_cast<const typename Source::Vector*>(d_in),
-            reinterpret_cast<uint4*>(d_out), num_lines, length, unknown_is_filled);
+            reinterpret_cast<uint4*>(d_out), num_lines, length, unknown_is_filled); NoteKernelLaunch();
     VGT_CUDA_TRY(cudaGetLastError(), "ScanContiguousAxisVec4Kernel launch");
     return VGT_B200_OK;
   }
   ScanContiguousAxisKernel<In><<<static_cast<unsigned>(blocks), kScanWarpsPerBlock * kWarp, smem,
-                                 stream>>>(d_in, d_out, num_lines, length, unknown_is_filled);
+                                 stream>>>(d_in, d_out, num_lines, length, unknown_is_filled); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "ScanContiguousAxisKernel launch");
   return VGT_B200_OK;
 }
@@ -106,7 +106,7 @@ int LaunchEnvelopeInPlaceStack(uint32_t* d_in, typename OutputOf<kMode>::Type* d
                  "EnvelopeAxisInPlaceStackKernel smem attribute");
   }
   kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, smem, stream>>>(
-      d_in, d_out, d_positions, family, finalize, d_keys);
+      d_in, d_out, d_positions, family, finalize, d_keys); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "EnvelopeAxisInPlaceStackKernel launch");
   return VGT_B200_OK;
 }
@@ -158,7 +158,7 @@ int LaunchEnvelopeLeanKernel(uint32_t* d_in, typename OutputOf<kMode>::Type* d_o
   const auto launch = [&](auto kernel)
   {
     kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, 0, stream>>>(
-        d_in, d_out, d_positions, class_scratch.get(), derived, finalize, d_keys, d_redo_list);
+        d_in, d_out, d_positions, class_scratch.get(), derived, finalize, d_keys, d_redo_list); NoteKernelLaunch();
   };
   if constexpr (kMode == kEmitPacked)
   {
@@ -284,16 +284,27 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   derived.num_words = static_cast<uint32_t>((family.length + 31) >> 5);
   const uint32_t step_rate = WindowStepRate();
   // Lines are cut into segments so that there are about six waves of blocks (and never
-  // segments shorter than three chunks; measured at 512^3: 1.68 ms with one segment per line,
+  // segments shorter than eight chunks; measured at 512^3: 1.68 ms with one segment per line,
   // 1.49 ms with four): the block scheduler then balances tiles of uneven depth
   // and the last wave is thin. A segment re-reads 2 R rows of its neighbours.
   constexpr int kRadius = (kMode == kEmitPacked) ? kWindowRadiusPacked : kWindowRadiusFinal;
   const int64_t chunks = (family.length + kRadius - 1) / kRadius;
   const int64_t wanted_blocks = MultiprocessorCount() * 192 / kWindowWarpsPerBlock;
   int64_t segments = (wanted_blocks + blocks - 1) / blocks;
-  segments = std::max<int64_t>(1, std::min<int64_t>(segments, chunks / 3));
+  segments = std::max<int64_t>(1, std::min<int64_t>(segments, chunks / 8));
   const int segment_rows = static_cast<int>((chunks + segments - 1) / segments) * kRadius;
   segments = (family.length + segment_rows - 1) / segment_rows;
+  derived.first_segment = 0;
+  if (family.out_parts > 1 && family.scatter_base[0] != nullptr)
+  {
+    // first row of the part after this rank's own
+    const int64_t next_part = (family.scatter_rank + 1) % family.out_parts;
+    const int64_t wide = family.out_base + 1;
+    const int64_t row = next_part < family.out_extra
+        ? next_part * wide
+        : family.out_extra * wide + (next_part - family.out_extra) * family.out_base;
+    derived.first_segment = static_cast<uint32_t>((row / segment_rows) % segments);
+  }
   // (VGT_B200_WINDOW_PILOT=0: no pilot, the window kernel works on every tile)
   const char* pilot_choice = std::getenv("VGT_B200_WINDOW_PILOT");
   const bool pilot = tiles >= 16 * static_cast<int64_t>(kPilotStride)
@@ -305,7 +316,7 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
     {
       kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)), threads, 0,
                stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list, step_rate,
-                         segment_rows, segment_rows, kSelectAll);
+                         segment_rows, segment_rows, kSelectAll); NoteKernelLaunch();
       return;
     }
     const int64_t pilot_blocks = (blocks + kPilotStride - 1) / kPilotStride;
@@ -315,11 +326,11 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
     kernel<<<dim3(static_cast<unsigned>(pilot_blocks), static_cast<unsigned>(probes_per_line)),
              threads, 0, stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list,
                                    std::min(step_rate, kPilotStepRate), 2 * kRadius, kPilotSpacing,
-                                   kSelectPilot);
-    DecideWindowModeKernel<<<1, 1, 0, stream>>>(d_redo_list, static_cast<uint32_t>(pilot_probes));
+                                   kSelectPilot); NoteKernelLaunch();
+    DecideWindowModeKernel<<<1, 1, 0, stream>>>(d_redo_list, static_cast<uint32_t>(pilot_probes)); NoteKernelLaunch();
     kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)), threads, 0,
              stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list, step_rate,
-                       segment_rows, segment_rows, kSelectAfterPilot);
+                       segment_rows, segment_rows, kSelectAfterPilot); NoteKernelLaunch();
   };
   // Rows reach the registers either by plain loads one chunk ahead (the y pass: 0.59 ms against
   // 0.61 staged at 512^3) or through shared memory with cp.async two chunks ahead (the finalizing
@@ -433,6 +444,30 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
                                                  d_keys, stream);
 }
 
+struct StreamGuard
+{
+  cudaStream_t stream = nullptr;
+  ~StreamGuard()
+  {
+    if (stream != nullptr)
+    {
+      cudaStreamDestroy(stream);
+    }
+  }
+};
+
+struct EventGuard
+{
+  cudaEvent_t event = nullptr;
+  ~EventGuard()
+  {
+    if (event != nullptr)
+    {
+      cudaEventDestroy(event);
+    }
+  }
+};
+
 LineFamily FamilyAlongY(int64_t nx, int64_t ny, int64_t nz)
 {
   return LineFamily{nx, ny * nz, nz, nz, static_cast<int32_t>(ny)};
@@ -448,7 +483,8 @@ LineFamily FamilyAlongX(int64_t nx, int64_t ny, int64_t nz)
 template <typename In>
 int RunLocalPasses(const In* d_in, int64_t nx, int64_t ny, int64_t nz, int unknown_is_filled,
                    uint32_t* d_result, uint32_t* d_other, cudaStream_t stream, int send_parts = 0,
-                   const uint64_t* scatter_bases = nullptr, int64_t scatter_row_offset = 0)
+                   const uint64_t* scatter_bases = nullptr, int64_t scatter_row_offset = 0,
+                   int scatter_rank = 0)
 {
   if (send_parts > 1)
   {
@@ -457,27 +493,39 @@ int RunLocalPasses(const In* d_in, int64_t nx, int64_t ny, int64_t nz, int unkno
       return FailInvalid("more parts (%d) than rows along y (%lld)", send_parts,
                          static_cast<long long>(ny));
     }
+    LineFamily family = FamilyAlongY(nx, ny, nz);
+    family.out_parts = send_parts;
+    family.out_base = static_cast<int32_t>(ny / send_parts);
+    family.out_extra = static_cast<int32_t>(ny % send_parts);
+    if (scatter_bases == nullptr)
+    {
+      const int status = LaunchScan<In>(d_in, d_other, nx * ny, static_cast<int32_t>(nz),
+                                        unknown_is_filled, stream);
+      if (status != VGT_B200_OK)
+      {
+        return status;
+      }
+      return LaunchEnvelope<kEmitPacked>(d_other, d_result, family, Square(nz - 1),
+                                         FinalizeParams{}, nullptr, stream);
+    }
+    if (send_parts > 8)
+    {
+      return FailInvalid("fused exchange supports at most 8 ranks");
+    }
+    family.scatter_rank = scatter_rank;
+    for (int part = 0; part < send_parts; part++)
+    {
+      family.scatter_base[part] = reinterpret_cast<uint32_t*>(scatter_bases[part]);
+    }
+    // (Tried: x-chunks with the scan of chunk c + 1 on a second stream under the y pass of chunk
+    // c. The y pass fills the register file, so the two kernels only alternate, and the extra
+    // pilot / tail per chunk made it slower: 1.57 against 1.45 ms at 2 GPUs.)
+    family.scatter_row_offset = scatter_row_offset;
     const int status = LaunchScan<In>(d_in, d_other, nx * ny, static_cast<int32_t>(nz),
                                       unknown_is_filled, stream);
     if (status != VGT_B200_OK)
     {
       return status;
-    }
-    LineFamily family = FamilyAlongY(nx, ny, nz);
-    family.out_parts = send_parts;
-    family.out_base = static_cast<int32_t>(ny / send_parts);
-    family.out_extra = static_cast<int32_t>(ny % send_parts);
-    if (scatter_bases != nullptr)
-    {
-      if (send_parts > 8)
-      {
-        return FailInvalid("fused exchange supports at most 8 ranks");
-      }
-      family.scatter_row_offset = scatter_row_offset;
-      for (int part = 0; part < send_parts; part++)
-      {
-        family.scatter_base[part] = reinterpret_cast<uint32_t*>(scatter_bases[part]);
-      }
     }
     return LaunchEnvelope<kEmitPacked>(d_other, d_result, family, Square(nz - 1),
                                        FinalizeParams{}, nullptr, stream);
@@ -513,7 +561,7 @@ public:
     VGT_CUDA_TRY(table_.Allocate(size_, stream), "magnitude table allocation");
     const unsigned threads = 256;
     BuildMagnitudeTableKernel<Out><<<(size_ + threads - 1) / threads, threads, 0, stream>>>(
-        table_.get(), size_, resolution);
+        table_.get(), size_, resolution); NoteKernelLaunch();
     VGT_CUDA_TRY(cudaGetLastError(), "BuildMagnitudeTableKernel launch");
     return VGT_B200_OK;
   }
@@ -541,7 +589,7 @@ int RunFinalPass(uint32_t* d_packed, int64_t nx, int64_t ny_local, int64_t nz, i
   if (d_min_max != nullptr)
   {
     VGT_CUDA_TRY(keys.Allocate(2, stream), "min/max scratch");
-    ResetMinMaxKeysKernel<Key><<<1, 1, 0, stream>>>(keys.get());
+    ResetMinMaxKeysKernel<Key><<<1, 1, 0, stream>>>(keys.get()); NoteKernelLaunch();
   }
   FinalizeParams finalize{};
   finalize.resolution = resolution;
@@ -569,7 +617,7 @@ int RunFinalPass(uint32_t* d_packed, int64_t nx, int64_t ny_local, int64_t nz, i
   }
   if (d_min_max != nullptr)
   {
-    DecodeMinMaxKernel<Out, Key><<<1, 1, 0, stream>>>(keys.get(), d_min_max);
+    DecodeMinMaxKernel<Out, Key><<<1, 1, 0, stream>>>(keys.get(), d_min_max); NoteKernelLaunch();
     VGT_CUDA_TRY(cudaGetLastError(), "DecodeMinMaxKernel launch");
   }
   return VGT_B200_OK;
@@ -654,30 +702,6 @@ int SdfOnDevice(const In* d_in, int64_t nx, int64_t ny, int64_t nz, double resol
   return status;
 }
 
-struct StreamGuard
-{
-  cudaStream_t stream = nullptr;
-  ~StreamGuard()
-  {
-    if (stream != nullptr)
-    {
-      cudaStreamDestroy(stream);
-    }
-  }
-};
-
-struct EventGuard
-{
-  cudaEvent_t event = nullptr;
-  ~EventGuard()
-  {
-    if (event != nullptr)
-    {
-      cudaEventDestroy(event);
-    }
-  }
-};
-
 // Grids above this size go through the pipelined host path (copies overlapped with the passes).
 constexpr int64_t kPipelineMinVoxels = int64_t{1} << 24;
 constexpr int kPipelineChunks = 8;
@@ -737,7 +761,7 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
   VGT_CUDA_TRY(scratch.Allocate(count, compute.stream), "SDF scratch allocation");
   VGT_CUDA_TRY(d_min_max.Allocate(2, compute.stream), "min/max allocation");
   VGT_CUDA_TRY(keys.Allocate(2, compute.stream), "min/max scratch");
-  ResetMinMaxKeysKernel<Key><<<1, 1, 0, compute.stream>>>(keys.get());
+  ResetMinMaxKeysKernel<Key><<<1, 1, 0, compute.stream>>>(keys.get()); NoteKernelLaunch();
   EventGuard allocated;
   VGT_CUDA_TRY(cudaEventCreateWithFlags(&allocated.event, cudaEventDisableTiming), "event");
   VGT_CUDA_TRY(cudaEventRecord(allocated.event, compute.stream), "event record");
@@ -810,7 +834,7 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
   Out min_max[2];
   if (status == VGT_B200_OK)
   {
-    DecodeMinMaxKernel<Out, Key><<<1, 1, 0, compute.stream>>>(keys.get(), d_min_max.get());
+    DecodeMinMaxKernel<Out, Key><<<1, 1, 0, compute.stream>>>(keys.get(), d_min_max.get()); NoteKernelLaunch();
     cudaMemcpyAsync(min_max, d_min_max.get(), sizeof(Out) * 2, cudaMemcpyDeviceToHost,
                     compute.stream);
   }
@@ -946,7 +970,7 @@ int SdfFromCellsOnDevice(const uint32_t* d_cells, int cell_words, int64_t nx, in
   const int threads = 256;
   CellsToMaskKernel<<<static_cast<unsigned>((count + threads - 1) / threads), threads, 0,
                       stream>>>(d_cells, cell_words, count, unknown_is_filled, object_rule,
-                                d_sorted_ids, num_ids, mask.get());
+                                d_sorted_ids, num_ids, mask.get()); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "CellsToMaskKernel launch");
   return SdfOnDevice<uint8_t, kMode>(mask.get(), nx, ny, nz, resolution, 0, add_virtual_border,
                                      d_sdf, d_min_max, stream);
@@ -1130,13 +1154,13 @@ int SdfFreeAndNamedHost(const void* h_cells, int cell_bytes, int64_t nx, int64_t
     cudaStreamSynchronize(stream);
     return status;
   }
-  ResetMinMaxKeysKernel<Key><<<1, 1, 0, stream>>>(keys.get());
+  ResetMinMaxKeysKernel<Key><<<1, 1, 0, stream>>>(keys.get()); NoteKernelLaunch();
   const int threads = 256;
   const int64_t merge_blocks =
       std::min<int64_t>((count + threads - 1) / threads, MultiprocessorCount() * 16);
   MergeFreeAndNamedKernel<Out, Key><<<static_cast<unsigned>(merge_blocks), threads, 0, stream>>>(
-          d_free.get(), d_named.get(), count, d_free.get(), keys.get());
-  DecodeMinMaxKernel<Out, Key><<<1, 1, 0, stream>>>(keys.get(), d_min_max.get());
+          d_free.get(), d_named.get(), count, d_free.get(), keys.get()); NoteKernelLaunch();
+  DecodeMinMaxKernel<Out, Key><<<1, 1, 0, stream>>>(keys.get(), d_min_max.get()); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "MergeFreeAndNamedKernel launch");
   Out min_max[2];
   VGT_CUDA_TRY(cudaMemcpyAsync(h_out, d_free.get(), sizeof(Out) * count, cudaMemcpyDeviceToHost,
@@ -1295,23 +1319,40 @@ int vgt_b200_edt_local_passes_dev(
 
 int vgt_b200_edt_local_passes_scatter_dev(
     const float* d_occupancy, int64_t nx_local, int64_t ny, int64_t nz, int unknown_is_filled,
-    int num_ranks, int64_t x_offset, const uint64_t* peer_receive_buffers, int device,
-    void* stream)
+    int num_ranks, int rank, int64_t x_offset, int64_t nx_total,
+    const uint64_t* peer_receive_buffers, int64_t receive_capacity_words, int device, void* stream)
 {
   const int check = CheckSdfArguments(d_occupancy, peer_receive_buffers, nx_local, ny, nz, 1.0);
   if (check != VGT_B200_OK)
   {
     return check;
   }
-  if (num_ranks < 2 || num_ranks > 8 || x_offset < 0)
+  if (num_ranks < 2 || num_ranks > 8 || rank < 0 || rank >= num_ranks)
   {
-    return FailInvalid("fused exchange needs 2..8 ranks and a non-negative x offset");
+    return FailInvalid("fused exchange needs 2..8 ranks and a rank inside that range");
   }
-  for (int rank = 0; rank < num_ranks; rank++)
+  if (x_offset < 0 || nx_total > VGT_B200_MAX_AXIS || x_offset + nx_local > nx_total)
   {
-    if (peer_receive_buffers[rank] == 0)
+    return FailInvalid("x slab [%lld, %lld) does not fit nx_total = %lld",
+                       static_cast<long long>(x_offset),
+                       static_cast<long long>(x_offset + nx_local),
+                       static_cast<long long>(nx_total));
+  }
+  // the largest part of a y line is ceil(ny / num_ranks) rows: every receive buffer must hold
+  // [nx_total][that many rows][nz] words, or a peer store would land outside it
+  const int64_t widest_part = (ny + num_ranks - 1) / num_ranks;
+  if (receive_capacity_words < nx_total * widest_part * nz)
+  {
+    return FailInvalid("receive buffers of %lld words cannot hold %lld x %lld x %lld",
+                       static_cast<long long>(receive_capacity_words),
+                       static_cast<long long>(nx_total), static_cast<long long>(widest_part),
+                       static_cast<long long>(nz));
+  }
+  for (int peer = 0; peer < num_ranks; peer++)
+  {
+    if (peer_receive_buffers[peer] == 0)
     {
-      return FailInvalid("null peer receive buffer %d", rank);
+      return FailInvalid("null peer receive buffer %d", peer);
     }
   }
   ScopedDevice scoped(device);
@@ -1322,7 +1363,7 @@ int vgt_b200_edt_local_passes_scatter_dev(
   VGT_CUDA_TRY(scratch.Allocate(nx_local * ny * nz, s), "local pass scratch allocation");
   // d_result is unused in scatter mode (every part has a remote or self-mapped destination).
   return RunLocalPasses<float>(d_occupancy, nx_local, ny, nz, unknown_is_filled, scratch.get(),
-                               scratch.get(), s, num_ranks, peer_receive_buffers, x_offset);
+                               scratch.get(), s, num_ranks, peer_receive_buffers, x_offset, rank);
 }
 
 int vgt_b200_edt_final_pass_f32_dev(
@@ -1497,7 +1538,7 @@ int vgt_b200_edt_sq_i32(
   }
   const int threads = 256;
   SplitFieldsKernel<<<static_cast<unsigned>((count + threads - 1) / threads), threads>>>(
-      d_packed, count, d_filled.get(), d_free.get());
+      d_packed, count, d_filled.get(), d_free.get()); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "SplitFieldsKernel launch");
   VGT_CUDA_TRY(cudaMemcpy(dist_to_filled_sq, d_filled.get(), sizeof(int32_t) * count,
                           cudaMemcpyDeviceToHost),

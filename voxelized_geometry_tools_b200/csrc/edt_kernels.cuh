@@ -51,6 +51,12 @@ struct LineFamily
   // The y pass then IS the all-to-all: no collective call, no intermediate copy.
   int64_t scatter_row_offset;
   uint32_t* scatter_base[8];
+  // Fused exchange: this rank's index. The window kernel starts its sweep over the line segments
+  // at the part that belongs to rank scatter_rank + 1, so that at any moment the ranks store
+  // into DIFFERENT peers (all ranks sweeping the parts in the same order would aim every NVLink
+  // store of the box at one receiver at a time).
+  int32_t scatter_rank;
+  uint32_t first_segment;     // derived by the launcher from scatter_rank
   // Derived values, filled by the launcher (FillDerived) so that the kernels read them straight
   // from the constant bank as instruction operands instead of re-deriving them in the hot loops.
   uint32_t stride_bytes;      // line_stride * 4 (the packed intermediate)

@@ -352,7 +352,7 @@ int LaunchRaycast(const double* d_points, int64_t num_points, const double* x_gc
   const int threads = 128;
   const int64_t blocks = (num_points + threads - 1) / threads;
   RaycastCloudKernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-      d_points, num_points, pose, max_range, grid, d_counts);
+      d_points, num_points, pose, max_range, grid, d_counts); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "RaycastCloudKernel launch");
   return VGT_B200_OK;
 }
@@ -364,7 +364,7 @@ int LaunchFilter(const int32_t* d_counts, int32_t num_grids, int64_t num_voxels,
   const int64_t blocks = (num_voxels + threads - 1) / threads;
   FilterGridsKernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
       reinterpret_cast<const int2*>(d_counts), num_grids, num_voxels, filter.percent_seen_free,
-      filter.outlier_points_threshold, filter.num_cameras_seen_free, d_occupancy);
+      filter.outlier_points_threshold, filter.num_cameras_seen_free, d_occupancy); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "FilterGridsKernel launch");
   return VGT_B200_OK;
 }

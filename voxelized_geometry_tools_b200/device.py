@@ -118,18 +118,21 @@ def edt_local_passes(occupancy_slab: torch.Tensor, unknown_is_filled: bool = Tru
     return out
 
 
-def edt_local_passes_scatter(occupancy_slab: torch.Tensor, x_offset: int, peer_buffer_ptrs,
+def edt_local_passes_scatter(occupancy_slab: torch.Tensor, rank: int, x_offset: int,
+                             nx_total: int, peer_buffer_ptrs, receive_capacity_words: int,
                              unknown_is_filled: bool = True) -> None:
     """z and y passes on an x-slab with the exchange fused in: the y pass stores each rank's
     part of every line straight into that rank's receive buffer (peer-mapped device pointers,
-    entry h = rank h's buffer laid out [nx_total, rows_h, nz])."""
+    entry h = rank h's buffer laid out [nx_total, rows_h, nz], every buffer
+    ``receive_capacity_words`` int32 words long; the library refuses a layout that does not fit)."""
     _require_cuda(occupancy_slab, torch.float32, "occupancy_slab")
     device = occupancy_slab.device
     nx, ny, nz = occupancy_slab.shape
     pointers = (ctypes.c_uint64 * len(peer_buffer_ptrs))(*[int(p) for p in peer_buffer_ptrs])
     code = _capi.library().vgt_b200_edt_local_passes_scatter_dev(
         occupancy_slab.data_ptr(), nx, ny, nz, int(unknown_is_filled), len(peer_buffer_ptrs),
-        int(x_offset), pointers, device.index or 0, _stream_handle(device))
+        int(rank), int(x_offset), int(nx_total), pointers, int(receive_capacity_words),
+        device.index or 0, _stream_handle(device))
     if code == _capi.ERR_UNSUPPORTED:
         raise NotImplementedError(_capi.last_error())
     _capi.check(code)

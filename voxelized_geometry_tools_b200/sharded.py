@@ -40,8 +40,8 @@ class Stages:
     local_passes: Callable
     final_pass: Callable
     local_passes_send: Callable | None = None
-    # (occupancy_slab, x_offset, peer_buffer_ptrs, unknown_is_filled) -> None: passes with the
-    # exchange fused in (peer stores); CUDA only.
+    # (occupancy_slab, rank, x_offset, nx_total, peer_buffer_ptrs, capacity_words,
+    # unknown_is_filled) -> None: passes with the exchange fused in (peer stores); CUDA only.
     local_passes_scatter: Callable | None = None
 
 
@@ -58,9 +58,10 @@ def cuda_stages() -> Stages:
     def final_pass(packed, y_offset, ny_total, resolution, add_virtual_border):
         return device.edt_final_pass(packed, y_offset, ny_total, resolution, add_virtual_border)
 
-    def local_passes_scatter(occupancy_slab, x_offset, peer_buffer_ptrs, unknown_is_filled):
-        device.edt_local_passes_scatter(occupancy_slab, x_offset, peer_buffer_ptrs,
-                                        unknown_is_filled)
+    def local_passes_scatter(occupancy_slab, rank, x_offset, nx_total, peer_buffer_ptrs,
+                             capacity_words, unknown_is_filled):
+        device.edt_local_passes_scatter(occupancy_slab, rank, x_offset, nx_total,
+                                        peer_buffer_ptrs, capacity_words, unknown_is_filled)
 
     return Stages(local_passes, final_pass, local_passes_send, local_passes_scatter)
 
@@ -205,8 +206,9 @@ class ShardedSignedDistanceField:
         buffer, handle = self._peer["buffers"][index], self._peer["handles"][index]
         # The y pass of every rank writes its part of our y-slab into `buffer`. Double buffering
         # plus the barrier below keeps a rank from overwriting a buffer its owner still reads.
-        self.stages.local_passes_scatter(occupancy_slab, self.x_range[0],
-                                         [int(p) for p in handle.buffer_ptrs], unknown_is_filled)
+        self.stages.local_passes_scatter(occupancy_slab, self.rank, self.x_range[0], nx,
+                                         [int(p) for p in handle.buffer_ptrs], buffer.numel(),
+                                         unknown_is_filled)
         self._mark("local", occupancy_slab)
         handle.barrier(channel=0)
         return buffer[:nx * nyl * nz].view(nx, nyl, nz)

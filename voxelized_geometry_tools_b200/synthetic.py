@@ -101,12 +101,15 @@ def quantise_spheres(centres: np.ndarray, radii: np.ndarray, radius_scale: float
     return centres_h, r2_h
 
 
-def rasterise_spheres_numpy(dims, centres_h: np.ndarray, r2_h: np.ndarray) -> np.ndarray:
+def rasterise_spheres_numpy(dims, centres_h: np.ndarray, r2_h: np.ndarray,
+                            x_range=None) -> np.ndarray:
+    """``x_range`` = (x_begin, x_end) rasterises one x-slab of the grid."""
     nx, ny, nz = dims
-    filled = np.zeros(dims, dtype=bool)
+    xb, xe = (0, nx) if x_range is None else x_range
+    filled = np.zeros((xe - xb, ny, nz), dtype=bool)
     for (cx, cy, cz), r2 in zip(centres_h, r2_h):
         reach = int(math.isqrt(int(r2))) // 2 + 1
-        x0, x1 = max(0, (cx // 2) - reach), min(nx, (cx // 2) + reach + 1)
+        x0, x1 = max(xb, (cx // 2) - reach), min(xe, (cx // 2) + reach + 1)
         y0, y1 = max(0, (cy // 2) - reach), min(ny, (cy // 2) + reach + 1)
         z0, z1 = max(0, (cz // 2) - reach), min(nz, (cz // 2) + reach + 1)
         if x0 >= x1 or y0 >= y1 or z0 >= z1:
@@ -115,7 +118,7 @@ def rasterise_spheres_numpy(dims, centres_h: np.ndarray, r2_h: np.ndarray) -> np
         dy = (2 * np.arange(y0, y1, dtype=np.int64) + 1 - cy) ** 2
         dz = (2 * np.arange(z0, z1, dtype=np.int64) + 1 - cz) ** 2
         inside = (dx[:, None, None] + dy[None, :, None] + dz[None, None, :]) <= r2
-        filled[x0:x1, y0:y1, z0:z1] |= inside
+        filled[x0 - xb:x1 - xb, y0:y1, z0:z1] |= inside
     return filled
 
 
@@ -188,20 +191,22 @@ def fit_radius_scale(dims, centres, radii, target_fill: float = 0.10, tolerance:
 
 
 def clustered_spheres_occupancy(dims, seed: int = 42, target_fill: float = 0.10,
-                                unknown_percent: bool = True) -> np.ndarray:
-    """Config 2 (host): ~10 % filled clustered spheres, 1 % of voxels set to 0.5 (unknown)."""
+                                unknown_percent: bool = True, x_range=None) -> np.ndarray:
+    """Config 2 (host): ~10 % filled clustered spheres, 1 % of voxels set to 0.5 (unknown);
+    optionally one x-slab of the grid."""
     dims = tuple(int(d) for d in dims)
     centres, radii = sphere_list(dims, seed)
     scale = fit_radius_scale(dims, centres, radii, target_fill)
     c_h, r2_h = quantise_spheres(centres, radii, scale)
-    filled = rasterise_spheres_numpy(dims, c_h, r2_h)
+    filled = rasterise_spheres_numpy(dims, c_h, r2_h, x_range)
     occupancy = filled.astype(np.float32)
     if unknown_percent:
+        first = 0 if x_range is None else x_range[0] * dims[1] * dims[2]
         flat = occupancy.reshape(-1)
         chunk = 1 << 24
         for start in range(0, flat.size, chunk):
             index = np.arange(start, min(flat.size, start + chunk), dtype=np.int64)
-            flat[start:start + index.size][_unknown_hash_numpy(index) % 100 == 0] = 0.5
+            flat[start:start + index.size][_unknown_hash_numpy(index + first) % 100 == 0] = 0.5
     return occupancy
 
 
