@@ -632,13 +632,14 @@ def bench_voxelizer(dev, peak, include_cpu=True):
     import numpy as np
     import torch
     from voxelized_geometry_tools_b200 import device as vdev, synthetic
+    from voxelized_geometry_tools_b200.grids import compose_rigid
     from voxelized_geometry_tools_b200.pointcloud_voxelization import (
         PointCloudVoxelizationFilterOptions)
     scene = synthetic.depth_camera_scene()
     n = scene["static_occupancy"].shape[0]
     x_gw = np.eye(4)
     x_gw[:3, 3] = -scene["origin_transform"][:3, 3]
-    clouds = [(torch.from_numpy(points).to(dev), x_gw @ x_wc, max_range)
+    clouds = [(torch.from_numpy(points).to(dev), compose_rigid(x_gw, x_wc), max_range)
               for points, x_wc, max_range in scene["clouds"]]
     finite_rays = int(sum(np.isfinite(points).all(axis=1).sum() for points, _, _ in scene["clouds"]))
     counts = torch.zeros((len(clouds), n, n, n, 2), dtype=torch.int32, device=dev)
@@ -695,13 +696,26 @@ def bench_voxelizer(dev, peak, include_cpu=True):
     cpu = None
     if include_cpu:
         from oracle import oracle
-        prepared = [(p, x_gw @ x, r) for p, x, r in scene["clouds"]]
+        prepared = [(p, compose_rigid(x_gw, x), r) for p, x, r in scene["clouds"]]
+        kind, run_cpu = "port", oracle.voxelize
+        try:
+            from oracle import reference_oracle
+            if reference_oracle.voxelizer_available():
+                # the reference's own cpu_pointcloud_voxelization.cpp (oracle/_ref)
+                kind, run_cpu = "reference", reference_oracle.voxelize
+        except Exception:
+            pass
+        threads = host_threads()
+        run_cpu(scene["static_occupancy"], prepared, scene["voxel_size"], 0.9, 2, 2,
+                threads=threads)
         begin = time.perf_counter()
-        oracle.voxelize(scene["static_occupancy"], prepared, scene["voxel_size"], 0.9, 2, 2)
+        run_cpu(scene["static_occupancy"], prepared, scene["voxel_size"], 0.9, 2, 2,
+                threads=threads)
         cpu_seconds = time.perf_counter() - begin
         cpu = {"value": finite_rays / cpu_seconds / 1e6, "unit": "Mrays/s",
-               "cores": oracle.max_threads(), "kind": "port",
-               "sample": f"the whole config-3 workload once ({cpu_seconds:.2f} s), raycast + filter"}
+               "cores": threads, "kind": kind,
+               "sample": f"the whole config-3 workload once ({cpu_seconds:.2f} s), raycast + "
+                         "filter + the counter read-back of the test entry"}
     return {"metric": "voxelization_mrays_per_s", "value": finite_rays / (raycast * 1e-3) / 1e6,
             "unit": "Mrays/s", "rays": finite_rays, "grid": f"{n}^3", "cameras": len(clouds),
             "raycast_ms": raycast, "filter_ms": filt, "zero_ms": statistics.mean(zero_ms),

@@ -1,7 +1,9 @@
 // TEST INFRASTRUCTURE ONLY -- stand-in for common_robotics_utilities/parallelism.hpp (the real
 // library is an unvendored, unpinned dependency of the reference: package.xml.ros2:12).
-// Only what signed_distance_field_generation.cpp uses: DegreeOfParallelism, ThreadWorkRange and
-// StaticParallelForRangeLoop (a static split of [start, end) into one range per thread).
+// Only what signed_distance_field_generation.cpp and cpu_pointcloud_voxelization.cpp use:
+// DegreeOfParallelism, ThreadWorkRange, StaticParallelForRangeLoop (a static split of
+// [start, end) into one range per thread) and StaticParallelForIndexLoop (the same split, the
+// functor called per index).
 #pragma once
 
 #include <cstdint>
@@ -74,6 +76,22 @@ void StaticParallelForRangeLoop(
     const int64_t end = begin + base + (t < extra ? 1 : 0);
     functor(ThreadWorkRange(begin, end, t));
   }
+}
+template <typename Functor>
+void StaticParallelForIndexLoop(
+    const DegreeOfParallelism& parallelism, int64_t range_start, int64_t range_end,
+    const Functor& functor, ParallelForBackend backend = ParallelForBackend::BEST_AVAILABLE)
+{
+  StaticParallelForRangeLoop(
+      parallelism, range_start, range_end,
+      [&](const ThreadWorkRange& range)
+      {
+        for (int64_t index = range.GetRangeStart(); index < range.GetRangeEnd(); index++)
+        {
+          functor(range.GetThreadNum(), index);
+        }
+      },
+      backend);
 }
 }  // namespace parallelism
 }  // namespace common_robotics_utilities

@@ -1,0 +1,38 @@
+// TEST INFRASTRUCTURE ONLY -- stand-in for common_robotics_utilities/utility.hpp with the one
+// type the reference's CPU voxelizer uses: an atomic that can be copied (a std::vector of
+// tracking grids is built from one prototype, cpu_pointcloud_voxelization.cpp:146-149).
+#pragma once
+
+#include <atomic>
+
+namespace common_robotics_utilities
+{
+namespace utility
+{
+template <typename T, std::memory_order kOrder>
+class CopyableMoveableAtomic
+{
+public:
+  CopyableMoveableAtomic() : value_(T()) {}
+  explicit CopyableMoveableAtomic(const T& value) : value_(value) {}
+  CopyableMoveableAtomic(const CopyableMoveableAtomic& other) : value_(other.load()) {}
+  CopyableMoveableAtomic(CopyableMoveableAtomic&& other) : value_(other.load()) {}
+  CopyableMoveableAtomic& operator=(const CopyableMoveableAtomic& other)
+  {
+    store(other.load());
+    return *this;
+  }
+  CopyableMoveableAtomic& operator=(CopyableMoveableAtomic&& other)
+  {
+    store(other.load());
+    return *this;
+  }
+  T load() const { return value_.load(kOrder); }
+  void store(const T& value) { value_.store(value, kOrder); }
+  T fetch_add(const T& operand) { return value_.fetch_add(operand, kOrder); }
+
+private:
+  std::atomic<T> value_;
+};
+}  // namespace utility
+}  // namespace common_robotics_utilities

@@ -1,5 +1,8 @@
 // TEST INFRASTRUCTURE ONLY -- stand-in for common_robotics_utilities/voxel_grid.hpp with just the
-// surface signed_distance_field_generation.{hpp,cpp} use. Storage convention as in the real
+// surface signed_distance_field_generation.{hpp,cpp} and cpu_pointcloud_voxelization.cpp use
+// (index <-> location: floor(p * (1 / voxel_size)) and voxel_size * (index + 0.5), the
+// conventions the reference mirrors in-tree at cuda_voxelization_helpers.cu:139-144, 250-255;
+// grid extent = voxel count * voxel size). Storage convention as in the real
 // library (mirrored in-tree at cuda_voxelization_helpers.cu:281-282): x slowest, z contiguous.
 #pragma once
 
@@ -67,6 +70,13 @@ public:
   int64_t NumZVoxels() const { return counts_.z; }
   int64_t TotalVoxels() const { return counts_.x * counts_.y * counts_.z; }
   double VoxelXSize() const { return voxel_size_; }
+  double InvVoxelXSize() const { return 1.0 / voxel_size_; }
+  Eigen::Vector3d Sizes() const
+  {
+    return Eigen::Vector3d(static_cast<double>(counts_.x) * voxel_size_,
+                           static_cast<double>(counts_.y) * voxel_size_,
+                           static_cast<double>(counts_.z) * voxel_size_);
+  }
   bool UniformVoxelSize() const { return true; }
   bool operator==(const VoxelGridSizes& o) const
   {
@@ -118,11 +128,43 @@ public:
   int64_t NumZVoxels() const { return sizes_.NumZVoxels(); }
   int64_t NumTotalVoxels() const { return sizes_.TotalVoxels(); }
   double VoxelXSize() const { return sizes_.VoxelXSize(); }
+  Eigen::Vector3d GridSizes() const { return sizes_.Sizes(); }
 
   bool CheckGridIndexInBounds(int64_t x, int64_t y, int64_t z) const
   {
     return x >= 0 && x < NumXVoxels() && y >= 0 && y < NumYVoxels() && z >= 0 && z < NumZVoxels();
   }
+  bool CheckGridIndexInBounds(const GridIndex& index) const
+  {
+    return CheckGridIndexInBounds(index.X(), index.Y(), index.Z());
+  }
+  GridIndex LocationInGridFrameToGridIndex4d(const Eigen::Vector4d& location) const
+  {
+    const double inverse = sizes_.InvVoxelXSize();
+    return GridIndex(static_cast<int64_t>(std::floor(location(0) * inverse)),
+                     static_cast<int64_t>(std::floor(location(1) * inverse)),
+                     static_cast<int64_t>(std::floor(location(2) * inverse)));
+  }
+  Eigen::Vector4d GridIndexToLocationInGridFrame(const GridIndex& index) const
+  {
+    const double voxel = sizes_.VoxelXSize();
+    return Eigen::Vector4d(voxel * (static_cast<double>(index.X()) + 0.5),
+                           voxel * (static_cast<double>(index.Y()) + 0.5),
+                           voxel * (static_cast<double>(index.Z()) + 0.5), 1.0);
+  }
+  GridQuery<T> GetIndexMutable(const GridIndex& index)
+  {
+    if (!CheckGridIndexInBounds(index) || !OnMutableAccess(index.X(), index.Y(), index.Z()))
+    {
+      return GridQuery<T>();
+    }
+    return GridQuery<T>(&data_[static_cast<size_t>(GetDataIndex(index.X(), index.Y(), index.Z()))]);
+  }
+  const T& GetDataIndexImmutable(int64_t data_index) const
+  {
+    return data_.at(static_cast<size_t>(data_index));
+  }
+  T& GetDataIndexMutable(int64_t data_index) { return data_.at(static_cast<size_t>(data_index)); }
   int64_t GetDataIndex(int64_t x, int64_t y, int64_t z) const
   {
     return (x * NumYVoxels() + y) * NumZVoxels() + z;

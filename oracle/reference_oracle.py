@@ -63,3 +63,123 @@ def transform_inplace(field: np.ndarray, threads: int = 0) -> np.ndarray:
     if lib().vgt_ref_transform_inplace_f64(field.ctypes.data_as(_f64p), *field.shape, threads):
         raise RuntimeError("reference transform failed")
     return field
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's own CPU voxelizer (cpu_pointcloud_voxelization.cpp compiled unmodified; the
+# entry points are in oracle/ref_shim/ref_voxelizer_entry.cpp).
+# ------------------------------------------------------------------------------------------------
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_voxelizer_bound = False
+
+
+def _voxelizer_lib() -> ctypes.CDLL:
+    global _voxelizer_bound
+    handle = lib()
+    if not _voxelizer_bound:
+        handle.vgt_ref_voxelize_f64.argtypes = [
+            _f32p, _i64, _i64, _i64, ctypes.c_double, ctypes.c_int32,
+            ctypes.POINTER(_f64p), ctypes.POINTER(_i64), _f64p, _f64p, ctypes.c_double,
+            ctypes.c_int32, ctypes.c_int32, _int, _f32p, _i32p]
+        handle.vgt_ref_voxelize_posed_f64.argtypes = [
+            _f32p, _i64, _i64, _i64, ctypes.c_double, _f64p, ctypes.c_int32,
+            ctypes.POINTER(_f64p), ctypes.POINTER(_i64), _f64p, _f64p, ctypes.c_double,
+            ctypes.c_int32, ctypes.c_int32, _int, _f32p]
+        handle.vgt_ref_raycast_single_f64.argtypes = [
+            _f64p, _f64p, ctypes.c_double, _i64, _i64, _i64, ctypes.c_double, _i32p]
+        handle.vgt_ref_isometry_product.argtypes = [_f64p, _f64p, _f64p]
+        handle.vgt_ref_isometry_product.restype = None
+        handle.vgt_ref_isometry_inverse.argtypes = [_f64p, _f64p]
+        handle.vgt_ref_isometry_inverse.restype = None
+        _voxelizer_bound = True
+    return handle
+
+
+def voxelizer_available() -> bool:
+    if not available():
+        return False
+    try:
+        return hasattr(lib(), "vgt_ref_voxelize_f64")
+    except OSError:
+        return False
+
+
+def _cloud_arrays(clouds):
+    points = [np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 3) for p, _, _ in clouds]
+    pointers = (_f64p * max(1, len(clouds)))(*[p.ctypes.data_as(_f64p) for p in points])
+    sizes = (_i64 * max(1, len(clouds)))(*[p.shape[0] for p in points])
+    poses = np.ascontiguousarray(
+        np.stack([np.asarray(x, dtype=np.float64).reshape(4, 4).T for _, x, _ in clouds])
+        if clouds else np.zeros((1, 4, 4)))
+    ranges = np.ascontiguousarray([float(r) for _, _, r in clouds] or [0.0], dtype=np.float64)
+    return points, pointers, sizes, poses, ranges
+
+
+def voxelize(static_occupancy, clouds, voxel_size: float, percent_seen_free: float,
+             outlier_points_threshold: int, num_cameras_seen_free: int, threads: int = 0):
+    """clouds = [(points_xyz, x_gc 4x4, max_range), ...] -> (filtered occupancy,
+    counts[cloud, x, y, z, 2]); same contract as oracle.voxelize, computed by the reference's
+    RaycastPointCloud / CombineAndFilterGrids."""
+    occ = np.ascontiguousarray(static_occupancy, dtype=np.float32)
+    out = np.empty_like(occ)
+    counts = np.zeros((len(clouds),) + occ.shape + (2,), dtype=np.int32)
+    keep, pointers, sizes, poses, ranges = _cloud_arrays(clouds)
+    code = _voxelizer_lib().vgt_ref_voxelize_f64(
+        occ.ctypes.data_as(_f32p), *occ.shape, float(voxel_size), len(clouds), pointers, sizes,
+        poses.ctypes.data_as(_f64p), ranges.ctypes.data_as(_f64p), float(percent_seen_free),
+        int(outlier_points_threshold), int(num_cameras_seen_free), threads,
+        out.ctypes.data_as(_f32p), counts.ctypes.data_as(_i32p))
+    del keep
+    if code != 0:
+        raise RuntimeError("reference voxelizer failed")
+    return out, counts
+
+
+def voxelize_posed(static_occupancy, x_wg, clouds, voxel_size: float, percent_seen_free: float,
+                   outlier_points_threshold: int, num_cameras_seen_free: int, threads: int = 0):
+    """The interface call with a posed grid: clouds = [(points, x_wc, max_range), ...]; the
+    reference composes X_GC = X_WG^-1 * X_WC itself. Returns the filtered occupancy."""
+    occ = np.ascontiguousarray(static_occupancy, dtype=np.float32)
+    out = np.empty_like(occ)
+    keep, pointers, sizes, poses, ranges = _cloud_arrays(clouds)
+    origin = np.ascontiguousarray(np.asarray(x_wg, dtype=np.float64).reshape(4, 4).T)
+    code = _voxelizer_lib().vgt_ref_voxelize_posed_f64(
+        occ.ctypes.data_as(_f32p), *occ.shape, float(voxel_size), origin.ctypes.data_as(_f64p),
+        len(clouds), pointers, sizes, poses.ctypes.data_as(_f64p), ranges.ctypes.data_as(_f64p),
+        float(percent_seen_free), int(outlier_points_threshold), int(num_cameras_seen_free),
+        threads, out.ctypes.data_as(_f32p))
+    del keep
+    if code != 0:
+        raise RuntimeError("reference voxelizer failed")
+    return out
+
+
+def raycast_single(origin, point, max_range: float, dims, voxel_size: float):
+    nx, ny, nz = (int(d) for d in dims)
+    counts = np.zeros((nx, ny, nz, 2), dtype=np.int32)
+    o = np.ascontiguousarray(origin, dtype=np.float64)
+    p = np.ascontiguousarray(point, dtype=np.float64)
+    if _voxelizer_lib().vgt_ref_raycast_single_f64(
+            o.ctypes.data_as(_f64p), p.ctypes.data_as(_f64p), float(max_range), nx, ny, nz,
+            float(voxel_size), counts.ctypes.data_as(_i32p)):
+        raise ValueError("reference RaycastSinglePoint threw")
+    return counts
+
+
+def isometry_product(a, b) -> np.ndarray:
+    """a * b for rigid 4x4 transforms (row-major numpy in and out), in the fixed operation order
+    of the stand-in (oracle/ref_shim/Eigen/Geometry)."""
+    a_cm = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(4, 4).T)
+    b_cm = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(4, 4).T)
+    out = np.empty((4, 4), dtype=np.float64)
+    _voxelizer_lib().vgt_ref_isometry_product(
+        a_cm.ctypes.data_as(_f64p), b_cm.ctypes.data_as(_f64p), out.ctypes.data_as(_f64p))
+    return np.ascontiguousarray(out.T)
+
+
+def isometry_inverse(a) -> np.ndarray:
+    a_cm = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(4, 4).T)
+    out = np.empty((4, 4), dtype=np.float64)
+    _voxelizer_lib().vgt_ref_isometry_inverse(a_cm.ctypes.data_as(_f64p),
+                                              out.ctypes.data_as(_f64p))
+    return np.ascontiguousarray(out.T)

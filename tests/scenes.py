@@ -53,10 +53,15 @@ def reference_voxelization_scene():
 
 
 def inverse_rigid(transform):
-    inverse = np.eye(4)
-    inverse[:3, :3] = transform[:3, :3].T
-    inverse[:3, 3] = -(transform[:3, :3].T @ transform[:3, 3])
-    return inverse
+    """The front end's fixed-order inverse (grids.inverse_rigid)."""
+    from voxelized_geometry_tools_b200.grids import inverse_rigid as fixed_order_inverse
+    return fixed_order_inverse(transform)
+
+
+def compose(a, b):
+    """a * b in the fixed operation order every front end uses for X_GC (grids.compose_rigid)."""
+    from voxelized_geometry_tools_b200.grids import compose_rigid
+    return compose_rigid(a, b)
 
 
 def check_empty_voxelization(occupancy):

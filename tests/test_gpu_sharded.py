@@ -92,12 +92,12 @@ def test_device_voxelizer_pieces(shared_library, oracle):
     x_gw = scenes.inverse_rigid(scene["origin_transform"])
     counts = torch.zeros((len(scene["clouds"]), n, n, n, 2), dtype=torch.int32, device=dev)
     for index, (points, x_wc, max_range) in enumerate(scene["clouds"]):
-        vdev.raycast_cloud(torch.from_numpy(points).to(dev), x_gw @ x_wc, max_range,
+        vdev.raycast_cloud(torch.from_numpy(points).to(dev), scenes.compose(x_gw, x_wc), max_range,
                            counts[index], scene["voxel_size"])
     occupancy = torch.from_numpy(scene["static_occupancy"]).to(dev)
     vdev.filter_grids(counts, occupancy, PointCloudVoxelizationFilterOptions(0.9, 2, 2))
     want, want_counts = oracle.voxelize(
-        scene["static_occupancy"], [(p, x_gw @ x, r) for p, x, r in scene["clouds"]],
+        scene["static_occupancy"], [(p, scenes.compose(x_gw, x), r) for p, x, r in scene["clouds"]],
         scene["voxel_size"], 0.9, 2, 2)
     np.testing.assert_array_equal(counts.cpu().numpy(), want_counts)
     np.testing.assert_array_equal(occupancy.cpu().numpy(), want)

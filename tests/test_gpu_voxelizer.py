@@ -20,7 +20,7 @@ def build(scene, clouds):
 
 def oracle_voxelize(oracle, scene, clouds, filter_options):
     x_gw = scenes.inverse_rigid(scene["x_wg"])
-    prepared = [(points, x_gw @ x_wc, max_range) for points, x_wc, max_range in clouds]
+    prepared = [(points, scenes.compose(x_gw, x_wc), max_range) for points, x_wc, max_range in clouds]
     return oracle.voxelize(scene["static"], prepared, scene["voxel_size"], *filter_options)
 
 
@@ -117,3 +117,46 @@ def test_argument_errors(shared_library):
         vgt.PointCloudVoxelizationFilterOptions(0.0, 1, 1)
     with pytest.raises(_capi.BackendUnavailable):   # dev_pcv.hpp:34-46
         vgt.B200PointCloudVoxelizer({"CUDA_DEVICE": 77})
+
+
+def test_zero_length_rays_with_the_origin_outside_the_grid(shared_library, oracle):
+    # A point ON the sensor origin (zero-filled invalid depth return) while the origin is outside
+    # the grid: direction 0 / 0. The CPU path marks nothing (cpu_pcv.cpp:229-297: the NaN start
+    # index is out of bounds); the device path must not walk from voxel (0, 0, 0).
+    dims, voxel = (16, 16, 16), 0.1
+    sizes = vgt.VoxelGridSizes.FromVoxelCounts(voxel, dims)
+    static = vgt.OccupancyMap(np.eye(4), "world", sizes)
+    points = np.zeros((64, 3))
+    points[1::2] = [0.3, 0.2, 0.1]          # every other point is a real one
+    for origin in ((-1.0, 0.5, 0.5), (0.5, 3.0, 0.5), (-2.0, -2.0, -2.0), (0.5, 0.5, 0.5)):
+        pose = scenes.translation(*origin)
+        wrapper = vgt.VectorPointCloudWrapper(points, pose, np.inf)
+        _, counts = vgt.B200PointCloudVoxelizer().VoxelizePointCloudsWithCounts(
+            static, vgt.PointCloudVoxelizationFilterOptions(), [wrapper])
+        want = oracle.raycast_cloud(points, pose, np.inf, dims, voxel)
+        np.testing.assert_array_equal(counts[0], want)
+
+
+def test_counts_equal_the_compiled_reference(shared_library):
+    # Directly against the REFERENCE'S OWN cpu_pointcloud_voxelization.cpp (oracle/_ref, built in
+    # the dev container, travels prebuilt): raw counts and the filtered map, bit for bit.
+    from oracle import reference_oracle
+    if not reference_oracle.voxelizer_available():
+        pytest.skip("oracle/_ref/libvgt_ref.so not built with the voxelizer")
+    scene = synthetic.depth_camera_scene(128, 0.04, 320, 240, max_range=4.0)
+    packed = {"static": scene["static_occupancy"], "x_wg": scene["origin_transform"],
+              "voxel_size": scene["voxel_size"]}
+    static, wrappers = build(packed, scene["clouds"])
+    x_gw = scenes.inverse_rigid(scene["origin_transform"])
+    prepared = [(p, scenes.compose(x_gw, x), r) for p, x, r in scene["clouds"]]
+    for filter_options in ((1.0, 1, 1), (0.9, 2, 2)):
+        got, counts = vgt.B200PointCloudVoxelizer().VoxelizePointCloudsWithCounts(
+            static, vgt.PointCloudVoxelizationFilterOptions(*filter_options), wrappers)
+        want, want_counts = reference_oracle.voxelize(scene["static_occupancy"], prepared,
+                                                      scene["voxel_size"], *filter_options)
+        np.testing.assert_array_equal(counts, want_counts)
+        np.testing.assert_array_equal(got.GetImmutableRawData(), want)
+    # and the interface call on the posed grid (the reference composes X_GC itself)
+    posed = reference_oracle.voxelize_posed(scene["static_occupancy"], scene["origin_transform"],
+                                            scene["clouds"], scene["voxel_size"], 0.9, 2, 2)
+    np.testing.assert_array_equal(got.GetImmutableRawData(), posed)

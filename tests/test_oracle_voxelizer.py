@@ -7,7 +7,7 @@ from . import scenes
 
 def _oracle_voxelize(oracle, scene, clouds):
     x_gw = scenes.inverse_rigid(scene["x_wg"])
-    prepared = [(points, x_gw @ x_wc, max_range) for points, x_wc, max_range in clouds]
+    prepared = [(points, scenes.compose(x_gw, x_wc), max_range) for points, x_wc, max_range in clouds]
     return oracle.voxelize(scene["static"], prepared, scene["voxel_size"], *scene["filter"])
 
 
@@ -28,8 +28,8 @@ def test_threads_do_not_change_counts(oracle, threads):
     scene = scenes.reference_voxelization_scene()
     x_gw = scenes.inverse_rigid(scene["x_wg"])
     points, x_wc, max_range = scene["clouds"][0]
-    base = oracle.raycast_cloud(points, x_gw @ x_wc, max_range, (8, 8, 8), 0.25, threads=1)
-    other = oracle.raycast_cloud(points, x_gw @ x_wc, max_range, (8, 8, 8), 0.25, threads=threads)
+    base = oracle.raycast_cloud(points, scenes.compose(x_gw, x_wc), max_range, (8, 8, 8), 0.25, threads=1)
+    other = oracle.raycast_cloud(points, scenes.compose(x_gw, x_wc), max_range, (8, 8, 8), 0.25, threads=threads)
     np.testing.assert_array_equal(base, other)
 
 

@@ -133,6 +133,15 @@ __global__ void __launch_bounds__(128) RaycastCloudKernel(
   const Cell origin_cell = CellOf(grid, ox, oy, oz);
   if (!InGrid(grid, origin_cell))
   {
+    // A point on the sensor origin (e.g. a zero-filled invalid depth return): the direction is
+    // 0 / 0, the start point NaN. On the CPU the NaN start index converts to INT64_MIN, is out
+    // of bounds and the ray marks nothing (its final voxel, the origin's, is outside the grid
+    // too); a device float -> int conversion of NaN gives 0 instead and would walk from voxel
+    // (0, 0, 0). Same outcome as the CPU path, stated explicitly.
+    if (!(ray_length > 0.0))
+    {
+      return;
+    }
     double t_enter = 0.0;
     double t_exit = max_range;
     const double direction[3] = {rx / ray_length, ry / ray_length, rz / ray_length};

@@ -29,6 +29,38 @@ import numpy as np
 from . import _capi
 
 
+
+def compose_rigid(a, b) -> np.ndarray:
+    """a * b for rigid 4x4 transforms with ONE fixed operation order, element (r, c) =
+    ((a[r,0]*b[0,c] + a[r,1]*b[1,c]) + a[r,2]*b[2,c]) + a[r,3]*b[3,c], no fused multiply-add.
+    The voxelizer's counts depend on the last bits of X_GC = X_GW * X_WC
+    (cpu_pointcloud_voxelization.cpp:172-176), and a BLAS matmul is free to sum in another
+    order; the C++ adapter, the oracle's stand-in for Eigen (oracle/ref_shim/Eigen/Geometry) and
+    this function all use this order (tests/test_oracle_vs_reference.py pins it)."""
+    a = np.asarray(a, dtype=np.float64).reshape(4, 4)
+    b = np.asarray(b, dtype=np.float64).reshape(4, 4)
+    out = np.empty((4, 4), dtype=np.float64)
+    for r in range(4):
+        for c in range(4):
+            out[r, c] = ((a[r, 0] * b[0, c] + a[r, 1] * b[1, c]) + a[r, 2] * b[2, c]) \
+                + a[r, 3] * b[3, c]
+    return out
+
+
+def inverse_rigid(transform) -> np.ndarray:
+    """Inverse of a rigid transform: R^T and -(R^T t) with t summed left to right, as the
+    oracle's stand-in for Eigen::Isometry3d::inverse() does."""
+    m = np.asarray(transform, dtype=np.float64).reshape(4, 4)
+    inverse = np.eye(4)
+    for r in range(3):
+        for c in range(3):
+            inverse[r, c] = m[c, r]
+    for r in range(3):
+        inverse[r, 3] = -((inverse[r, 0] * m[0, 3] + inverse[r, 1] * m[1, 3])
+                          + inverse[r, 2] * m[2, 3])
+    return inverse
+
+
 @dataclass(frozen=True)
 class VoxelGridSizes:
     voxel_size: float
@@ -199,12 +231,7 @@ class OccupancyMap:
         return self._origin_transform
 
     def InverseOriginTransform(self):
-        rotation = self._origin_transform[:3, :3]
-        translation = self._origin_transform[:3, 3]
-        inverse = np.eye(4)
-        inverse[:3, :3] = rotation.T
-        inverse[:3, 3] = -(rotation.T @ translation)
-        return inverse
+        return inverse_rigid(self._origin_transform)
 
     def GetMutableRawData(self) -> np.ndarray:
         return self._data

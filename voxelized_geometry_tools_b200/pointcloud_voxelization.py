@@ -20,7 +20,7 @@ from typing import Callable, Sequence
 import numpy as np
 
 from . import _capi
-from .grids import OccupancyMap
+from .grids import OccupancyMap, compose_rigid
 
 
 class SeenAs(enum.IntEnum):
@@ -160,7 +160,8 @@ class VoxelizerRuntime:
 def grid_from_cloud_transform(static_environment: OccupancyMap,
                               cloud: PointCloudWrapper) -> np.ndarray:
     """X_GC = X_GW * X_WC (cpu_pointcloud_voxelization.cpp:172-176)."""
-    return static_environment.InverseOriginTransform() @ cloud.PointCloudOriginTransform()
+    return compose_rigid(static_environment.InverseOriginTransform(),
+                         cloud.PointCloudOriginTransform())
 
 
 class PointCloudVoxelizationInterface:
