@@ -216,6 +216,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def time_cpp_adapter(n: int):
+    """The real drop-in call (C++ host adapter compiled against the reference's headers): the
+    prebuilt adapter_test binaries time b200::ExtractSignedDistanceFieldFromOccupancyMap on an
+    n^3 map with std::vector storage, piece by piece. None when they were not built."""
+    build = REPO / "voxelized_geometry_tools_b200" / "cpp" / "_build"
+    timed = {}
+    for key, name in (("reference_lock", "adapter_test"),
+                      ("with_known_extrema_accessor", "adapter_test_fast_lock")):
+        binary = build / name
+        if not binary.exists():
+            continue
+        try:
+            out = subprocess.run([str(binary), "--time", str(n)], capture_output=True, text=True,
+                                 timeout=600)
+            timed[key] = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as error:     # a timing aid must not break the bench line
+            timed[key] = {"error": repr(error)}
+    return timed or None
+
+
 def sharded_parity(sharded, vdev, synthetic, plan, result, dims, dev, rank, world):
     """Outside the timed region: (1) the sharded SDF of the bench grid == the one-GPU SDF of the
     same grid, bit for bit, slab by slab on rank 0 (plus min/max); (2) a 256^3 grid through the
@@ -476,6 +496,7 @@ def run_ours(args):
                                    "unit": "Gvoxels/s", "ms_per_step": pageable_seconds * 1e3,
                                    "equals_pinned_result": bool(
                                        np.array_equal(pageable_out, host_out.numpy()))}
+        e2e["cpp_adapter"] = time_cpp_adapter(dims[0])
     else:
         # Per-rank host slabs in, y-slabs out, through the sharded public API; pinned buffers on
         # both sides (as at N=1), reused across steps.

@@ -145,6 +145,19 @@ VGT_B200_API int vgt_b200_sdf_free_and_named_f64(
     int unknown_is_filled, int add_virtual_border, int device, double* sdf_out, double* out_min,
     double* out_max);
 
+/* Replaces internal::ComputeDistanceFieldTransformInPlace(DegreeOfParallelism, VoxelGrid<double>&)
+ * (include/.../signed_distance_field_generation.hpp:34-37, src/.../signed_distance_field_generation.cpp:258-391):
+ * the in-place 3-D squared distance transform D(p) = min over q of f(q) + |p - q|^2 (voxel
+ * units) of an arbitrary sampled function, passes along X, Y, Z, axes of one voxel skipped.
+ *   field   host double[nx*ny*nz], GetMutableRawData().data() of the EDTDistanceField; on return
+ *           it holds the transform. Samples must be +inf ("no site") or non-negative integers --
+ *           what every caller in the reference stores (0 / +inf marks, sdfgen.hpp:47-74) and what
+ *           keeps the transform exact; anything else, or values whose transform could pass 2^29,
+ *           fails with VGT_B200_ERR_UNSUPPORTED and leaves the field untouched.
+ * The reference's DegreeOfParallelism argument has no device meaning and is not passed. */
+VGT_B200_API int vgt_b200_edt_transform_inplace_f64(
+    double* field, int64_t nx, int64_t ny, int64_t nz, int device);
+
 /* Parity hook for internal::ComputeDistanceFieldTransformInPlace on the two 0/inf fields
  * (include/.../signed_distance_field_generation.hpp:34-37, 47-80): both squared fields in voxel
  * units as int32, VGT_B200_SQ_INF where the reference holds +inf. Host pointers. */

@@ -227,3 +227,39 @@ def test_axes_longer_than_1024_and_large_distances(shared_library, oracle):
     sparse = np.zeros((3, 40, 2100), dtype=np.float32)   # z distances up to 2099 -> sq > 2^21
     sparse[1, 20, 0] = 1.0
     assert_matches_oracle(oracle, sparse, 0.5)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 1, 40), (9, 1, 7), (1, 33, 5), (11, 14, 9),
+                                   (40, 36, 70), (3, 130, 33), (64, 64, 64)])
+def test_transform_in_place_on_sampled_functions(shared_library, oracle, shape):
+    # vgt_b200_edt_transform_inplace_f64 == ComputeDistanceFieldTransformInPlace
+    # (sdfgen.hpp:34-37) on arbitrary integer / +inf samples, against the reference's own code
+    # where oracle/_ref is there, else the restatement.
+    from oracle import reference_oracle
+    checker = reference_oracle.transform_inplace if reference_oracle.available() \
+        else oracle.transform_inplace
+    rng = np.random.default_rng(sum(shape))
+    for scale, inf_rate in ((1, 0.0), (400, 0.3), (50000, 0.9), (7, 1.0), (3, 0.97)):
+        field = rng.integers(0, scale + 1, size=shape).astype(np.float64)
+        field[rng.random(shape) < inf_rate] = np.inf
+        want = checker(field.copy())
+        got = vgt.ComputeDistanceFieldTransformInPlace(field.copy())
+        np.testing.assert_array_equal(got, want)
+    # the binary 0 / inf marks of the SDF path
+    marks = np.where(rng.random(shape) < 0.05, 0.0, np.inf)
+    np.testing.assert_array_equal(vgt.ComputeDistanceFieldTransformInPlace(marks.copy()),
+                                  checker(marks.copy()))
+
+
+def test_transform_in_place_rejects_what_it_cannot_do_exactly(shared_library):
+    field = np.full((4, 4, 4), 2.5)
+    before = field.copy()
+    with pytest.raises(NotImplementedError):
+        vgt.ComputeDistanceFieldTransformInPlace(field)
+    np.testing.assert_array_equal(field, before)
+    with pytest.raises(NotImplementedError):
+        vgt.ComputeDistanceFieldTransformInPlace(np.full((4, 4, 4), -1.0))
+    with pytest.raises(NotImplementedError):
+        vgt.ComputeDistanceFieldTransformInPlace(np.full((4, 4, 4), 2.0 ** 30))
+    with pytest.raises(ValueError):
+        vgt.ComputeDistanceFieldTransformInPlace(np.zeros((4, 4), dtype=np.float64))

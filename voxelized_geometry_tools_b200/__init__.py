@@ -11,6 +11,7 @@ the GPU through libvgt_b200.so (include/vgt_b200.h); there is no CPU fallback.
 """
 from ._capi import BackendUnavailable, device_count  # noqa: F401
 from .grids import (  # noqa: F401
+    ComputeDistanceFieldTransformInPlace,
     ComputeSquaredDistanceFields,
     ExtractSignedDistanceFieldFromMask,
     OccupancyComponentMap,

@@ -65,6 +65,7 @@ SIGNATURES = {
                                                _vp, _f32p, _f32p]),
     "vgt_b200_sdf_free_and_named_f64": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _int, _int,
                                                _vp, _f64p, _f64p]),
+    "vgt_b200_edt_transform_inplace_f64": (_int, [_vp, _i64, _i64, _i64, _int]),
     "vgt_b200_edt_sq_i32": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "vgt_b200_sdf_f32_dev": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _int, _vp, _vp, _vp]),
     "vgt_b200_sdf_f32_dev_profile": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _int, _vp, _vp,
@@ -121,6 +122,8 @@ def check(code: int) -> None:
     message = last_error()
     if code == ERR_INVALID_ARGUMENT:
         raise ValueError(message)        # std::invalid_argument
+    if code == ERR_UNSUPPORTED:
+        raise NotImplementedError(message)
     raise RuntimeError(message)          # std::runtime_error
 
 

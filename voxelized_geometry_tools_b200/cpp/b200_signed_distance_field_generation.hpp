@@ -46,6 +46,43 @@ inline void ThrowOnError(const int status)
   throw std::runtime_error(message);
 }
 
+// Locks a finished SDF. The reference's Lock() re-derives the extrema with a serial
+// std::minmax_element over every value (signed_distance_field.hpp:765-787) - at 512^3 that is
+// longer than the whole device computation. The device already returns the same pair, so with
+// the one-line accessor INTEGRATION.md proposes for SignedDistanceField (install known extrema
+// and lock; define VGT_B200_SDF_HAS_LOCK_WITH_KNOWN_EXTREMA when it is there) the scan is
+// skipped; without it the adapter calls Lock() like the reference.
+template <typename ScalarType>
+inline void FinishAndLock(SignedDistanceField<ScalarType>& sdf, const ScalarType minimum,
+                          const ScalarType maximum)
+{
+#ifdef VGT_B200_SDF_HAS_LOCK_WITH_KNOWN_EXTREMA
+  sdf.LockWithKnownExtrema(minimum, maximum);
+#else
+  (void)minimum;
+  (void)maximum;
+  sdf.Lock();
+#endif
+}
+
+// Drop-in for internal::ComputeDistanceFieldTransformInPlace(parallelism, distance_field)
+// (signed_distance_field_generation.hpp:34-37): the squared distance transform of the sampled
+// function in `distance_field`, in place, on the device. `parallelism` is accepted and ignored.
+// The device transform is exact integer arithmetic: samples must be +inf or non-negative
+// integers (all the reference's callers store 0 / +inf); anything else throws
+// std::runtime_error and leaves the field untouched.
+template <typename DistanceFieldType, typename ParallelismType>
+inline void ComputeDistanceFieldTransformInPlace(
+    const ParallelismType& /* parallelism */, DistanceFieldType& distance_field,
+    const int device = 0)
+{
+  static_assert(sizeof(distance_field.GetMutableRawData()[0]) == sizeof(double),
+                "EDTDistanceField is a VoxelGrid<double> (sdfgen.hpp:30-32)");
+  ThrowOnError(vgt_b200_edt_transform_inplace_f64(
+      distance_field.GetMutableRawData().data(), distance_field.NumXVoxels(),
+      distance_field.NumYVoxels(), distance_field.NumZVoxels(), device));
+}
+
 namespace detail
 {
 inline int CallMask(const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz, double resolution,
@@ -113,9 +150,7 @@ inline SignedDistanceField<SDFScalarType> ExtractSignedDistanceField(
   ThrowOnError(detail::CallMask(
       mask.data(), nx, ny, nz, grid.VoxelXSize(), parameters.AddVirtualBorder(), device,
       new_sdf.GetMutableRawData().data(), &minimum, &maximum));
-  // Lock() recomputes min/max on the host exactly like the reference (sdf.hpp:765-787); the
-  // device-computed pair is identical and is what a friend accessor could install instead.
-  new_sdf.Lock();
+  FinishAndLock(new_sdf, minimum, maximum);
   return new_sdf;
 }
 
@@ -145,7 +180,7 @@ inline SignedDistanceField<SDFScalarType> ExtractSignedDistanceFieldFromOccupanc
       occupancy, map.NumXVoxels(), map.NumYVoxels(), map.NumZVoxels(), map.VoxelXSize(),
       parameters.UnknownIsFilled(), parameters.AddVirtualBorder(), device,
       new_sdf.GetMutableRawData().data(), &minimum, &maximum));
-  new_sdf.Lock();
+  FinishAndLock(new_sdf, minimum, maximum);
   return new_sdf;
 }
 }  // namespace b200

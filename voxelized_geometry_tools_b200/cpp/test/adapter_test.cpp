@@ -14,11 +14,21 @@
 #include <stdexcept>
 #include <vector>
 
+#include <chrono>
+#include <cstring>
+#include <set>
+#include <string>
+
 #include <Eigen/Geometry>
+#include <voxelized_geometry_tools/occupancy_component_map.hpp>
 #include <voxelized_geometry_tools/occupancy_map.hpp>
+#include <voxelized_geometry_tools/pointcloud_voxelization.hpp>
 #include <voxelized_geometry_tools/pointcloud_voxelization_interface.hpp>
 #include <voxelized_geometry_tools/signed_distance_field.hpp>
+#include <voxelized_geometry_tools/tagged_object_occupancy_component_map.hpp>
+#include <voxelized_geometry_tools/tagged_object_occupancy_map.hpp>
 
+#include "b200_cell_map_signed_distance_fields.hpp"
 #include "b200_pointcloud_voxelization.hpp"
 #include "b200_signed_distance_field_generation.hpp"
 
@@ -281,15 +291,350 @@ void VoxelizationTest()
   EXPECT_TRUE(sdf.GetIndexImmutable(3, 3, 4).Value() > 0.0f);
 }
 
-int main()
+// A small deterministic scene for the cell maps: occupancy in {0, 0.5, 1}, object ids 0..3.
+struct CellScene
+{
+  int64_t nx = 9, ny = 12, nz = 10;
+  double resolution = 0.25;
+  float Occupancy(int64_t x, int64_t y, int64_t z) const
+  {
+    const uint32_t h = static_cast<uint32_t>(x * 73856093u) ^ static_cast<uint32_t>(y * 19349663u)
+        ^ static_cast<uint32_t>(z * 83492791u);
+    if ((x / 3 + y / 4 + z / 3) % 3 == 0) { return 1.0f; }
+    return (h % 17u == 0u) ? 0.5f : 0.0f;
+  }
+  uint32_t ObjectId(int64_t x, int64_t y, int64_t z) const
+  {
+    return static_cast<uint32_t>((x / 3 + 2 * (y / 4) + z / 5) % 4);
+  }
+  VoxelGridSizes Sizes() const
+  {
+    return VoxelGridSizes::FromVoxelCounts(
+        resolution, common_robotics_utilities::voxel_grid::Vector3i64(nx, ny, nz));
+  }
+};
+
+template <typename ScalarType>
+bool SameValues(const SignedDistanceField<ScalarType>& a, const SignedDistanceField<ScalarType>& b)
+{
+  return a.GetImmutableRawData() == b.GetImmutableRawData()
+      && a.GetMinimumMaximum().Minimum() == b.GetMinimumMaximum().Minimum()
+      && a.GetMinimumMaximum().Maximum() == b.GetMinimumMaximum().Maximum() && a.IsLocked()
+      && b.IsLocked();
+}
+
+// The three cell-map types: same SDF as OccupancyMap for the same occupancy
+// (test/sdf_generation_test.cpp:152-189), object lists, per-object batches, free-and-named merge.
+template <typename ScalarType>
+void CellMapTests()
+{
+  const CellScene scene;
+  const auto origin = Eigen::Isometry3d::FromTranslation(1.0, 2.0, 3.0);
+  OccupancyMap occupancy_map(origin, "cells", scene.Sizes(), OccupancyCell(0.0f));
+  OccupancyComponentMap component_map(origin, "cells", scene.Sizes(), OccupancyComponentCell(0.0f));
+  TaggedObjectOccupancyMap tagged_map(origin, "cells", scene.Sizes(),
+                                      TaggedObjectOccupancyCell(0.0f));
+  TaggedObjectOccupancyComponentMap tagged_component_map(
+      origin, "cells", scene.Sizes(), TaggedObjectOccupancyComponentCell(0.0f));
+  for (int64_t x = 0; x < scene.nx; x++)
+    for (int64_t y = 0; y < scene.ny; y++)
+      for (int64_t z = 0; z < scene.nz; z++)
+      {
+        const float occupancy = scene.Occupancy(x, y, z);
+        const uint32_t id = scene.ObjectId(x, y, z);
+        occupancy_map.SetIndex(x, y, z, OccupancyCell(occupancy));
+        component_map.SetIndex(x, y, z, OccupancyComponentCell(occupancy, 7u));
+        tagged_map.SetIndex(x, y, z, TaggedObjectOccupancyCell(occupancy, id));
+        tagged_component_map.SetIndex(
+            x, y, z, TaggedObjectOccupancyComponentCell(occupancy, id, 5u, 9u));
+      }
+  for (const bool unknown_is_filled : {true, false})
+    for (const bool border : {false, true})
+    {
+      const SignedDistanceFieldGenerationParameters<ScalarType> params(
+          std::numeric_limits<ScalarType>::infinity(), DegreeOfParallelism::None(),
+          unknown_is_filled, border);
+      const auto want = b200::ExtractSignedDistanceFieldFromOccupancyMap(occupancy_map, params);
+      EXPECT_TRUE(SameValues(want, b200::ExtractSignedDistanceFieldFromCellMap(
+                                       component_map, {}, params)));
+      EXPECT_TRUE(SameValues(want, b200::ExtractSignedDistanceFieldFromCellMap(
+                                       tagged_map, {}, params)));
+      EXPECT_TRUE(SameValues(want, b200::ExtractSignedDistanceFieldFromCellMap(
+                                       tagged_component_map, {}, params)));
+      // objects_to_use (tagged_object_occupancy_map.hpp:199-247) against the opaque-predicate
+      // path with the reference's own predicate
+      const std::vector<uint32_t> objects_to_use = {3u, 1u, 3u};
+      const std::set<uint32_t> wanted(objects_to_use.begin(), objects_to_use.end());
+      const std::function<bool(const GridIndex&)> listed_fn = [&](const GridIndex& index)
+      {
+        const auto cell = tagged_map.GetIndexImmutable(index).Value();
+        if (wanted.count(cell.ObjectId()) != 1) { return false; }
+        return (cell.Occupancy() > 0.5) || (unknown_is_filled && cell.Occupancy() == 0.5);
+      };
+      const auto listed_want = b200::ExtractSignedDistanceField<
+          TaggedObjectOccupancyCell, std::vector<TaggedObjectOccupancyCell>, ScalarType>(
+          tagged_map, listed_fn, tagged_map.Frame(), params);
+      EXPECT_TRUE(SameValues(listed_want, b200::ExtractSignedDistanceFieldFromCellMap(
+                                              tagged_map, objects_to_use, params)));
+      EXPECT_TRUE(SameValues(listed_want, b200::ExtractSignedDistanceFieldFromCellMap(
+                                              tagged_component_map, objects_to_use, params)));
+      // MakeSeparateObjectSDFs / MakeAllObjectSDFs (:249-291)
+      const auto separate = b200::MakeSeparateObjectSDFs(tagged_map, {2u, 1u}, params);
+      EXPECT_TRUE(separate.size() == 2);
+      for (const auto& id_and_sdf : separate)
+      {
+        EXPECT_TRUE(SameValues(id_and_sdf.second, b200::ExtractSignedDistanceFieldFromCellMap(
+                                                      tagged_map, {id_and_sdf.first}, params)));
+      }
+      const auto all_objects = b200::MakeAllObjectSDFs(tagged_component_map, params);
+      EXPECT_TRUE(all_objects.size() == 3 && all_objects.count(0u) == 0);
+      EXPECT_TRUE(SameValues(all_objects.at(2u), separate.at(2u)));
+      // ExtractFreeAndNamedObjectsSignedDistanceField (:293-378): free >= 0 -> free; else
+      // named <= -0 -> named; else 0
+      const std::function<bool(const GridIndex&)> named_fn = [&](const GridIndex& index)
+      {
+        const auto cell = tagged_map.GetIndexImmutable(index).Value();
+        if (cell.ObjectId() == 0u) { return false; }
+        return (cell.Occupancy() > 0.5) || (unknown_is_filled && cell.Occupancy() == 0.5);
+      };
+      const auto named = b200::ExtractSignedDistanceField<
+          TaggedObjectOccupancyCell, std::vector<TaggedObjectOccupancyCell>, ScalarType>(
+          tagged_map, named_fn, tagged_map.Frame(), params);
+      const auto merged = b200::ExtractFreeAndNamedObjectsSignedDistanceField(tagged_map, params);
+      EXPECT_TRUE(merged.IsLocked());
+      bool merge_ok = true;
+      for (size_t i = 0; i < merged.GetImmutableRawData().size(); i++)
+      {
+        const ScalarType free_value = want.GetImmutableRawData()[i];
+        const ScalarType named_value = named.GetImmutableRawData()[i];
+        const ScalarType expected =
+            (free_value >= 0) ? free_value : ((named_value <= -0.0) ? named_value : ScalarType(0));
+        merge_ok = merge_ok && (merged.GetImmutableRawData()[i] == expected);
+      }
+      EXPECT_TRUE(merge_ok);
+      EXPECT_TRUE(SameValues(merged, b200::ExtractFreeAndNamedObjectsSignedDistanceField(
+                                         tagged_component_map, params)));
+    }
+}
+
+// b200::ComputeDistanceFieldTransformInPlace against a brute-force transform.
+void TransformTest()
+{
+  using common_robotics_utilities::voxel_grid::VoxelGrid;
+  const int64_t nx = 7, ny = 9, nz = 11;
+  const double inf = std::numeric_limits<double>::infinity();
+  VoxelGrid<double> field(
+      Eigen::Isometry3d::Identity(),
+      VoxelGridSizes::FromVoxelCounts(1.0, common_robotics_utilities::voxel_grid::Vector3i64(nx, ny, nz)),
+      inf);
+  std::vector<double> samples(static_cast<size_t>(nx * ny * nz), inf);
+  for (int64_t x = 0; x < nx; x++)
+    for (int64_t y = 0; y < ny; y++)
+      for (int64_t z = 0; z < nz; z++)
+      {
+        const uint32_t h = static_cast<uint32_t>(x * 7 + y * 31 + z * 101);
+        if (h % 13u == 0u)
+        {
+          samples[static_cast<size_t>((x * ny + y) * nz + z)] = static_cast<double>(h % 5u);
+          field.SetIndex(x, y, z, static_cast<double>(h % 5u));
+        }
+      }
+  b200::ComputeDistanceFieldTransformInPlace(DegreeOfParallelism::None(), field);
+  bool ok = true;
+  for (int64_t x = 0; x < nx; x++)
+    for (int64_t y = 0; y < ny; y++)
+      for (int64_t z = 0; z < nz; z++)
+      {
+        double best = inf;
+        for (int64_t a = 0; a < nx; a++)
+          for (int64_t b = 0; b < ny; b++)
+            for (int64_t c = 0; c < nz; c++)
+            {
+              const double candidate = samples[static_cast<size_t>((a * ny + b) * nz + c)]
+                  + static_cast<double>((x - a) * (x - a) + (y - b) * (y - b) + (z - c) * (z - c));
+              best = (candidate < best) ? candidate : best;
+            }
+        ok = ok && (field.GetIndexImmutable(x, y, z).Value() == best);
+      }
+  EXPECT_TRUE(ok);
+  // a sample the exact integer passes cannot take -> runtime_error, field untouched
+  field.SetIndex(0, 0, 0, 0.5);
+  bool threw = false;
+  try { b200::ComputeDistanceFieldTransformInPlace(DegreeOfParallelism::None(), field); }
+  catch (const std::runtime_error&) { threw = true; }
+  EXPECT_TRUE(threw && field.GetIndexImmutable(0, 0, 0).Value() == 0.5);
+}
+
+// The replacement factory (b200_voxelizer_backends.cpp) behind the reference's own declarations
+// (pointcloud_voxelization.hpp:53-68), as test/pointcloud_voxelization_test.cpp:269-311 uses it:
+// every available backend voxelizes the scene, and the B200 backend's map equals the map of the
+// REFERENCE'S OWN CPU backend (cpu_pointcloud_voxelization.cpp, linked into this binary).
+void FactoryTest()
+{
+  using namespace pointcloud_voxelization;
+  const auto backends = GetAvailableBackends();
+  EXPECT_TRUE(backends.size() >= 3);
+  EXPECT_TRUE(backends.front().BackendOption() == BackendOptions::CUDA);
+  EXPECT_TRUE(backends.front().DeviceOptions().at("CUDA_DEVICE") == 0);
+  EXPECT_TRUE(backends.back().BackendOption() == BackendOptions::CPU);
+  // a scene with clipped rays and rays from outside the grid
+  const auto grid_sizes = VoxelGridSizes::FromGridSizes(0.125, Eigen::Vector3d(4.0, 3.0, 2.0));
+  OccupancyMap static_environment(Eigen::Isometry3d::FromTranslation(-2.0, -1.5, -1.0), "world",
+                                  grid_sizes, OccupancyCell(0.0f));
+  for (int64_t x = 0; x < static_environment.NumXVoxels(); x++)
+    for (int64_t y = 0; y < static_environment.NumYVoxels(); y++)
+      static_environment.SetIndex(x, y, 0, OccupancyCell(1.0f));
+  std::vector<PointCloudWrapperSharedPtr> clouds;
+  const double poses[3][3] = {{-3.0, 0.1, 0.2}, {0.3, 0.2, 0.1}, {1.0, -2.5, 0.4}};
+  for (int c = 0; c < 3; c++)
+  {
+    auto cloud = std::make_shared<VectorVector3dPointCloudWrapper>();
+    cloud->SetPointCloudOriginTransform(
+        Eigen::Isometry3d::FromTranslation(poses[c][0], poses[c][1], poses[c][2]));
+    cloud->SetMaxRange((c == 1) ? 1.5 : std::numeric_limits<double>::infinity());
+    uint32_t state = 12345u + static_cast<uint32_t>(c);
+    for (int i = 0; i < 20000; i++)
+    {
+      double xyz[3];
+      for (double& value : xyz)
+      {
+        state = state * 1664525u + 1013904223u;
+        value = (static_cast<double>(state >> 8) / 16777216.0) * 6.0 - 3.0;
+      }
+      cloud->PushBack(xyz[0], xyz[1], xyz[2]);
+    }
+    clouds.push_back(cloud);
+  }
+  const PointCloudVoxelizationFilterOptions filter_options(0.9, 2, 1);
+  std::vector<OccupancyMap> results;
+  for (const auto& backend : backends)
+  {
+    std::vector<std::string> log;
+    const auto voxelizer =
+        MakePointCloudVoxelizer(backend, [&](const std::string& m) { log.push_back(m); });
+    EXPECT_TRUE(voxelizer != nullptr);
+    results.push_back(voxelizer->VoxelizePointClouds(static_environment, filter_options, clouds));
+  }
+  size_t filled = 0;
+  for (const auto& cell : results.front().GetImmutableRawData())
+  {
+    filled += (cell.Occupancy() == 1.0f) ? 1u : 0u;
+  }
+  EXPECT_TRUE(filled > 1000);
+  for (size_t i = 1; i < results.size(); i++)
+  {
+    EXPECT_TRUE(std::memcmp(results.front().GetImmutableRawData().data(),
+                            results[i].GetImmutableRawData().data(),
+                            sizeof(float) * results[i].GetImmutableRawData().size()) == 0);
+  }
+  // BEST_AVAILABLE picks the device backend; OpenCL is not part of this build; null logging ok
+  std::vector<std::string> log;
+  const auto best = MakePointCloudVoxelizer(BackendOptions::BEST_AVAILABLE, {},
+                                            [&](const std::string& m) { log.push_back(m); });
+  EXPECT_TRUE(dynamic_cast<const B200PointCloudVoxelizer*>(best.get()) != nullptr);
+  EXPECT_TRUE(!log.empty());
+  bool threw = false;
+  try { MakePointCloudVoxelizer(BackendOptions::OPENCL, {}); }
+  catch (const std::runtime_error&) { threw = true; }
+  EXPECT_TRUE(threw);
+  EXPECT_TRUE(MakePointCloudVoxelizer(BackendOptions::CPU, {{"CPU_PARALLELIZE", 0}}) != nullptr);
+}
+
+// `adapter_test --time N`: the REAL drop-in call on an N^3 map - SignedDistanceField
+// construction (the oob_value fill), the C-ABI call on pageable std::vector storage, Lock() -
+// timed piece by piece; one JSON line for bench.py (e2e.cpp_adapter).
+int TimeAdapter(const int64_t n)
+{
+  using Clock = std::chrono::steady_clock;
+  const auto sizes = VoxelGridSizes::FromVoxelCounts(
+      0.02, common_robotics_utilities::voxel_grid::Vector3i64(n, n, n));
+  OccupancyMap map(Eigen::Isometry3d::Identity(), "bench", sizes, OccupancyCell(0.0f));
+  {
+    // blobs: ~10 % filled
+    auto& cells = map.GetMutableRawData();
+    const int64_t spheres = 96;
+    uint32_t state = 42u;
+    const auto next = [&]() { state = state * 1664525u + 1013904223u; return state >> 8; };
+    for (int64_t s = 0; s < spheres; s++)
+    {
+      const int64_t cx = next() % n, cy = next() % n, cz = next() % n;
+      const int64_t radius = n / 16 + static_cast<int64_t>(next() % (n / 12 + 1));
+      for (int64_t x = std::max<int64_t>(0, cx - radius); x < std::min(n, cx + radius + 1); x++)
+        for (int64_t y = std::max<int64_t>(0, cy - radius); y < std::min(n, cy + radius + 1); y++)
+          for (int64_t z = std::max<int64_t>(0, cz - radius); z < std::min(n, cz + radius + 1); z++)
+            if ((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz) <= radius * radius)
+              cells[static_cast<size_t>((x * n + y) * n + z)] = OccupancyCell(1.0f);
+    }
+  }
+  const auto params = SDFGenerationParams<float>();
+  const auto seconds = [](Clock::time_point a, Clock::time_point b)
+  { return std::chrono::duration<double>(b - a).count(); };
+  double whole = 0.0, construct = 0.0, call = 0.0, lock = 0.0, known = 0.0;
+  const int reps = 3;
+  for (int rep = 0; rep < reps + 1; rep++)
+  {
+    const auto t0 = Clock::now();
+    const auto sdf = b200::ExtractSignedDistanceFieldFromOccupancyMap(map, params);
+    const auto t1 = Clock::now();
+    // the same pieces one by one
+    SignedDistanceField<float> pieces(map.OriginTransform(), map.Frame(), map.ControlSizes(),
+                                      params.OOBValue());
+    const auto t2 = Clock::now();
+    float lo = 0.0f, hi = 0.0f;
+    b200::ThrowOnError(vgt_b200_sdf_f32(
+        reinterpret_cast<const float*>(map.GetImmutableRawData().data()), n, n, n, 0.02, 1, 0, 0,
+        pieces.GetMutableRawData().data(), &lo, &hi));
+    const auto t3 = Clock::now();
+    pieces.Lock();
+    const auto t4 = Clock::now();
+    pieces.Unlock();
+    pieces.LockWithKnownExtrema(lo, hi);
+    const auto t5 = Clock::now();
+    if (!(pieces.GetImmutableRawData() == sdf.GetImmutableRawData())) { return 1; }
+    if (rep > 0)
+    {
+      whole += seconds(t0, t1);
+      construct += seconds(t1, t2);
+      call += seconds(t2, t3);
+      lock += seconds(t3, t4);
+      known += seconds(t4, t5);
+    }
+  }
+  const double voxels = static_cast<double>(n) * n * n;
+  std::printf(
+      "{\"api\": \"b200::ExtractSignedDistanceFieldFromOccupancyMap (std::vector storage, "
+      "SignedDistanceField construction, C-ABI call, Lock)\", \"grid\": \"%lld^3\", "
+      "\"ms_per_call\": %.3f, \"gvoxels_per_s\": %.3f, \"construct_fill_ms\": %.3f, "
+      "\"c_abi_call_pageable_ms\": %.3f, \"lock_minmax_scan_ms\": %.3f, "
+      "\"lock_with_known_extrema_ms\": %.4f, \"fast_lock_compiled_in\": %s}\n",
+      static_cast<long long>(n), whole / reps * 1e3, voxels / (whole / reps) / 1e9,
+      construct / reps * 1e3, call / reps * 1e3, lock / reps * 1e3, known / reps * 1e3,
+#ifdef VGT_B200_SDF_HAS_LOCK_WITH_KNOWN_EXTREMA
+      "true"
+#else
+      "false"
+#endif
+  );
+  return 0;
+}
+
+int main(int argc, char** argv)
 {
   if (vgt_b200_device_count() < 1)
   {
     std::printf("no usable CUDA device: %s\n", vgt_b200_version());
     return 2;
   }
+  if (argc >= 3 && std::string(argv[1]) == "--time")
+  {
+    return TimeAdapter(std::atoll(argv[2]));
+  }
   SdfTests();
   VoxelizationTest();
+  CellMapTests<float>();
+  CellMapTests<double>();
+  TransformTest();
+  FactoryTest();
   if (g_failures == 0)
   {
     std::printf("ADAPTER_TEST_OK\n");

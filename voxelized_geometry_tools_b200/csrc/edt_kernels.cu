@@ -16,6 +16,7 @@
 #include "edt_envelope_window.cuh"
 #include "edt_scan_registers.cuh"
 #include "edt_cells.cuh"
+#include "edt_transform.cuh"
 
 namespace vgt_b200
 {
@@ -1180,6 +1181,106 @@ int SdfFreeAndNamedHost(const void* h_cells, int cell_bytes, int64_t nx, int64_t
   }
   return VGT_B200_OK;
 }
+// ComputeDistanceFieldTransformInPlace on a host double field: see edt_transform.cuh.
+int TransformFieldInPlace(double* h_field, int64_t nx, int64_t ny, int64_t nz)
+{
+  const int64_t count = nx * ny * nz;
+  StreamGuard guard;
+  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&guard.stream, cudaStreamNonBlocking),
+               "cudaStreamCreate");
+  cudaStream_t stream = guard.stream;
+  StreamScratch<double> d_field;
+  StreamScratch<uint32_t> d_a;
+  StreamScratch<uint32_t> d_b;
+  StreamScratch<uint32_t> d_report;
+  VGT_CUDA_TRY(d_field.Allocate(count, stream), "field allocation");
+  VGT_CUDA_TRY(d_a.Allocate(count, stream), "packed field allocation");
+  VGT_CUDA_TRY(d_b.Allocate(count, stream), "packed field allocation");
+  VGT_CUDA_TRY(d_report.Allocate(2, stream), "ingest report allocation");
+  VGT_CUDA_TRY(cudaMemsetAsync(d_report.get(), 0, sizeof(uint32_t) * 2, stream), "report reset");
+  VGT_CUDA_TRY(cudaMemcpyAsync(d_field.get(), h_field, sizeof(double) * count,
+                               cudaMemcpyHostToDevice, stream),
+               "copy field to device");
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((count + threads - 1) / threads);
+  IngestSamplesKernel<<<blocks, threads, 0, stream>>>(d_field.get(), count, d_a.get(),
+                                                      d_report.get()); NoteKernelLaunch();
+  uint32_t report[2] = {0u, 0u};
+  VGT_CUDA_TRY(cudaMemcpyAsync(report, d_report.get(), sizeof(report), cudaMemcpyDeviceToHost,
+                               stream),
+               "copy ingest report");
+  VGT_CUDA_TRY(cudaStreamSynchronize(stream), "field ingest");
+  if (report[0] != 0u)
+  {
+    SetLastError("%u samples are neither +inf nor a non-negative integer below 2^31 - 1 (the "
+                 "device transform is exact integer arithmetic)", report[0]);
+    return VGT_B200_ERR_UNSUPPORTED;
+  }
+  const int64_t largest = static_cast<int64_t>(report[1]) + Square(nx - 1) + Square(ny - 1)
+      + Square(nz - 1);
+  if (largest > kLeanMaxInput)
+  {
+    SetLastError("samples up to %u on a %lld x %lld x %lld grid exceed the 2^29 range of the "
+                 "integer passes", report[1], static_cast<long long>(nx),
+                 static_cast<long long>(ny), static_cast<long long>(nz));
+    return VGT_B200_ERR_UNSUPPORTED;
+  }
+  // Pass order X, Y, Z as the reference (sdfgen.cpp:276-390); an axis of one voxel is skipped.
+  uint32_t* front = d_a.get();
+  uint32_t* back = d_b.get();
+  int64_t max_input = report[1];
+  if (nx > 1)
+  {
+    const int status = LaunchEnvelope<kEmitPacked>(front, back, FamilyAlongX(nx, ny, nz),
+                                                   max_input, FinalizeParams{}, nullptr, stream);
+    if (status != VGT_B200_OK)
+    {
+      return status;
+    }
+    std::swap(front, back);
+    max_input += Square(nx - 1);
+  }
+  if (ny > 1)
+  {
+    const int status = LaunchEnvelope<kEmitPacked>(front, back, FamilyAlongY(nx, ny, nz),
+                                                   max_input, FinalizeParams{}, nullptr, stream);
+    if (status != VGT_B200_OK)
+    {
+      return status;
+    }
+    std::swap(front, back);
+    max_input += Square(ny - 1);
+  }
+  if (nz > 1)
+  {
+    // [nx][ny][nz] -> [nx][nz][ny], lines along the (now strided) z axis, and back
+    const dim3 tile(32, 8);
+    TransposePlanesKernel<<<dim3(static_cast<unsigned>((nz + 31) / 32),
+                                 static_cast<unsigned>((ny + 31) / 32),
+                                 static_cast<unsigned>(nx)),
+                            tile, 0, stream>>>(front, back, static_cast<int>(ny),
+                                               static_cast<int>(nz)); NoteKernelLaunch();
+    const int status = LaunchEnvelope<kEmitPacked>(back, front, FamilyAlongY(nx, nz, ny),
+                                                   max_input, FinalizeParams{}, nullptr, stream);
+    if (status != VGT_B200_OK)
+    {
+      return status;
+    }
+    TransposePlanesKernel<<<dim3(static_cast<unsigned>((ny + 31) / 32),
+                                 static_cast<unsigned>((nz + 31) / 32),
+                                 static_cast<unsigned>(nx)),
+                            tile, 0, stream>>>(front, back, static_cast<int>(nz),
+                                               static_cast<int>(ny)); NoteKernelLaunch();
+    std::swap(front, back);
+  }
+  EmitSamplesKernel<<<blocks, threads, 0, stream>>>(front, count, d_field.get()); NoteKernelLaunch();
+  VGT_CUDA_TRY(cudaGetLastError(), "transform kernels");
+  VGT_CUDA_TRY(cudaMemcpyAsync(h_field, d_field.get(), sizeof(double) * count,
+                               cudaMemcpyDeviceToHost, stream),
+               "copy field to host");
+  VGT_CUDA_TRY(cudaStreamSynchronize(stream), "distance field transform");
+  return VGT_B200_OK;
+}
 }  // namespace
 }  // namespace edt
 }  // namespace vgt_b200
@@ -1488,6 +1589,24 @@ int vgt_b200_sdf_free_and_named_f64(
   return SdfFreeAndNamedHost<kEmitDouble>(cells, cell_bytes, nx, ny, nz, resolution,
                                           unknown_is_filled, add_virtual_border, device, sdf_out,
                                           out_min, out_max);
+}
+
+int vgt_b200_edt_transform_inplace_f64(double* field, int64_t nx, int64_t ny, int64_t nz,
+                                       int device)
+{
+  const int check = CheckSdfArguments(field, field, nx, ny, nz, 1.0);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  if (nz > 65535 * 32LL || ny > 65535 * 32LL || nx > 65535)
+  {
+    return FailInvalid("grid too large for the transpose launch");
+  }
+  ScopedDevice scoped(device);
+  VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+  KeepPoolMemory(device);
+  return TransformFieldInPlace(field, nx, ny, nz);
 }
 
 int vgt_b200_edt_sq_i32(

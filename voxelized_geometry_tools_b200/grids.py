@@ -492,3 +492,17 @@ def ComputeSquaredDistanceFields(occupancy: np.ndarray, unknown_is_filled: bool 
         to_free.ctypes.data)
     _capi.check(code)
     return to_filled, to_free
+
+
+def ComputeDistanceFieldTransformInPlace(field: np.ndarray, device: int = 0) -> np.ndarray:
+    """internal::ComputeDistanceFieldTransformInPlace (signed_distance_field_generation.hpp:34-37)
+    on a float64 [x, y, z] field of +inf / non-negative integer samples, in place on the device
+    (vgt_b200_edt_transform_inplace_f64). Raises NotImplementedError for samples the exact
+    integer passes cannot take; the field is then untouched."""
+    _capi.require_device(device)
+    if field.dtype != np.float64 or field.ndim != 3 or not field.flags.c_contiguous:
+        raise ValueError("field must be a C-contiguous float64 array indexed [x, y, z]")
+    code = _capi.library().vgt_b200_edt_transform_inplace_f64(field.ctypes.data, *field.shape,
+                                                              device)
+    _capi.check(code)
+    return field
