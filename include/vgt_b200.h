@@ -250,6 +250,63 @@ VGT_B200_API int vgt_b200_edt_final_pass_f32_dev(
     float* d_min_max, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Signed distance field queries (the consumers right after the path: planners keep the SDF on
+ * the device and ask it about many points at once)
+ * ------------------------------------------------------------------------------------------- */
+
+/* A device-resident SignedDistanceField<float>: the grid vgt_b200_sdf_f32_dev wrote plus the
+ * pose VoxelGridBase keeps (OriginTransform, column-major 4x4 as Eigen's .data() gives it). */
+typedef struct vgt_b200_sdf_view
+{
+  const float* d_sdf; /* device float[nx*ny*nz] */
+  int64_t nx;
+  int64_t ny;
+  int64_t nz;
+  double resolution;
+  double origin_transform[16];
+} vgt_b200_sdf_view;
+
+/* d_valid[i] after a query: */
+#define VGT_B200_QUERY_NO_VALUE 0 /* the reference returns an empty query / ProjectedPosition */
+#define VGT_B200_QUERY_VALUE 1
+#define VGT_B200_QUERY_THROWS 2   /* the reference throws std::runtime_error for this point */
+
+/* All four: d_points_xyz = device double[num_points*3], WORLD frame; one thread per point;
+ * asynchronous on `stream`; outputs are 0 where d_valid is not VGT_B200_QUERY_VALUE.
+ *
+ * vgt_b200_sdf_estimate_distance_dev replaces SignedDistanceField::EstimateLocationDistance4d
+ *   (include/.../signed_distance_field.hpp:823-838 with the helpers at :259-357): trilinear
+ *   interpolation of the half-cell-corrected distances of the 8 surrounding cell centres.
+ * vgt_b200_sdf_coarse_gradient_dev replaces GetLocationCoarseGradient4d (:887-900, :903-1025):
+ *   central differences of the neighbouring cells, one-sided at the grid faces when
+ *   enable_edge_gradients, rotated into the world frame; d_gradients_xyz = double[num_points*3].
+ * vgt_b200_sdf_fine_gradient_dev replaces GetLocationFineGradient (:1051-1092, :213-255):
+ *   differences of seven distance estimates at +/- |nominal_window_size|.
+ * vgt_b200_sdf_project_out_of_collision_dev replaces
+ *   ProjectLocationOutOfCollisionToMinimumDistance4d (:1159-1203): gradient steps of at most
+ *   resolution * stepsize_multiplier until the estimate exceeds minimum_distance. The
+ *   reference's loop is unbounded; a point still in collision after max_steps steps reports
+ *   VGT_B200_QUERY_THROWS. */
+VGT_B200_API int vgt_b200_sdf_estimate_distance_dev(
+    const vgt_b200_sdf_view* sdf, const double* d_points_xyz, int64_t num_points, int device,
+    double* d_distances, uint8_t* d_valid, void* stream);
+
+VGT_B200_API int vgt_b200_sdf_coarse_gradient_dev(
+    const vgt_b200_sdf_view* sdf, const double* d_points_xyz, int64_t num_points,
+    int enable_edge_gradients, int device, double* d_gradients_xyz, uint8_t* d_valid,
+    void* stream);
+
+VGT_B200_API int vgt_b200_sdf_fine_gradient_dev(
+    const vgt_b200_sdf_view* sdf, const double* d_points_xyz, int64_t num_points,
+    double nominal_window_size, int device, double* d_gradients_xyz, uint8_t* d_valid,
+    void* stream);
+
+VGT_B200_API int vgt_b200_sdf_project_out_of_collision_dev(
+    const vgt_b200_sdf_view* sdf, const double* d_points_xyz, int64_t num_points,
+    double minimum_distance, double stepsize_multiplier, int64_t max_steps, int device,
+    double* d_projected_xyz, uint8_t* d_valid, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Point cloud voxelization
  * ------------------------------------------------------------------------------------------- */
 

@@ -34,6 +34,12 @@ class Cloud(ctypes.Structure):
                 ("max_range", _dbl)]
 
 
+class SdfView(ctypes.Structure):
+    """struct vgt_b200_sdf_view."""
+    _fields_ = [("d_sdf", ctypes.c_void_p), ("nx", _i64), ("ny", _i64), ("nz", _i64),
+                ("resolution", _dbl), ("origin_transform", _dbl * 16)]
+
+
 class FilterOptions(ctypes.Structure):
     """struct vgt_b200_filter_options."""
     _fields_ = [("percent_seen_free", _dbl), ("outlier_points_threshold", ctypes.c_int32),
@@ -79,6 +85,14 @@ SIGNATURES = {
                                                      _int, _vp]),
     "vgt_b200_edt_final_pass_f32_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _dbl, _int, _int,
                                                _vp, _vp, _vp]),
+    "vgt_b200_sdf_estimate_distance_dev": (_int, [ctypes.POINTER(SdfView), _vp, _i64, _int, _vp,
+                                                  _vp, _vp]),
+    "vgt_b200_sdf_coarse_gradient_dev": (_int, [ctypes.POINTER(SdfView), _vp, _i64, _int, _int,
+                                                _vp, _vp, _vp]),
+    "vgt_b200_sdf_fine_gradient_dev": (_int, [ctypes.POINTER(SdfView), _vp, _i64, _dbl, _int, _vp,
+                                              _vp, _vp]),
+    "vgt_b200_sdf_project_out_of_collision_dev": (_int, [ctypes.POINTER(SdfView), _vp, _i64, _dbl,
+                                                         _dbl, _i64, _int, _vp, _vp, _vp]),
     "vgt_b200_voxelize_f64": (_int, [_vp, _i64, _i64, _i64, _dbl, ctypes.POINTER(Cloud),
                                      ctypes.c_int32, ctypes.POINTER(FilterOptions), _int, _vp,
                                      _vp, _f64p]),

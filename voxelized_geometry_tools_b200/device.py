@@ -185,3 +185,77 @@ def filter_grids(counts: torch.Tensor, occupancy: torch.Tensor,
         device.index or 0, occupancy.data_ptr(), _stream_handle(device))
     _capi.check(code)
     return occupancy
+
+
+# --------------------------------------------------------------------------------------------------
+# SignedDistanceField queries on a device-resident SDF
+# --------------------------------------------------------------------------------------------------
+QUERY_NO_VALUE, QUERY_VALUE, QUERY_THROWS = 0, 1, 2
+
+
+class DeviceSignedDistanceField:
+    """A SignedDistanceField<float> that stays on the GPU: the float grid [nx, ny, nz] plus
+    resolution and origin transform. The batched queries mirror the reference's per-point
+    members (signed_distance_field.hpp:808-1203); points are float64 [N, 3] CUDA tensors in the
+    WORLD frame. Every query returns (values, valid uint8): 1 = value, 0 = the reference returns
+    an empty query, 2 = the reference throws for that point."""
+
+    def __init__(self, sdf: torch.Tensor, resolution: float, origin_transform=None):
+        _require_cuda(sdf, torch.float32, "sdf")
+        if sdf.dim() != 3:
+            raise ValueError("sdf must be indexed [x, y, z]")
+        self.sdf = sdf
+        self.resolution = float(resolution)
+        self.origin_transform = np.eye(4) if origin_transform is None else \
+            np.asarray(origin_transform, dtype=np.float64).reshape(4, 4)
+        self._view = _capi.SdfView()
+        self._view.d_sdf = sdf.data_ptr()
+        self._view.nx, self._view.ny, self._view.nz = (int(d) for d in sdf.shape)
+        self._view.resolution = self.resolution
+        column_major = np.ascontiguousarray(self.origin_transform.T).reshape(-1)
+        for i in range(16):
+            self._view.origin_transform[i] = float(column_major[i])
+
+    def _points(self, points: torch.Tensor) -> torch.Tensor:
+        _require_cuda(points, torch.float64, "points")
+        if points.dim() != 2 or points.shape[1] != 3:
+            raise ValueError("points must be [N, 3]")
+        if points.device != self.sdf.device:
+            raise ValueError("points and sdf must live on the same device")
+        return points
+
+    def _launch(self, name, points, width, *middle):
+        points = self._points(points)
+        device = self.sdf.device
+        count = points.shape[0]
+        shape = (count,) if width == 1 else (count, width)
+        values = torch.empty(shape, dtype=torch.float64, device=device)
+        valid = torch.empty(count, dtype=torch.uint8, device=device)
+        function = getattr(_capi.library(), name)
+        code = function(ctypes.byref(self._view), points.data_ptr(), count, *middle,
+                        device.index or 0, values.data_ptr(), valid.data_ptr(),
+                        _stream_handle(device))
+        _capi.check(code)
+        return values, valid
+
+    def EstimateLocationDistance(self, points: torch.Tensor):
+        return self._launch("vgt_b200_sdf_estimate_distance_dev", points, 1)
+
+    def GetLocationCoarseGradient(self, points: torch.Tensor, enable_edge_gradients=False):
+        return self._launch("vgt_b200_sdf_coarse_gradient_dev", points, 3,
+                            int(bool(enable_edge_gradients)))
+
+    def GetLocationFineGradient(self, points: torch.Tensor, nominal_window_size: float):
+        return self._launch("vgt_b200_sdf_fine_gradient_dev", points, 3,
+                            float(nominal_window_size))
+
+    def ProjectLocationOutOfCollisionToMinimumDistance(
+            self, points: torch.Tensor, minimum_distance: float = 0.0,
+            stepsize_multiplier: float = 1.0 / 10.0, max_steps: int = 1_000_000):
+        return self._launch("vgt_b200_sdf_project_out_of_collision_dev", points, 3,
+                            float(minimum_distance), float(stepsize_multiplier), int(max_steps))
+
+    def ProjectLocationOutOfCollision(self, points: torch.Tensor,
+                                      stepsize_multiplier: float = 1.0 / 10.0):
+        return self.ProjectLocationOutOfCollisionToMinimumDistance(points, 0.0,
+                                                                   stepsize_multiplier)
