@@ -320,6 +320,18 @@ typedef struct vgt_b200_cloud
   double max_range;         /* PointCloudWrapper::MaxRange(), may be +inf */
 } vgt_b200_cloud;
 
+/* The same for a cloud whose points are float32 (what a sensor_msgs/PointCloud2 carries; the
+ * reference's PointCloud2Wrapper widens them per point,
+ * include/.../pointcloud_voxelization_ros_interface.hpp:35-97): 12 bytes per point cross the bus
+ * and are widened on the device. Counts are identical to the double entry on the same values. */
+typedef struct vgt_b200_cloud_f32
+{
+  const float* points_xyz; /* num_points * 3 floats, cloud frame */
+  int64_t num_points;
+  double x_gc[16];
+  double max_range;
+} vgt_b200_cloud_f32;
+
 /* PointCloudVoxelizationFilterOptions (pointcloud_voxelization_interface.hpp:20-92). */
 typedef struct vgt_b200_filter_options
 {
@@ -342,6 +354,12 @@ VGT_B200_API int vgt_b200_voxelize_f64(
     const vgt_b200_cloud* clouds, int32_t num_clouds, const vgt_b200_filter_options* filter,
     int device, float* out_occupancy, int32_t* out_counts, double* out_seconds);
 
+/* vgt_b200_voxelize_f64 for float32 clouds (see vgt_b200_cloud_f32). */
+VGT_B200_API int vgt_b200_voxelize_f32(
+    const float* static_occupancy, int64_t nx, int64_t ny, int64_t nz, double voxel_size,
+    const vgt_b200_cloud_f32* clouds, int32_t num_clouds, const vgt_b200_filter_options* filter,
+    int device, float* out_occupancy, int32_t* out_counts, double* out_seconds);
+
 /* Device-resident pieces (asynchronous on `stream`).
  * vgt_b200_raycast_f64_dev accumulates one cloud into d_counts (int32[V][2], caller zeroes it).
  *   Replaces CpuPointCloudVoxelizer::DoRaycastPointCloud (cpu_pcv.cpp:167-206) and, positionally,
@@ -352,6 +370,12 @@ VGT_B200_API int vgt_b200_voxelize_f64(
  */
 VGT_B200_API int vgt_b200_raycast_f64_dev(
     const double* d_points_xyz, int64_t num_points, const double* x_gc /* host, 16 */,
+    double max_range, int64_t nx, int64_t ny, int64_t nz, double voxel_size, int device,
+    int32_t* d_counts, void* stream);
+
+/* vgt_b200_raycast_f64_dev for device float[num_points*3] points. */
+VGT_B200_API int vgt_b200_raycast_f32_dev(
+    const float* d_points_xyz, int64_t num_points, const double* x_gc /* host, 16 */,
     double max_range, int64_t nx, int64_t ny, int64_t nz, double voxel_size, int device,
     int32_t* d_counts, void* stream);
 

@@ -160,3 +160,24 @@ def test_counts_equal_the_compiled_reference(shared_library):
     posed = reference_oracle.voxelize_posed(scene["static_occupancy"], scene["origin_transform"],
                                             scene["clouds"], scene["voxel_size"], 0.9, 2, 2)
     np.testing.assert_array_equal(got.GetImmutableRawData(), posed)
+
+
+def test_float32_clouds_give_the_counts_of_the_same_values_as_doubles(shared_library, oracle):
+    # vgt_b200_voxelize_f32: PointCloud2-style float32 points, widened on the device
+    scene = synthetic.depth_camera_scene(64, 0.08, 160, 120, max_range=5.0)
+    packed = {"static": scene["static_occupancy"], "x_wg": scene["origin_transform"],
+              "voxel_size": scene["voxel_size"]}
+    rounded = [(p.astype(np.float32), x, r) for p, x, r in scene["clouds"]]
+    static, as_double = build(packed, [(p.astype(np.float64), x, r) for p, x, r in rounded])
+    as_float = [vgt.Float32PointCloudWrapper(p, x, r) for p, x, r in rounded]
+    options = vgt.PointCloudVoxelizationFilterOptions(0.9, 1, 1)
+    voxelizer = vgt.B200PointCloudVoxelizer()
+    got_f, counts_f = voxelizer.VoxelizePointCloudsWithCounts(static, options, as_float)
+    got_d, counts_d = voxelizer.VoxelizePointCloudsWithCounts(static, options, as_double)
+    assert counts_f.sum() > 100000
+    np.testing.assert_array_equal(counts_f, counts_d)
+    np.testing.assert_array_equal(got_f.GetImmutableRawData(), got_d.GetImmutableRawData())
+    want, want_counts = oracle_voxelize(
+        oracle, packed, [(p.astype(np.float64), x, r) for p, x, r in rounded], (0.9, 1, 1))
+    np.testing.assert_array_equal(counts_f, want_counts)
+    np.testing.assert_array_equal(got_f.GetImmutableRawData(), want)

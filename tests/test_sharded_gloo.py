@@ -124,3 +124,71 @@ def test_world_size_one_needs_no_process_group(oracle):
     want, (lo, hi) = oracle.sdf(occupancy, 0.5)
     np.testing.assert_array_equal(sdf.numpy(), want)
     assert (float(min_max[0]), float(min_max[1])) == (lo, hi)
+
+
+# --------------------------------------------------------------------------------------------------
+# Sharded voxelizer: rays split over the ranks, counters summed into x-slabs, slab-local filter
+# --------------------------------------------------------------------------------------------------
+def _cpu_voxelizer_stages(oracle):
+    from voxelized_geometry_tools_b200.sharded import VoxelizerStages
+
+    def raycast(points, x_gc, max_range, counts, voxel_size):
+        grid = counts.numpy()
+        oracle.raycast_cloud(points.numpy(), x_gc, max_range, grid.shape[:3], voxel_size,
+                             counts=grid)
+
+    def filter_slab(counts, occupancy, options):
+        filtered = oracle.filter_grids(counts.numpy(), occupancy.numpy(), *options)
+        occupancy.copy_(torch.from_numpy(filtered))
+
+    return VoxelizerStages(raycast, filter_slab)
+
+
+def _voxelizer_worker(rank, world, port, grid_n, result_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle
+        from voxelized_geometry_tools_b200 import synthetic
+        from voxelized_geometry_tools_b200.grids import compose_rigid, inverse_rigid
+        from voxelized_geometry_tools_b200.sharded import (ShardedPointCloudVoxelizer,
+                                                           ShardedSignedDistanceField)
+        scene = synthetic.depth_camera_scene(grid_n, 5.12 / grid_n, 48, 36, max_range=5.0)
+        x_gw = inverse_rigid(scene["origin_transform"])
+        clouds = [(p, compose_rigid(x_gw, x), r) for p, x, r in scene["clouds"]]
+        options = (0.9, 1, 2)
+        dims = scene["static_occupancy"].shape
+        voxelizer = ShardedPointCloudVoxelizer(dims, scene["voxel_size"],
+                                               stages=_cpu_voxelizer_stages(oracle))
+        x0, x1 = voxelizer.x_range
+        static_slab = torch.from_numpy(scene["static_occupancy"][x0:x1].copy())
+        slab = voxelizer.voxelize(static_slab, [(torch.from_numpy(p), x, r) for p, x, r in clouds],
+                                  options, keep_counts=True)
+        want, want_counts = oracle.voxelize(scene["static_occupancy"], clouds,
+                                            scene["voxel_size"], *options)
+        np.testing.assert_array_equal(slab.numpy(), want[x0:x1])
+        np.testing.assert_array_equal(voxelizer.last_counts.numpy(), want_counts[:, x0:x1])
+        # no clouds at all: everything that is not filled becomes unknown
+        empty = voxelizer.voxelize(static_slab, [], options)
+        want_empty, _ = oracle.voxelize(scene["static_occupancy"], [], scene["voxel_size"],
+                                        *options)
+        np.testing.assert_array_equal(empty.numpy(), want_empty[x0:x1])
+        # ... and straight into the sharded SDF (the slab is what it starts from)
+        plan = ShardedSignedDistanceField(dims, stages=_cpu_stages(oracle))
+        sdf_slab, _ = plan.extract(slab, scene["voxel_size"])
+        full = plan.gather_to_host(sdf_slab)
+        if rank == 0:
+            want_sdf, _ = oracle.sdf(want, scene["voxel_size"])
+            np.testing.assert_array_equal(full.numpy(), want_sdf)
+            Path(result_path).write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,grid_n", [(2, 16), (3, 13)])
+def test_sharded_voxelizer_matches_single_process(tmp_path, oracle, world, grid_n):
+    result = tmp_path / "result.txt"
+    mp.spawn(_voxelizer_worker, args=(world, _free_port(), grid_n, str(result)), nprocs=world,
+             join=True)
+    assert result.read_text() == "ok"

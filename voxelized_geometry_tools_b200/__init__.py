@@ -24,6 +24,7 @@ from .grids import (  # noqa: F401
 )
 from .pointcloud_voxelization import (  # noqa: F401
     B200PointCloudVoxelizer,
+    Float32PointCloudWrapper,
     GetAvailableBackends,
     MakePointCloudVoxelizer,
     PointCloudVoxelizationFilterOptions,

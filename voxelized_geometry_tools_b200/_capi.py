@@ -34,6 +34,12 @@ class Cloud(ctypes.Structure):
                 ("max_range", _dbl)]
 
 
+class CloudF32(ctypes.Structure):
+    """struct vgt_b200_cloud_f32."""
+    _fields_ = [("points_xyz", _f32p), ("num_points", _i64), ("x_gc", _dbl * 16),
+                ("max_range", _dbl)]
+
+
 class SdfView(ctypes.Structure):
     """struct vgt_b200_sdf_view."""
     _fields_ = [("d_sdf", ctypes.c_void_p), ("nx", _i64), ("ny", _i64), ("nz", _i64),
@@ -96,6 +102,11 @@ SIGNATURES = {
     "vgt_b200_voxelize_f64": (_int, [_vp, _i64, _i64, _i64, _dbl, ctypes.POINTER(Cloud),
                                      ctypes.c_int32, ctypes.POINTER(FilterOptions), _int, _vp,
                                      _vp, _f64p]),
+    "vgt_b200_voxelize_f32": (_int, [_vp, _i64, _i64, _i64, _dbl, ctypes.POINTER(CloudF32),
+                                     ctypes.c_int32, ctypes.POINTER(FilterOptions), _int, _vp,
+                                     _vp, _f64p]),
+    "vgt_b200_raycast_f32_dev": (_int, [_vp, _i64, _f64p, _dbl, _i64, _i64, _i64, _dbl, _int, _vp,
+                                        _vp]),
     "vgt_b200_raycast_f64_dev": (_int, [_vp, _i64, _f64p, _dbl, _i64, _i64, _i64, _dbl, _int, _vp,
                                         _vp]),
     "vgt_b200_filter_dev": (_int, [_vp, ctypes.c_int32, _i64, ctypes.POINTER(FilterOptions), _int,

@@ -772,6 +772,20 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
   uint32_t* const d_front = reinterpret_cast<uint32_t*>(d_out.get());
   // pageable caller buffers go through pinned slots filled / drained by several host threads
   StagedTransfer transfer;
+  // Declared after the buffers and the staging object, so it runs first on every exit path
+  // (early error returns included): nothing of this call is still queued when the pinned slots
+  // go back to the process-wide cache and the scratch to the pool.
+  struct DrainOnExit
+  {
+    cudaStream_t streams[3];
+    ~DrainOnExit()
+    {
+      for (cudaStream_t stream : streams)
+      {
+        cudaStreamSynchronize(stream);
+      }
+    }
+  } drain{{copy_in.stream, compute.stream, copy_out.stream}};
   const int in_chunks = static_cast<int>(nx < kPipelineChunks ? nx : kPipelineChunks);
   EventGuard arrived[kPipelineChunks];
   int status = VGT_B200_OK;
@@ -836,8 +850,6 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
   if (status == VGT_B200_OK)
   {
     DecodeMinMaxKernel<Out, Key><<<1, 1, 0, compute.stream>>>(keys.get(), d_min_max.get()); NoteKernelLaunch();
-    cudaMemcpyAsync(min_max, d_min_max.get(), sizeof(Out) * 2, cudaMemcpyDeviceToHost,
-                    compute.stream);
   }
   for (int c = 0; c < out_chunks && status == VGT_B200_OK; c++)
   {
@@ -850,6 +862,13 @@ int SdfFromHostPipelined(const In* h_in, int64_t nx, int64_t ny, int64_t nz, dou
                                  sizeof(Out) * plane, sizeof(Out) * (y1 - y0) * nz,
                                  static_cast<size_t>(nx), copy_out.stream),
                  "copy SDF slab to host");
+  }
+  if (status == VGT_B200_OK)
+  {
+    // (after the copy-out loop: a device-to-host copy into pageable memory blocks the host
+    // until the compute stream has drained, which would serialise the slab copies behind it)
+    cudaMemcpyAsync(min_max, d_min_max.get(), sizeof(Out) * 2, cudaMemcpyDeviceToHost,
+                    compute.stream);
   }
   const cudaError_t sync_in = cudaStreamSynchronize(copy_in.stream);
   const cudaError_t sync_compute = cudaStreamSynchronize(compute.stream);

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_transfer.cuh"
 
 namespace vgt_b200
 {
@@ -83,8 +84,13 @@ __device__ __forceinline__ double FirstBoundaryT(double point_axis, double ray_a
 
 // One thread per point: the literal double-precision DDA of
 // CpuPointCloudVoxelizer::DoRaycastSinglePoint (cpu_pcv.cpp:208-436).
+// Scalar = double, or float for clouds that arrive as float32 (the reference's ROS wrapper,
+// pointcloud_voxelization_ros_interface.hpp:35-97, hands PointCloud2 floats over through
+// CopyPointLocationIntoDoublePtr, i.e. widened to double exactly): 12 instead of 24 bytes per
+// point over the bus, the widening happens here.
+template <typename Scalar>
 __global__ void __launch_bounds__(128) RaycastCloudKernel(
-    const double* __restrict__ points, int64_t num_points, CloudPose pose, double max_range,
+    const Scalar* __restrict__ points, int64_t num_points, CloudPose pose, double max_range,
     GridFrame grid, int32_t* counts)
 {
   const int64_t index = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -92,9 +98,9 @@ __global__ void __launch_bounds__(128) RaycastCloudKernel(
   {
     return;
   }
-  const double cx = points[3 * index + 0];
-  const double cy = points[3 * index + 1];
-  const double cz = points[3 * index + 2];
+  const double cx = static_cast<double>(points[3 * index + 0]);
+  const double cy = static_cast<double>(points[3 * index + 1]);
+  const double cz = static_cast<double>(points[3 * index + 2]);
   // Skip NaN / infinite points (cpu_pcv.cpp:191-192).
   if (!(isfinite(cx) && isfinite(cy) && isfinite(cz)))
   {
@@ -346,7 +352,8 @@ GridFrame MakeFrame(int64_t nx, int64_t ny, int64_t nz, double voxel_size)
   return g;
 }
 
-int LaunchRaycast(const double* d_points, int64_t num_points, const double* x_gc,
+template <typename Scalar>
+int LaunchRaycast(const Scalar* d_points, int64_t num_points, const double* x_gc,
                   double max_range, const GridFrame& grid, int32_t* d_counts, cudaStream_t stream)
 {
   if (num_points <= 0)
@@ -360,7 +367,7 @@ int LaunchRaycast(const double* d_points, int64_t num_points, const double* x_gc
   }
   const int threads = 128;
   const int64_t blocks = (num_points + threads - 1) / threads;
-  RaycastCloudKernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+  RaycastCloudKernel<Scalar><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
       d_points, num_points, pose, max_range, grid, d_counts); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "RaycastCloudKernel launch");
   return VGT_B200_OK;
@@ -387,6 +394,217 @@ int CheckGrid(int64_t nx, int64_t ny, int64_t nz, double voxel_size)
   if (!(voxel_size > 0.0) || !std::isfinite(voxel_size))
   {
     return FailInvalid("voxel_size must be positive and finite");
+  }
+  return VGT_B200_OK;
+}
+template <typename Scalar>
+struct CloudOf;
+template <>
+struct CloudOf<double>
+{
+  using Type = vgt_b200_cloud;
+};
+template <>
+struct CloudOf<float>
+{
+  using Type = vgt_b200_cloud_f32;
+};
+
+struct OwnedStream
+{
+  cudaStream_t stream = nullptr;
+  ~OwnedStream()
+  {
+    if (stream != nullptr)
+    {
+      // (nothing of this call may still be queued when its buffers go back to the pool)
+      cudaStreamSynchronize(stream);
+      cudaStreamDestroy(stream);
+    }
+  }
+};
+
+struct OwnedEvent
+{
+  cudaEvent_t event = nullptr;
+  ~OwnedEvent()
+  {
+    if (event != nullptr)
+    {
+      cudaEventDestroy(event);
+    }
+  }
+};
+
+// <Backend>PointCloudVoxelizer::DoVoxelizePointClouds on host buffers. Two streams: the static
+// map travels on the copy stream while the clouds are raycast on the compute stream; the points
+// of cloud c + 1 are uploaded (into the other of two buffers) while cloud c is raycast; pageable
+// buffers go through the pinned staging ring (host_transfer.cuh). The two durations of
+// VoxelizerRuntime come from CUDA events, so the host never waits in the middle of the call.
+template <typename Scalar>
+int VoxelizeFromHost(
+    const float* static_occupancy, int64_t nx, int64_t ny, int64_t nz, double voxel_size,
+    const typename CloudOf<Scalar>::Type* clouds, int32_t num_clouds,
+    const vgt_b200_filter_options* filter, int device, float* out_occupancy, int32_t* out_counts,
+    double* out_seconds)
+{
+  int check = CheckGrid(nx, ny, nz, voxel_size);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  check = CheckFilter(filter);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  if (static_occupancy == nullptr || out_occupancy == nullptr || num_clouds < 0
+      || (num_clouds > 0 && clouds == nullptr))
+  {
+    return FailInvalid("null pointer or negative cloud count");
+  }
+  for (int32_t c = 0; c < num_clouds; c++)
+  {
+    if (clouds[c].num_points < 0 || (clouds[c].num_points > 0 && clouds[c].points_xyz == nullptr))
+    {
+      // pcv_if.hpp:281-289 rejects null clouds with invalid_argument.
+      return FailInvalid("pointclouds[%d] is null", c);
+    }
+  }
+  ScopedDevice scoped(device);
+  VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+  KeepPoolMemory(device);
+  const int64_t num_voxels = nx * ny * nz;
+  const int64_t num_grids = num_clouds > 0 ? num_clouds : 1;
+  const GridFrame grid = MakeFrame(nx, ny, nz, voxel_size);
+  OwnedStream compute, copy;
+  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&compute.stream, cudaStreamNonBlocking), "stream");
+  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&copy.stream, cudaStreamNonBlocking), "stream");
+  OwnedEvent started, raycast_done, filter_done, map_arrived, allocated;
+  VGT_CUDA_TRY(cudaEventCreate(&started.event), "event");
+  VGT_CUDA_TRY(cudaEventCreate(&raycast_done.event), "event");
+  VGT_CUDA_TRY(cudaEventCreate(&filter_done.event), "event");
+  VGT_CUDA_TRY(cudaEventCreateWithFlags(&map_arrived.event, cudaEventDisableTiming), "event");
+  VGT_CUDA_TRY(cudaEventCreateWithFlags(&allocated.event, cudaEventDisableTiming), "event");
+  OwnedEvent buffer_free[2];
+  vgt_b200::StagedTransfer points_transfer;
+  vgt_b200::StagedTransfer map_transfer;
+
+  StreamScratch<int32_t> d_counts;
+  StreamScratch<float> d_occupancy;
+  StreamScratch<Scalar> d_points[2];
+  VGT_CUDA_TRY(d_counts.Allocate(2 * num_voxels * num_grids, compute.stream),
+               "tracking grid allocation");
+  VGT_CUDA_TRY(d_occupancy.Allocate(num_voxels, compute.stream), "occupancy allocation");
+  int64_t max_points = 0;
+  for (int32_t c = 0; c < num_clouds; c++)
+  {
+    max_points = (clouds[c].num_points > max_points) ? clouds[c].num_points : max_points;
+  }
+  if (max_points > 0)
+  {
+    VGT_CUDA_TRY(d_points[0].Allocate(3 * max_points, compute.stream), "points allocation");
+    VGT_CUDA_TRY(d_points[1].Allocate(3 * max_points, compute.stream), "points allocation");
+  }
+  // Declared after the buffers and the staging objects, so it runs first on every exit path:
+  // nothing of this call is still queued when they go back to the pool / the slot cache.
+  struct DrainOnExit
+  {
+    cudaStream_t a;
+    cudaStream_t b;
+    ~DrainOnExit()
+    {
+      cudaStreamSynchronize(a);
+      cudaStreamSynchronize(b);
+    }
+  } drain{compute.stream, copy.stream};
+  VGT_CUDA_TRY(cudaEventRecord(allocated.event, compute.stream), "event record");
+  VGT_CUDA_TRY(cudaStreamWaitEvent(copy.stream, allocated.event, 0), "stream wait");
+  VGT_CUDA_TRY(cudaEventRecord(started.event, compute.stream), "event record");
+  VGT_CUDA_TRY(cudaMemsetAsync(d_counts.get(), 0, sizeof(int32_t) * 2 * num_voxels * num_grids,
+                               compute.stream),
+               "zero tracking grids");
+  // the static map, on its own stream: only the filter needs it
+  {
+    const size_t bytes = sizeof(float) * static_cast<size_t>(num_voxels);
+    VGT_CUDA_TRY(map_transfer.ToDevice(reinterpret_cast<char*>(d_occupancy.get()), bytes,
+                                       reinterpret_cast<const char*>(static_occupancy), bytes,
+                                       bytes, 1, copy.stream),
+                 "copy occupancy to device");
+    VGT_CUDA_TRY(cudaEventRecord(map_arrived.event, copy.stream), "event record");
+  }
+  // clouds: upload into buffer c % 2 on the copy stream, raycast on the compute stream
+  OwnedEvent uploaded[2];
+  for (int b = 0; b < 2; b++)
+  {
+    VGT_CUDA_TRY(cudaEventCreateWithFlags(&uploaded[b].event, cudaEventDisableTiming), "event");
+    VGT_CUDA_TRY(cudaEventCreateWithFlags(&buffer_free[b].event, cudaEventDisableTiming),
+                 "event");
+  }
+  int used = 0;
+  for (int32_t c = 0; c < num_clouds; c++)
+  {
+    if (clouds[c].num_points == 0)
+    {
+      continue;
+    }
+    const int b = used & 1;
+    if (used >= 2)
+    {
+      // the raycast that last read this buffer must have finished
+      VGT_CUDA_TRY(cudaStreamWaitEvent(copy.stream, buffer_free[b].event, 0), "stream wait");
+    }
+    const size_t bytes = sizeof(Scalar) * 3 * static_cast<size_t>(clouds[c].num_points);
+    VGT_CUDA_TRY(points_transfer.ToDevice(reinterpret_cast<char*>(d_points[b].get()), bytes,
+                                          reinterpret_cast<const char*>(clouds[c].points_xyz),
+                                          bytes, bytes, 1, copy.stream),
+                 "copy points to device");
+    VGT_CUDA_TRY(cudaEventRecord(uploaded[b].event, copy.stream), "event record");
+    VGT_CUDA_TRY(cudaStreamWaitEvent(compute.stream, uploaded[b].event, 0), "stream wait");
+    const int status = LaunchRaycast<Scalar>(d_points[b].get(), clouds[c].num_points,
+                                             clouds[c].x_gc, clouds[c].max_range, grid,
+                                             d_counts.get() + 2 * num_voxels * c, compute.stream);
+    if (status != VGT_B200_OK)
+    {
+      return status;
+    }
+    VGT_CUDA_TRY(cudaEventRecord(buffer_free[b].event, compute.stream), "event record");
+    used++;
+  }
+  VGT_CUDA_TRY(cudaEventRecord(raycast_done.event, compute.stream), "event record");
+  VGT_CUDA_TRY(cudaStreamWaitEvent(compute.stream, map_arrived.event, 0), "stream wait");
+  const int status = LaunchFilter(d_counts.get(), num_clouds, num_voxels, *filter,
+                                  d_occupancy.get(), compute.stream);
+  if (status != VGT_B200_OK)
+  {
+    return status;
+  }
+  VGT_CUDA_TRY(cudaEventRecord(filter_done.event, compute.stream), "event record");
+  {
+    const size_t bytes = sizeof(float) * static_cast<size_t>(num_voxels);
+    VGT_CUDA_TRY(map_transfer.ToHost(reinterpret_cast<char*>(out_occupancy), bytes,
+                                     reinterpret_cast<const char*>(d_occupancy.get()), bytes,
+                                     bytes, 1, compute.stream),
+                 "copy occupancy to host");
+  }
+  if (out_counts != nullptr && num_clouds > 0)
+  {
+    const size_t bytes = sizeof(int32_t) * 2 * static_cast<size_t>(num_voxels * num_clouds);
+    VGT_CUDA_TRY(map_transfer.ToHost(reinterpret_cast<char*>(out_counts), bytes,
+                                     reinterpret_cast<const char*>(d_counts.get()), bytes, bytes,
+                                     1, compute.stream),
+                 "copy counts to host");
+  }
+  VGT_CUDA_TRY(cudaStreamSynchronize(copy.stream), "uploads");
+  VGT_CUDA_TRY(cudaStreamSynchronize(compute.stream), "voxelization");
+  if (out_seconds != nullptr)
+  {
+    float raycast_ms = 0.0f;
+    float filter_ms = 0.0f;
+    cudaEventElapsedTime(&raycast_ms, started.event, raycast_done.event);
+    cudaEventElapsedTime(&filter_ms, raycast_done.event, filter_done.event);
+    out_seconds[0] = static_cast<double>(raycast_ms) * 1e-3;
+    out_seconds[1] = static_cast<double>(filter_ms) * 1e-3;
   }
   return VGT_B200_OK;
 }
@@ -441,114 +659,43 @@ int vgt_b200_filter_dev(
                       static_cast<cudaStream_t>(stream));
 }
 
+int vgt_b200_raycast_f32_dev(
+    const float* d_points_xyz, int64_t num_points, const double* x_gc, double max_range,
+    int64_t nx, int64_t ny, int64_t nz, double voxel_size, int device, int32_t* d_counts,
+    void* stream)
+{
+  const int check = CheckGrid(nx, ny, nz, voxel_size);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  if (x_gc == nullptr || d_counts == nullptr || (num_points > 0 && d_points_xyz == nullptr)
+      || num_points < 0)
+  {
+    return FailInvalid("null pointer or negative point count");
+  }
+  ScopedDevice scoped(device);
+  VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+  return LaunchRaycast(d_points_xyz, num_points, x_gc, max_range,
+                       MakeFrame(nx, ny, nz, voxel_size), d_counts,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int vgt_b200_voxelize_f64(
     const float* static_occupancy, int64_t nx, int64_t ny, int64_t nz, double voxel_size,
     const vgt_b200_cloud* clouds, int32_t num_clouds, const vgt_b200_filter_options* filter,
     int device, float* out_occupancy, int32_t* out_counts, double* out_seconds)
 {
-  int check = CheckGrid(nx, ny, nz, voxel_size);
-  if (check != VGT_B200_OK)
-  {
-    return check;
-  }
-  check = CheckFilter(filter);
-  if (check != VGT_B200_OK)
-  {
-    return check;
-  }
-  if (static_occupancy == nullptr || out_occupancy == nullptr || num_clouds < 0
-      || (num_clouds > 0 && clouds == nullptr))
-  {
-    return FailInvalid("null pointer or negative cloud count");
-  }
-  for (int32_t c = 0; c < num_clouds; c++)
-  {
-    if (clouds[c].num_points < 0 || (clouds[c].num_points > 0 && clouds[c].points_xyz == nullptr))
-    {
-      // pcv_if.hpp:281-289 rejects null clouds with invalid_argument.
-      return FailInvalid("pointclouds[%d] is null", c);
-    }
-  }
-  ScopedDevice scoped(device);
-  VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
-  KeepPoolMemory(device);
-  const auto start_time = std::chrono::steady_clock::now();
-  const int64_t num_voxels = nx * ny * nz;
-  const GridFrame grid = MakeFrame(nx, ny, nz, voxel_size);
-  cudaStream_t stream = nullptr;
-  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  struct StreamGuard
-  {
-    cudaStream_t s;
-    ~StreamGuard() { cudaStreamDestroy(s); }
-  } guard{stream};
+  return VoxelizeFromHost<double>(static_occupancy, nx, ny, nz, voxel_size, clouds, num_clouds,
+                                  filter, device, out_occupancy, out_counts, out_seconds);
+}
 
-  // Stream-ordered pool allocations: steady-state calls reuse the same blocks.
-  StreamScratch<int32_t> d_counts;
-  StreamScratch<float> d_occupancy;
-  VGT_CUDA_TRY(d_counts.Allocate(2 * num_voxels * (num_clouds > 0 ? num_clouds : 1), stream),
-               "tracking grid allocation");
-  VGT_CUDA_TRY(d_occupancy.Allocate(num_voxels, stream), "occupancy allocation");
-  VGT_CUDA_TRY(cudaMemsetAsync(d_counts.get(), 0,
-                               sizeof(int32_t) * 2 * num_voxels * (num_clouds > 0 ? num_clouds : 1),
-                               stream),
-               "zero tracking grids");
-  VGT_CUDA_TRY(cudaMemcpyAsync(d_occupancy.get(), static_occupancy, sizeof(float) * num_voxels,
-                               cudaMemcpyHostToDevice, stream),
-               "copy occupancy to device");
-  int64_t max_points = 0;
-  for (int32_t c = 0; c < num_clouds; c++)
-  {
-    max_points = (clouds[c].num_points > max_points) ? clouds[c].num_points : max_points;
-  }
-  StreamScratch<double> d_points;
-  if (max_points > 0)
-  {
-    VGT_CUDA_TRY(d_points.Allocate(3 * max_points, stream), "points allocation");
-  }
-  for (int32_t c = 0; c < num_clouds; c++)
-  {
-    if (clouds[c].num_points == 0)
-    {
-      continue;
-    }
-    VGT_CUDA_TRY(cudaMemcpyAsync(d_points.get(), clouds[c].points_xyz,
-                                 sizeof(double) * 3 * clouds[c].num_points,
-                                 cudaMemcpyHostToDevice, stream),
-                 "copy points to device");
-    const int status =
-        LaunchRaycast(d_points.get(), clouds[c].num_points, clouds[c].x_gc, clouds[c].max_range,
-                      grid, d_counts.get() + 2 * num_voxels * c, stream);
-    if (status != VGT_B200_OK)
-    {
-      return status;
-    }
-  }
-  VGT_CUDA_TRY(cudaStreamSynchronize(stream), "raycasting");
-  const auto raycast_time = std::chrono::steady_clock::now();
-  const int status =
-      LaunchFilter(d_counts.get(), num_clouds, num_voxels, *filter, d_occupancy.get(), stream);
-  if (status != VGT_B200_OK)
-  {
-    return status;
-  }
-  VGT_CUDA_TRY(cudaMemcpyAsync(out_occupancy, d_occupancy.get(), sizeof(float) * num_voxels,
-                               cudaMemcpyDeviceToHost, stream),
-               "copy occupancy to host");
-  if (out_counts != nullptr && num_clouds > 0)
-  {
-    VGT_CUDA_TRY(cudaMemcpyAsync(out_counts, d_counts.get(),
-                                 sizeof(int32_t) * 2 * num_voxels * num_clouds,
-                                 cudaMemcpyDeviceToHost, stream),
-                 "copy counts to host");
-  }
-  VGT_CUDA_TRY(cudaStreamSynchronize(stream), "filtering");
-  const auto done_time = std::chrono::steady_clock::now();
-  if (out_seconds != nullptr)
-  {
-    out_seconds[0] = std::chrono::duration<double>(raycast_time - start_time).count();
-    out_seconds[1] = std::chrono::duration<double>(done_time - raycast_time).count();
-  }
-  return VGT_B200_OK;
+int vgt_b200_voxelize_f32(
+    const float* static_occupancy, int64_t nx, int64_t ny, int64_t nz, double voxel_size,
+    const vgt_b200_cloud_f32* clouds, int32_t num_clouds, const vgt_b200_filter_options* filter,
+    int device, float* out_occupancy, int32_t* out_counts, double* out_seconds)
+{
+  return VoxelizeFromHost<float>(static_occupancy, nx, ny, nz, voxel_size, clouds, num_clouds,
+                                 filter, device, out_occupancy, out_counts, out_seconds);
 }
 }  // extern "C"

@@ -157,15 +157,19 @@ def edt_final_pass(packed: torch.Tensor, y_offset: int, ny_total: int, resolutio
 
 def raycast_cloud(points_xyz: torch.Tensor, x_gc, max_range: float, counts: torch.Tensor,
                   voxel_size: float) -> torch.Tensor:
-    """Accumulates one cloud (float64 [N, 3], cloud frame) into counts int32 [nx, ny, nz, 2]."""
-    _require_cuda(points_xyz, torch.float64, "points_xyz")
+    """Accumulates one cloud (float64 or float32 [N, 3], cloud frame) into counts int32
+    [nx, ny, nz, 2]; float32 points are widened on the device."""
+    single = points_xyz.dtype == torch.float32
+    _require_cuda(points_xyz, torch.float32 if single else torch.float64, "points_xyz")
     _require_cuda(counts, torch.int32, "counts")
     if counts.dim() != 4 or counts.shape[3] != 2:
         raise ValueError("counts must be [nx, ny, nz, 2]")
     device = counts.device
     column_major = np.ascontiguousarray(np.asarray(x_gc, dtype=np.float64).reshape(4, 4).T)
     nx, ny, nz, _ = counts.shape
-    code = _capi.library().vgt_b200_raycast_f64_dev(
+    entry = _capi.library().vgt_b200_raycast_f32_dev if single \
+        else _capi.library().vgt_b200_raycast_f64_dev
+    code = entry(
         points_xyz.data_ptr(), points_xyz.shape[0],
         column_major.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), float(max_range), nx, ny,
         nz, float(voxel_size), device.index or 0, counts.data_ptr(), _stream_handle(device))

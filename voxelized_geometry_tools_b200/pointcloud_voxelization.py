@@ -141,6 +141,31 @@ class VectorPointCloudWrapper(PointCloudWrapper):
         return self._points
 
 
+class Float32PointCloudWrapper(VectorPointCloudWrapper):
+    """Dense [N, 3] float32 cloud: what a sensor_msgs/PointCloud2 carries. The reference's
+    PointCloud2Wrapper (pointcloud_voxelization_ros_interface.hpp:35-97) widens each point to
+    double when it is asked for one; here the float32 buffer goes to the device as it is (half
+    the bytes) and is widened there (vgt_b200_voxelize_f32). Same counts as the same values held
+    in a VectorPointCloudWrapper."""
+
+    def __init__(self, points=None, origin_transform=None, max_range: float = float("inf")):
+        super().__init__(None, origin_transform, max_range)
+        self._points32 = (np.zeros((0, 3), dtype=np.float32) if points is None
+                          else np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3))
+
+    def Size(self) -> int:
+        return int(self._points32.shape[0])
+
+    def CopyPointLocationIntoDoublePtrImpl(self, point_index: int, destination: np.ndarray):
+        destination[:3] = self._points32[point_index]
+
+    def PointsAsDoubleArray(self) -> np.ndarray:
+        return self._points32.astype(np.float64)
+
+    def PointsAsFloatArray(self) -> np.ndarray:
+        return self._points32
+
+
 class VoxelizerRuntime:
     def __init__(self, raycasting_time: float, filtering_time: float):
         if raycasting_time < 0.0:
@@ -211,13 +236,21 @@ class B200PointCloudVoxelizer(PointCloudVoxelizationInterface):
                               output_environment, keep_counts: bool = False) -> VoxelizerRuntime:
         lib = _capi.library()
         nx, ny, nz = static_environment.ControlSizes().shape
-        clouds = (_capi.Cloud * max(1, len(pointclouds)))()
+        # float32 clouds only: the float32 entry (12 bytes per point over the bus)
+        single = len(pointclouds) > 0 and all(hasattr(cloud, "PointsAsFloatArray")
+                                              for cloud in pointclouds)
+        cloud_type, scalar, c_scalar, entry = (
+            (_capi.CloudF32, np.float32, ctypes.c_float, lib.vgt_b200_voxelize_f32) if single
+            else (_capi.Cloud, np.float64, ctypes.c_double, lib.vgt_b200_voxelize_f64))
+        clouds = (cloud_type * max(1, len(pointclouds)))()
         keepalive = []
         for index, cloud in enumerate(pointclouds):
-            points = np.ascontiguousarray(cloud.PointsAsDoubleArray(), dtype=np.float64)
+            points = np.ascontiguousarray(
+                cloud.PointsAsFloatArray() if single else cloud.PointsAsDoubleArray(),
+                dtype=scalar)
             keepalive.append(points)
             x_gc = grid_from_cloud_transform(static_environment, cloud)
-            clouds[index].points_xyz = points.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+            clouds[index].points_xyz = points.ctypes.data_as(ctypes.POINTER(c_scalar))
             clouds[index].num_points = points.shape[0]
             clouds[index].x_gc = (ctypes.c_double * 16)(*x_gc.T.reshape(-1))  # column-major
             clouds[index].max_range = float(cloud.MaxRange())
@@ -228,7 +261,7 @@ class B200PointCloudVoxelizer(PointCloudVoxelizationInterface):
         seconds = (ctypes.c_double * 2)()
         static_data = static_environment.GetImmutableRawData()
         out_data = output_environment.GetMutableRawData()
-        code = lib.vgt_b200_voxelize_f64(
+        code = entry(
             static_data.ctypes.data, nx, ny, nz, static_environment.VoxelXSize(), clouds,
             len(pointclouds), ctypes.byref(options), self._device, out_data.ctypes.data,
             None if counts is None else counts.ctypes.data, seconds)

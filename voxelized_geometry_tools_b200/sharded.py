@@ -303,3 +303,116 @@ class ShardedSignedDistanceField:
             y0, y1 = split_range(ny, self.world_size, peer)
             full[:, y0:y1, :] = piece
         return full
+
+
+# --------------------------------------------------------------------------------------------------
+# Sharded voxelizer: counters are additive over rays
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class VoxelizerStages:
+    """raycast(points [n, 3] f64, x_gc 4x4, max_range, counts int32 [nx, ny, nz, 2], voxel_size)
+        accumulates one cloud (or part of one) into counts;
+    filter(counts int32 [cameras, nxl, ny, nz, 2], occupancy f32 [nxl, ny, nz], options)
+        applies the per-camera rule and the combine in place on a slab."""
+    raycast: Callable
+    filter: Callable
+
+
+def cuda_voxelizer_stages() -> VoxelizerStages:
+    from . import device
+
+    def raycast(points, x_gc, max_range, counts, voxel_size):
+        device.raycast_cloud(points, x_gc, max_range, counts, voxel_size)
+
+    def filter_slab(counts, occupancy, options):
+        device.filter_grids(counts, occupancy, options)
+
+    return VoxelizerStages(raycast, filter_slab)
+
+
+class ShardedPointCloudVoxelizer:
+    """PointCloudVoxelizationInterface::VoxelizePointClouds across the GPUs of one box.
+
+    The rays of every cloud are split evenly over the ranks (rank r takes points r, r + G, ...);
+    each rank raycasts its share into full-size tracking grids; one reduce-scatter (sum, int32)
+    per camera adds the shares and leaves rank g with the x-slab the sharded SDF starts from.
+    The per-camera rule (pointcloud_voxelization_interface.hpp:55-86) needs a camera's COMPLETE
+    counters, so the rays of one camera are summed before it, and cameras are combined after
+    it, slab-local (cpu_pointcloud_voxelization.cpp:438-497). The filtered occupancy x-slab feeds
+    ShardedSignedDistanceField.extract directly: voxelize -> SDF never leaves the devices.
+
+    The reference voxelizes in one process (cpu_pointcloud_voxelization.cpp:133-165); counts are
+    integers, so the sharded result is bit-identical to it whatever the split."""
+
+    def __init__(self, dims, voxel_size: float, rank: int | None = None,
+                 world_size: int | None = None, group=None,
+                 stages: VoxelizerStages | None = None):
+        self.dims = tuple(int(d) for d in dims)
+        self.voxel_size = float(voxel_size)
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world_size = dist.get_world_size(group) if world_size is None else world_size
+        if self.world_size > self.dims[0]:
+            raise ValueError("more ranks than voxels along x")
+        self.stages = stages if stages is not None else cuda_voxelizer_stages()
+        self.x_range = split_range(self.dims[0], self.world_size, self.rank)
+        self.last_counts = None
+
+    def share_of(self, points: torch.Tensor) -> torch.Tensor:
+        """This rank's rays of a cloud that every rank holds in full."""
+        return points[self.rank::self.world_size].contiguous()
+
+    def _reduce_scatter_x(self, counts: torch.Tensor) -> torch.Tensor:
+        """counts [nx, ny, nz, 2] (this rank's share) -> summed x-slab [nxl, ny, nz, 2]."""
+        nx, ny, nz = self.dims
+        world = self.world_size
+        if world == 1:
+            return counts
+        x0, x1 = self.x_range
+        backend = dist.get_backend(self.group)
+        if nx % world == 0 and backend == "nccl":
+            out = torch.empty((nx // world, ny, nz, 2), dtype=counts.dtype, device=counts.device)
+            dist.reduce_scatter_tensor(out, counts, op=dist.ReduceOp.SUM, group=self.group)
+            return out
+        if backend == "nccl":
+            # uneven slabs: reduce-scatter over a list of per-rank views (NCCL sends each one)
+            pieces = [counts[split_range(nx, world, r)[0]:split_range(nx, world, r)[1]]
+                      for r in range(world)]
+            out = torch.empty_like(pieces[self.rank])
+            works = [dist.reduce(piece, dst=r, op=dist.ReduceOp.SUM, group=self.group,
+                                 async_op=True) for r, piece in enumerate(pieces)]
+            for work in works:
+                work.wait()
+            out.copy_(pieces[self.rank])
+            return out
+        # gloo (CPU tests of the host logic): all-reduce, keep the own slab
+        total = counts.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        return total[x0:x1].contiguous()
+
+    def voxelize(self, static_occupancy_slab: torch.Tensor, clouds, filter_options,
+                 points_are_shares: bool = False, keep_counts: bool = False) -> torch.Tensor:
+        """static_occupancy_slab: this rank's x-slab [nxl, ny, nz] float32 of the static map.
+        clouds: [(points float64 [n, 3] in the cloud frame, X_GC 4x4, max_range), ...] - the same
+        list on every rank (points_are_shares=False: each rank takes its share of the rays) or
+        already this rank's share. Returns the filtered occupancy x-slab (a new tensor)."""
+        nx, ny, nz = self.dims
+        x0, x1 = self.x_range
+        if tuple(static_occupancy_slab.shape) != (x1 - x0, ny, nz):
+            raise ValueError(f"expected an x-slab of shape {(x1 - x0, ny, nz)}")
+        device = static_occupancy_slab.device
+        slabs = []
+        for points, x_gc, max_range in clouds:
+            share = points if points_are_shares else self.share_of(points)
+            counts = torch.zeros((nx, ny, nz, 2), dtype=torch.int32, device=device)
+            self.stages.raycast(share, x_gc, max_range, counts, self.voxel_size)
+            slabs.append(self._reduce_scatter_x(counts))
+            del counts
+        # at least one tracking grid even without clouds (device_pointcloud_voxelization.cpp:79-80)
+        if not slabs:
+            slabs.append(torch.zeros((x1 - x0, ny, nz, 2), dtype=torch.int32, device=device))
+        camera_counts = torch.stack(slabs)
+        occupancy = static_occupancy_slab.clone()
+        self.stages.filter(camera_counts, occupancy, filter_options)
+        self.last_counts = camera_counts if keep_counts else None
+        return occupancy
