@@ -633,7 +633,27 @@ def bench_tagged_map(device_index, include_cpu=True):
     tagged.ExtractFreeAndNamedObjectsSignedDistanceField(parameters, device=device_index)
     merged_seconds = time.perf_counter() - begin
     voxels = float(n) ** 3
+    # the C-ABI call alone, caller-owned output reused across calls (what a C++ caller that keeps
+    # its SDF storage pays; the Python mirror above allocates 8 fresh grids per call)
+    import ctypes as ct
+    from voxelized_geometry_tools_b200 import _capi
+    lib = _capi.library()
+    out = np.zeros((objects, n, n, n), dtype=np.float32)
+    lows, highs = (ct.c_float * objects)(), (ct.c_float * objects)()
+    id_array = (ct.c_uint32 * objects)(*ids)
+    call_times = []
+    for iteration in range(4):
+        begin = time.perf_counter()
+        _capi.check(lib.vgt_b200_sdf_per_object_f32(
+            cells.ctypes.data, cells.dtype.itemsize, n, n, n, RESOLUTION, 1, 0, id_array, objects,
+            device_index, out.ctypes.data, lows, highs))
+        if iteration >= 1:
+            call_times.append(time.perf_counter() - begin)
+    c_abi_seconds = statistics.mean(call_times)
     result = {"grid": f"{n}^3 TaggedObjectOccupancyMap, {objects} objects",
+              "c_abi_call_only": {"api": "vgt_b200_sdf_per_object_f32 (pageable buffers, reused)",
+                                  "ms_per_call": c_abi_seconds * 1e3,
+                                  "ms_per_object": c_abi_seconds * 1e3 / objects},
               "per_object_batch_ms": batch_seconds * 1e3,
               "per_object_batch_gvoxels_per_s": objects * voxels / batch_seconds / 1e9,
               "free_and_named_ms": merged_seconds * 1e3,
@@ -713,6 +733,39 @@ def bench_voxelizer(dev, peak, include_cpu=True):
         if iteration >= 1:
             host_times.append(time.perf_counter() - begin)
     host_seconds = statistics.mean(host_times)
+    # the C-ABI call alone (caller-owned pageable buffers reused across calls), double and
+    # float32 clouds: what a C++ caller that keeps its output map pays
+    import ctypes as ct
+    from voxelized_geometry_tools_b200 import _capi
+    lib = _capi.library()
+    out_map = np.empty_like(scene["static_occupancy"])
+    option_struct = options.as_struct()
+    c_abi = {}
+    for label, cloud_type, scalar, c_scalar, entry in (
+            ("f64", _capi.Cloud, np.float64, ct.c_double, lib.vgt_b200_voxelize_f64),
+            ("f32", _capi.CloudF32, np.float32, ct.c_float, lib.vgt_b200_voxelize_f32)):
+        array = (cloud_type * len(scene["clouds"]))()
+        keep = []
+        for index, (points, x_wc, max_range) in enumerate(scene["clouds"]):
+            held = np.ascontiguousarray(points, dtype=scalar)
+            keep.append(held)
+            array[index].points_xyz = held.ctypes.data_as(ct.POINTER(c_scalar))
+            array[index].num_points = held.shape[0]
+            array[index].x_gc = (ct.c_double * 16)(*compose_rigid(x_gw, x_wc).T.reshape(-1))
+            array[index].max_range = float(max_range)
+        seconds = (ct.c_double * 2)()
+        times = []
+        for iteration in range(5):
+            begin = time.perf_counter()
+            _capi.check(entry(scene["static_occupancy"].ctypes.data, n, n, n, scene["voxel_size"],
+                              array, len(scene["clouds"]), ct.byref(option_struct),
+                              dev.index or 0, out_map.ctypes.data, None, seconds))
+            if iteration >= 1:
+                times.append(time.perf_counter() - begin)
+        c_abi[label] = {"ms_per_call": statistics.mean(times) * 1e3,
+                        "mrays_per_s": finite_rays / statistics.mean(times) / 1e6,
+                        "raycast_ms_reported": seconds[0] * 1e3,
+                        "filter_ms_reported": seconds[1] * 1e3}
 
     cpu = None
     if include_cpu:
@@ -746,7 +799,9 @@ def bench_voxelizer(dev, peak, include_cpu=True):
             "e2e": {"value": finite_rays / host_seconds / 1e6, "unit": "Mrays/s",
                     "ms_per_call": host_seconds * 1e3,
                     "api": "B200PointCloudVoxelizer.VoxelizePointClouds (vgt_b200_voxelize_f64, "
-                           "host buffers, raycast + filter + map copy)"},
+                           "host buffers, raycast + filter + the copy of the static map the "
+                           "interface makes, pcv_if.hpp:252)",
+                    "c_abi_call_only": c_abi},
             "cpu_baseline": cpu,
             "filter_roofline": {"bound": "hbm", "achieved": filter_bytes / (filt * 1e-3) / 1e9,
                                 "peak": peak, "unit": "GB/s",

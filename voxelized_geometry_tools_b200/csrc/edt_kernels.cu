@@ -1006,9 +1006,16 @@ struct CellUpload
              int64_t num_object_ids, cudaStream_t stream)
   {
     VGT_CUDA_TRY(cells.Allocate(count * (cell_bytes / 4), stream), "cell array allocation");
-    VGT_CUDA_TRY(cudaMemcpyAsync(cells.get(), h_cells, static_cast<size_t>(count) * cell_bytes,
-                                 cudaMemcpyHostToDevice, stream),
-                 "copy cells to device");
+    {
+      // (pageable std::vector storage goes through the pinned staging ring)
+      StagedTransfer transfer;
+      const size_t bytes = static_cast<size_t>(count) * cell_bytes;
+      VGT_CUDA_TRY(transfer.ToDevice(reinterpret_cast<char*>(cells.get()), bytes,
+                                     static_cast<const char*>(h_cells), bytes, bytes, 1, stream),
+                   "copy cells to device");
+      // the slots go back to the cache when `transfer` dies: their DMA must have finished
+      VGT_CUDA_TRY(cudaStreamSynchronize(stream), "copy cells to device");
+    }
     sorted.assign(object_ids, object_ids + num_object_ids);
     std::sort(sorted.begin(), sorted.end());
     sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
@@ -1057,10 +1064,18 @@ int SdfFromCellsHost(const void* h_cells, int cell_bytes, int64_t nx, int64_t ny
     return uploaded;
   }
   const int64_t num_sdfs = per_object ? num_object_ids : 1;
-  StreamScratch<Out> d_out;
+  // Two result buffers and a copy stream: the SDF of object k + 1 is computed while object k
+  // travels to the host (through the pinned staging ring when the caller's buffer is pageable).
+  StreamGuard copy;
+  VGT_CUDA_TRY(cudaStreamCreateWithFlags(&copy.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  StreamScratch<Out> d_out[2];
   StreamScratch<Out> d_min_max;
   StreamScratch<uint32_t> d_one_id;
-  VGT_CUDA_TRY(d_out.Allocate(count, stream), "SDF allocation");
+  VGT_CUDA_TRY(d_out[0].Allocate(count, stream), "SDF allocation");
+  if (num_sdfs > 1)
+  {
+    VGT_CUDA_TRY(d_out[1].Allocate(count, stream), "SDF allocation");
+  }
   VGT_CUDA_TRY(d_min_max.Allocate(2 * std::max<int64_t>(num_sdfs, 1), stream), "min/max");
   if (per_object && num_sdfs > 0)
   {
@@ -1069,15 +1084,32 @@ int SdfFromCellsHost(const void* h_cells, int cell_bytes, int64_t nx, int64_t ny
                                  cudaMemcpyHostToDevice, stream),
                  "copy object ids to device");
   }
-  std::vector<Out> min_max(static_cast<size_t>(2 * std::max<int64_t>(num_sdfs, 1)));
-  for (int64_t k = 0; k < num_sdfs; k++)
+  StagedTransfer transfer;
+  EventGuard computed[2];
+  for (auto& guard_event : computed)
   {
+    VGT_CUDA_TRY(cudaEventCreateWithFlags(&guard_event.event, cudaEventDisableTiming), "event");
+  }
+  // (runs first on every exit path: nothing is still queued when the buffers are released)
+  struct DrainOnExit
+  {
+    cudaStream_t a;
+    cudaStream_t b;
+    ~DrainOnExit()
+    {
+      cudaStreamSynchronize(a);
+      cudaStreamSynchronize(b);
+    }
+  } drain{stream, copy.stream};
+  const auto enqueue = [&](int64_t k) -> int
+  {
+    Out* const target = d_out[k & 1].get();
     int status;
     if (per_object)
     {
       status = SdfFromCellsOnDevice<kMode>(upload.cells.get(), cell_bytes / 4, nx, ny, nz,
                                            resolution, unknown_is_filled, add_virtual_border,
-                                           kListedObjects, d_one_id.get() + k, 1, d_out.get(),
+                                           kListedObjects, d_one_id.get() + k, 1, target,
                                            d_min_max.get() + 2 * k, stream);
     }
     else
@@ -1086,18 +1118,43 @@ int SdfFromCellsHost(const void* h_cells, int cell_bytes, int64_t nx, int64_t ny
       status = SdfFromCellsOnDevice<kMode>(upload.cells.get(), cell_bytes / 4, nx, ny, nz,
                                            resolution, unknown_is_filled, add_virtual_border,
                                            num_ids > 0 ? kListedObjects : kAnyObject,
-                                           upload.ids.get(), num_ids, d_out.get(),
-                                           d_min_max.get(), stream);
+                                           upload.ids.get(), num_ids, target, d_min_max.get(),
+                                           stream);
     }
     if (status != VGT_B200_OK)
     {
-      cudaStreamSynchronize(stream);
       return status;
     }
-    // (stream order: the copy finishes before the next SDF overwrites d_out)
-    VGT_CUDA_TRY(cudaMemcpyAsync(h_out + k * count, d_out.get(), sizeof(Out) * count,
-                                 cudaMemcpyDeviceToHost, stream),
+    VGT_CUDA_TRY(cudaEventRecord(computed[k & 1].event, stream), "event record");
+    return VGT_B200_OK;
+  };
+  std::vector<Out> min_max(static_cast<size_t>(2 * std::max<int64_t>(num_sdfs, 1)));
+  if (num_sdfs > 0)
+  {
+    const int status = enqueue(0);
+    if (status != VGT_B200_OK)
+    {
+      return status;
+    }
+  }
+  for (int64_t k = 0; k < num_sdfs; k++)
+  {
+    if (k + 1 < num_sdfs)
+    {
+      // (buffer (k + 1) & 1 was drained by the blocking copy of object k - 1)
+      const int status = enqueue(k + 1);
+      if (status != VGT_B200_OK)
+      {
+        return status;
+      }
+    }
+    VGT_CUDA_TRY(cudaStreamWaitEvent(copy.stream, computed[k & 1].event, 0), "stream wait");
+    const size_t bytes = sizeof(Out) * static_cast<size_t>(count);
+    VGT_CUDA_TRY(transfer.ToHost(reinterpret_cast<char*>(h_out + k * count), bytes,
+                                 reinterpret_cast<const char*>(d_out[k & 1].get()), bytes, bytes,
+                                 1, copy.stream),
                  "copy SDF to host");
+    VGT_CUDA_TRY(cudaStreamSynchronize(copy.stream), "copy SDF to host");
   }
   if (num_sdfs > 0)
   {
