@@ -78,6 +78,21 @@ VGT_B200_API int vgt_b200_sdf_f32(
     int unknown_is_filled, int add_virtual_border, int device, float* sdf_out, float* out_min,
     float* out_max);
 
+/* The same call on SEVERAL devices of one box, from one process: the grid is cut into x-slabs
+ * (one per listed device), the z and y passes run slab-local with the exchange fused into the
+ * y pass (NVLink peer stores into the other devices' receive buffers; peer access is enabled
+ * between the listed devices), the x pass + finalize on y-slabs, and every device copies its
+ * y-slab into its rows of sdf_out. Same result, bit for bit, as vgt_b200_sdf_f32.
+ * Replaces the same reference code (include/.../occupancy_map.hpp:174-210); the reference's only
+ * parallelism is the OpenMP split over lines (src/.../signed_distance_field_generation.cpp:286-389).
+ *   devices, num_devices   1..8 distinct device ordinals; 1 device = vgt_b200_sdf_f32.
+ * Fails with VGT_B200_ERR_DEVICE when two of the devices cannot reach each other as peers (no
+ * fallback). Uses one host thread per device for the duration of the call. */
+VGT_B200_API int vgt_b200_sdf_f32_multi(
+    const float* occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const int* devices, int num_devices,
+    float* sdf_out, float* out_min, float* out_max);
+
 /* Same for SignedDistanceField<double> (ExtractSignedDistanceFieldDouble, occupancy_map.cpp:250-254). */
 VGT_B200_API int vgt_b200_sdf_f64(
     const float* occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,

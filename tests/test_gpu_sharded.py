@@ -114,3 +114,30 @@ def test_nccl_sharded_path_on_two_gpus(shared_library):
     result = subprocess.run(command, env=env, capture_output=True, text=True, timeout=600)
     assert result.returncode == 0, result.stdout[-3000:] + result.stderr[-3000:]
     assert "MULTI_GPU_CHECK_OK" in result.stdout
+
+
+def test_single_process_multi_device_entry(shared_library, oracle):
+    # vgt_b200_sdf_f32_multi: one process, several devices, peer stores between them; the result
+    # equals the one-device call bit for bit (and the oracle at a small size).
+    import torch
+    import voxelized_geometry_tools_b200 as vgt
+    from voxelized_geometry_tools_b200 import synthetic
+    count = torch.cuda.device_count()
+    if count < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    for dims, border in (((40, 36, 44), False), ((61, 45, 130), True), ((256, 192, 160), False)):
+        occupancy = synthetic.clustered_spheres_occupancy(dims)
+        sizes = vgt.VoxelGridSizes.FromVoxelCounts(0.02, dims)
+        grid = vgt.OccupancyMap(np.eye(4), "world", sizes, data=occupancy)
+        parameters = vgt.SignedDistanceFieldGenerationParameters(add_virtual_border=border)
+        single = grid.ExtractSignedDistanceFieldFloat(parameters)
+        for used in {2, count}:
+            multi = grid.ExtractSignedDistanceFieldFloat(parameters, devices=list(range(used)))
+            np.testing.assert_array_equal(multi.GetImmutableRawData(),
+                                          single.GetImmutableRawData())
+            assert multi.GetMinimumMaximum() == single.GetMinimumMaximum()
+        if np.prod(dims) < 2 ** 20:
+            want, _ = oracle.sdf(occupancy, 0.02, add_virtual_border=border)
+            np.testing.assert_array_equal(multi.GetImmutableRawData(), want)
+    with pytest.raises(ValueError):
+        grid.ExtractSignedDistanceFieldFloat(parameters, devices=[0, 0])

@@ -183,6 +183,29 @@ inline SignedDistanceField<SDFScalarType> ExtractSignedDistanceFieldFromOccupanc
   FinishAndLock(new_sdf, minimum, maximum);
   return new_sdf;
 }
+// The same on several devices of the box (vgt_b200_sdf_f32_multi: x-slabs, one per device, the
+// exchange fused into the y pass as NVLink peer stores). SignedDistanceField<float> only.
+template <typename OccupancyMapType>
+inline SignedDistanceField<float> ExtractSignedDistanceFieldFromOccupancyMap(
+    const OccupancyMapType& map, const SignedDistanceFieldGenerationParameters<float>& parameters,
+    const std::vector<int>& devices)
+{
+  if (!map.HasUniformVoxelSize())
+  {
+    throw std::invalid_argument("Grid must have uniform resolution");
+  }
+  const float* occupancy = reinterpret_cast<const float*>(map.GetImmutableRawData().data());
+  SignedDistanceField<float> new_sdf(
+      map.OriginTransform(), map.Frame(), map.ControlSizes(), parameters.OOBValue());
+  float minimum = 0;
+  float maximum = 0;
+  ThrowOnError(vgt_b200_sdf_f32_multi(
+      occupancy, map.NumXVoxels(), map.NumYVoxels(), map.NumZVoxels(), map.VoxelXSize(),
+      parameters.UnknownIsFilled() ? 1 : 0, parameters.AddVirtualBorder() ? 1 : 0, devices.data(),
+      static_cast<int>(devices.size()), new_sdf.GetMutableRawData().data(), &minimum, &maximum));
+  FinishAndLock(new_sdf, minimum, maximum);
+  return new_sdf;
+}
 }  // namespace b200
 }  // namespace signed_distance_field_generation
 VGT_NAMESPACE_END

@@ -174,6 +174,32 @@ void SdfTests()
   }
 }
 
+// With two or more devices: the multi-device overload gives the one-device result bit for bit.
+void MultiDeviceTest()
+{
+  const int devices = vgt_b200_device_count();
+  if (devices < 2)
+  {
+    return;
+  }
+  OccupancyMap map = MakeMap(0.25, 8.0, 6.0, 7.0, 0.0f);
+  FillBox(map, 3, 9, 2, 11, 5, 20);
+  FillBox(map, 20, 31, 14, 19, 1, 6);
+  for (const bool border : {false, true})
+  {
+    const SignedDistanceFieldGenerationParameters<float> params(
+        std::numeric_limits<float>::infinity(), DegreeOfParallelism::None(), true, border);
+    const auto single = b200::ExtractSignedDistanceFieldFromOccupancyMap(map, params);
+    std::vector<int> listed;
+    for (int d = 0; d < devices; d++) { listed.push_back(d); }
+    const auto multi = b200::ExtractSignedDistanceFieldFromOccupancyMap(map, params, listed);
+    EXPECT_TRUE(multi.IsLocked());
+    EXPECT_TRUE(multi.GetImmutableRawData() == single.GetImmutableRawData());
+    EXPECT_TRUE(multi.GetMinimumMaximum().Minimum() == single.GetMinimumMaximum().Minimum());
+    EXPECT_TRUE(multi.GetMinimumMaximum().Maximum() == single.GetMinimumMaximum().Maximum());
+  }
+}
+
 // test/pointcloud_voxelization_test.cpp:31-82
 class VectorVector3dPointCloudWrapper : public pointcloud_voxelization::PointCloudWrapper
 {
@@ -630,6 +656,7 @@ int main(int argc, char** argv)
     return TimeAdapter(std::atoll(argv[2]));
   }
   SdfTests();
+  MultiDeviceTest();
   VoxelizationTest();
   CellMapTests<float>();
   CellMapTests<double>();

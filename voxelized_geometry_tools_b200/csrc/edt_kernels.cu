@@ -2,7 +2,12 @@
 // Device code: edt_device.cuh (z scan, shared-memory envelope fallback, finalize helpers) and
 // edt_envelope_inplace.cuh (the fast envelope kernel). DESIGN.md has the roofline of each kernel.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 #include <cstdlib>
 #include <cstring>
@@ -1257,6 +1262,288 @@ int SdfFreeAndNamedHost(const void* h_cells, int cell_bytes, int64_t nx, int64_t
   }
   return VGT_B200_OK;
 }
+// ------------------------------------------------------------------------------------------------
+// One process, several devices: the slab-sharded path of voxelized_geometry_tools_b200/sharded.py
+// behind one C call, so that a C++ caller of OccupancyMap::ExtractSignedDistanceField can use
+// every GPU of the box. One host thread per device runs that device's share: upload of its
+// x-slab, z scan + y pass with the exchange fused in (peer stores into the other devices'
+// receive buffers: cudaMalloc memory with peer access enabled), a barrier between the threads
+// once every stream has drained, x pass + finalize on its y-slab, strided copy of the y-slab
+// into its place in the caller's grid.
+// ------------------------------------------------------------------------------------------------
+inline void SplitRange(int64_t total, int parts, int index, int64_t* begin, int64_t* end)
+{
+  const int64_t base = total / parts;
+  const int64_t extra = total % parts;
+  *begin = index * base + std::min<int64_t>(index, extra);
+  *end = *begin + base + (index < extra ? 1 : 0);
+}
+
+// A reusable barrier for the per-device host threads (std::barrier is C++20).
+class ThreadBarrier
+{
+public:
+  explicit ThreadBarrier(int count) : count_(count), waiting_(0), generation_(0) {}
+  void Wait()
+  {
+    std::unique_lock<std::mutex> lock(mutex_);
+    const int generation = generation_;
+    if (++waiting_ == count_)
+    {
+      waiting_ = 0;
+      generation_++;
+      released_.notify_all();
+      return;
+    }
+    released_.wait(lock, [&] { return generation != generation_; });
+  }
+
+private:
+  std::mutex mutex_;
+  std::condition_variable released_;
+  int count_;
+  int waiting_;
+  int generation_;
+};
+
+int SdfMultiDevice(const float* h_in, int64_t nx, int64_t ny, int64_t nz, double resolution,
+                   int unknown_is_filled, int add_virtual_border, const int* devices,
+                   int num_devices, float* h_out, float* out_min, float* out_max)
+{
+  const int check = CheckSdfArguments(h_in, h_out, nx, ny, nz, resolution);
+  if (check != VGT_B200_OK)
+  {
+    return check;
+  }
+  if (devices == nullptr || num_devices < 1 || num_devices > 8)
+  {
+    return FailInvalid("1..8 devices are supported");
+  }
+  for (int a = 0; a < num_devices; a++)
+  {
+    for (int b = a + 1; b < num_devices; b++)
+    {
+      if (devices[a] == devices[b])
+      {
+        return FailInvalid("device %d is listed twice", devices[a]);
+      }
+    }
+  }
+  if (num_devices == 1)
+  {
+    return SdfFromHost<float, kEmitFloat>(h_in, nx, ny, nz, resolution, unknown_is_filled,
+                                          add_virtual_border, devices[0], h_out, out_min, out_max);
+  }
+  if (num_devices > nx || num_devices > ny)
+  {
+    return FailInvalid("more devices than voxels along x or y");
+  }
+  // Peer access between every pair (a one-time, process-wide driver setting; "already enabled"
+  // is fine). Without it the fused exchange cannot run: no silent fallback.
+  for (int a = 0; a < num_devices; a++)
+  {
+    ScopedDevice scoped(devices[a]);
+    VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+    for (int b = 0; b < num_devices; b++)
+    {
+      if (a == b)
+      {
+        continue;
+      }
+      int can_access = 0;
+      VGT_CUDA_TRY(cudaDeviceCanAccessPeer(&can_access, devices[a], devices[b]), "peer query");
+      if (can_access == 0)
+      {
+        SetLastError("device %d cannot access device %d as a peer", devices[a], devices[b]);
+        return VGT_B200_ERR_DEVICE;
+      }
+      const cudaError_t enabled = cudaDeviceEnablePeerAccess(devices[b], 0);
+      if (enabled != cudaSuccess && enabled != cudaErrorPeerAccessAlreadyEnabled)
+      {
+        return FailDevice("cudaDeviceEnablePeerAccess", enabled);
+      }
+      cudaGetLastError();
+    }
+  }
+  const int64_t plane = ny * nz;
+  const int64_t widest_part = (ny + num_devices - 1) / num_devices;
+  const int64_t receive_words = nx * widest_part * nz;
+  // Receive buffers: plain cudaMalloc (peer-mapped once access is enabled), owned by this call.
+  std::vector<uint32_t*> receive(static_cast<size_t>(num_devices), nullptr);
+  struct ReceiveGuard
+  {
+    std::vector<uint32_t*>& buffers;
+    const int* devices;
+    ~ReceiveGuard()
+    {
+      for (size_t g = 0; g < buffers.size(); g++)
+      {
+        if (buffers[g] != nullptr)
+        {
+          ScopedDevice scoped(devices[g]);
+          cudaFree(buffers[g]);
+        }
+      }
+    }
+  } receive_guard{receive, devices};
+  for (int g = 0; g < num_devices; g++)
+  {
+    ScopedDevice scoped(devices[g]);
+    VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+    VGT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&receive[static_cast<size_t>(g)]),
+                            sizeof(uint32_t) * static_cast<size_t>(receive_words)),
+                 "receive buffer allocation");
+  }
+  std::vector<uint64_t> peer_bases(static_cast<size_t>(num_devices));
+  for (int g = 0; g < num_devices; g++)
+  {
+    peer_bases[static_cast<size_t>(g)] = reinterpret_cast<uint64_t>(receive[static_cast<size_t>(g)]);
+  }
+
+  ThreadBarrier barrier(num_devices);
+  std::vector<int> statuses(static_cast<size_t>(num_devices), VGT_B200_OK);
+  std::vector<std::string> messages(static_cast<size_t>(num_devices));
+  std::vector<float> minima(static_cast<size_t>(num_devices));
+  std::vector<float> maxima(static_cast<size_t>(num_devices));
+  std::atomic<int> failed{0};
+
+  const auto worker = [&](const int g)
+  {
+    int status = VGT_B200_OK;
+    const int device = devices[g];
+    ScopedDevice scoped(device);
+    int64_t x0, x1, y0, y1;
+    SplitRange(nx, num_devices, g, &x0, &x1);
+    SplitRange(ny, num_devices, g, &y0, &y1);
+    StreamGuard guard;
+    StreamScratch<float> d_occupancy;
+    StreamScratch<uint32_t> d_scratch;
+    StreamScratch<float> d_sdf;
+    StreamScratch<float> d_min_max;
+    StagedTransfer transfer;
+    // (runs first on every exit path: nothing is queued when the buffers are released)
+    struct DrainOnExit
+    {
+      const StreamGuard& guard;
+      ~DrainOnExit()
+      {
+        if (guard.stream != nullptr)
+        {
+          cudaStreamSynchronize(guard.stream);
+        }
+      }
+    } drain{guard};
+    // Up to the barrier: every thread must reach it, whatever happens before.
+    const auto local_passes = [&]() -> int
+    {
+      VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+      KeepPoolMemory(device);
+      VGT_CUDA_TRY(cudaStreamCreateWithFlags(&guard.stream, cudaStreamNonBlocking), "stream");
+      const int64_t slab_voxels = (x1 - x0) * plane;
+      VGT_CUDA_TRY(d_occupancy.Allocate(slab_voxels, guard.stream), "occupancy slab allocation");
+      VGT_CUDA_TRY(d_scratch.Allocate(slab_voxels, guard.stream), "local pass scratch allocation");
+      const size_t slab_bytes = sizeof(float) * static_cast<size_t>(slab_voxels);
+      VGT_CUDA_TRY(transfer.ToDevice(reinterpret_cast<char*>(d_occupancy.get()), slab_bytes,
+                                     reinterpret_cast<const char*>(h_in + x0 * plane), slab_bytes,
+                                     slab_bytes, 1, guard.stream),
+                   "copy occupancy slab to device");
+      const int local = RunLocalPasses<float>(d_occupancy.get(), x1 - x0, ny, nz,
+                                              unknown_is_filled, d_scratch.get(), d_scratch.get(),
+                                              guard.stream, num_devices, peer_bases.data(), x0, g);
+      if (local != VGT_B200_OK)
+      {
+        return local;
+      }
+      VGT_CUDA_TRY(cudaStreamSynchronize(guard.stream), "slab-local passes");
+      return VGT_B200_OK;
+    };
+    const auto final_pass = [&]() -> int
+    {
+      cudaStream_t stream = guard.stream;
+      const int64_t rows = y1 - y0;
+      VGT_CUDA_TRY(d_sdf.Allocate(nx * rows * nz, stream), "SDF slab allocation");
+      VGT_CUDA_TRY(d_min_max.Allocate(2, stream), "min/max allocation");
+      const int final_status = RunFinalPass<kEmitFloat>(
+          receive[static_cast<size_t>(g)], nx, rows, nz, y0, ny, resolution, add_virtual_border,
+          d_sdf.get(), d_min_max.get(), stream);
+      if (final_status != VGT_B200_OK)
+      {
+        return final_status;
+      }
+      // y-slab [nx][rows][nz] -> rows of the caller's [nx][ny][nz] grid (a strided 2-D copy)
+      VGT_CUDA_TRY(transfer.ToHost(reinterpret_cast<char*>(h_out + y0 * nz),
+                                   sizeof(float) * static_cast<size_t>(plane),
+                                   reinterpret_cast<const char*>(d_sdf.get()),
+                                   sizeof(float) * static_cast<size_t>(rows * nz),
+                                   sizeof(float) * static_cast<size_t>(rows * nz),
+                                   static_cast<size_t>(nx), stream),
+                   "copy SDF slab to host");
+      float min_max[2];
+      VGT_CUDA_TRY(cudaMemcpyAsync(min_max, d_min_max.get(), sizeof(min_max),
+                                   cudaMemcpyDeviceToHost, stream),
+                   "copy min/max to host");
+      VGT_CUDA_TRY(cudaStreamSynchronize(stream), "SDF generation");
+      minima[static_cast<size_t>(g)] = min_max[0];
+      maxima[static_cast<size_t>(g)] = min_max[1];
+      return VGT_B200_OK;
+    };
+    status = local_passes();
+    if (status != VGT_B200_OK)
+    {
+      messages[static_cast<size_t>(g)] = vgt_b200_last_error();  // thread-local text
+      failed.store(1);
+    }
+    // every device's stores into every receive buffer have landed
+    barrier.Wait();
+    if (status == VGT_B200_OK && failed.load() != 0)
+    {
+      status = VGT_B200_ERR_DEVICE;
+      messages[static_cast<size_t>(g)] = "another device failed";
+    }
+    else if (status == VGT_B200_OK)
+    {
+      status = final_pass();
+      if (status != VGT_B200_OK)
+      {
+        messages[static_cast<size_t>(g)] = vgt_b200_last_error();
+      }
+    }
+    statuses[static_cast<size_t>(g)] = status;
+  };
+  std::vector<std::thread> threads;
+  for (int g = 1; g < num_devices; g++)
+  {
+    threads.emplace_back(worker, g);
+  }
+  worker(0);
+  for (auto& thread : threads)
+  {
+    thread.join();
+  }
+  // the device that failed first-hand, not the ones that stood down because of it
+  for (const bool first_hand : {true, false})
+  {
+    for (int g = 0; g < num_devices; g++)
+    {
+      const bool stood_down = messages[static_cast<size_t>(g)] == "another device failed";
+      if (statuses[static_cast<size_t>(g)] != VGT_B200_OK && stood_down != first_hand)
+      {
+        SetLastError("device %d: %s", devices[g], messages[static_cast<size_t>(g)].c_str());
+        return statuses[static_cast<size_t>(g)];
+      }
+    }
+  }
+  if (out_min != nullptr)
+  {
+    *out_min = *std::min_element(minima.begin(), minima.end());
+  }
+  if (out_max != nullptr)
+  {
+    *out_max = *std::max_element(maxima.begin(), maxima.end());
+  }
+  return VGT_B200_OK;
+}
+
 // ComputeDistanceFieldTransformInPlace on a host double field: see edt_transform.cuh.
 int TransformFieldInPlace(double* h_field, int64_t nx, int64_t ny, int64_t nz)
 {
@@ -1580,6 +1867,15 @@ int vgt_b200_sdf_f32(
 {
   return SdfFromHost<float, kEmitFloat>(occupancy, nx, ny, nz, resolution, unknown_is_filled,
                                         add_virtual_border, device, sdf_out, out_min, out_max);
+}
+
+int vgt_b200_sdf_f32_multi(
+    const float* occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
+    int unknown_is_filled, int add_virtual_border, const int* devices, int num_devices,
+    float* sdf_out, float* out_min, float* out_max)
+{
+  return SdfMultiDevice(occupancy, nx, ny, nz, resolution, unknown_is_filled, add_virtual_border,
+                        devices, num_devices, sdf_out, out_min, out_max);
 }
 
 int vgt_b200_sdf_f64(

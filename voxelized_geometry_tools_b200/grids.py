@@ -252,13 +252,25 @@ class OccupancyMap:
 
     # --- the path's entry points (occupancy_map.hpp:174-216, occupancy_map.cpp:250-260) ----
     def ExtractSignedDistanceField(self, parameters: SignedDistanceFieldGenerationParameters,
-                                   dtype=np.float32, device: int = 0) -> SignedDistanceField:
-        _capi.require_device(device)
+                                   dtype=np.float32, device: int = 0,
+                                   devices=None) -> SignedDistanceField:
+        """devices (float32 only): several device ordinals -> the slab-sharded multi-device call
+        (vgt_b200_sdf_f32_multi), same result bit for bit."""
+        _capi.require_device(device if not devices else int(devices[0]))
         lib = _capi.library()
         occupancy = self._data
         nx, ny, nz = self._sizes.shape
         out = np.empty(self._sizes.shape, dtype=dtype)
-        if np.dtype(dtype) == np.float32:
+        if devices and len(devices) > 1:
+            if np.dtype(dtype) != np.float32:
+                raise ValueError("the multi-device entry produces SignedDistanceField<float>")
+            lo, hi = ctypes.c_float(), ctypes.c_float()
+            listed = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            code = lib.vgt_b200_sdf_f32_multi(
+                occupancy.ctypes.data, nx, ny, nz, self._sizes.voxel_size,
+                int(parameters.UnknownIsFilled()), int(parameters.AddVirtualBorder()), listed,
+                len(devices), out.ctypes.data, ctypes.byref(lo), ctypes.byref(hi))
+        elif np.dtype(dtype) == np.float32:
             lo, hi = ctypes.c_float(), ctypes.c_float()
             code = lib.vgt_b200_sdf_f32(
                 occupancy.ctypes.data, nx, ny, nz, self._sizes.voxel_size,
@@ -279,8 +291,8 @@ class OccupancyMap:
         sdf.Lock()
         return sdf
 
-    def ExtractSignedDistanceFieldFloat(self, parameters, device: int = 0):
-        return self.ExtractSignedDistanceField(parameters, np.float32, device)
+    def ExtractSignedDistanceFieldFloat(self, parameters, device: int = 0, devices=None):
+        return self.ExtractSignedDistanceField(parameters, np.float32, device, devices)
 
     def ExtractSignedDistanceFieldDouble(self, parameters, device: int = 0):
         return self.ExtractSignedDistanceField(parameters, np.float64, device)
