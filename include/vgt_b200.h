@@ -16,7 +16,10 @@
  *     DEVICE pointers on `device` plus a cudaStream_t (passed as void*; NULL = legacy default
  *     stream) and never synchronise the host unless stated.
  *   - all functions may be called concurrently from several host threads (each call sets the
- *     device it needs; there is no global mutable state besides the thread-local error string).
+ *     device it needs and works on its own streams and buffers). Process-wide state is limited
+ *     to mutex-protected caches that cannot change a result: the pinned staging slots and host
+ *     copy threads of the host-pointer entries, the A/B switches read once from the environment
+ *     (vgt_b200_reload_tuning) and a launch counter; the error string is thread-local.
  *   - there is NO CPU fallback: without a usable CUDA device every compute call fails with
  *     VGT_B200_ERR_DEVICE.
  */
@@ -49,6 +52,12 @@ enum
 
 VGT_B200_API const char* vgt_b200_last_error(void);
 VGT_B200_API const char* vgt_b200_version(void);
+
+/* Experiment / test aid (no reference counterpart). The library reads its VGT_B200_* A/B
+ * switches (which kernel variant serves the strided passes; none of them changes a result) from
+ * the environment once, at the first SDF call of the process. This re-reads them, for tests
+ * that force each variant inside one process. */
+VGT_B200_API void vgt_b200_reload_tuning(void);
 
 /* Measurement aid (no reference counterpart): the number of CUDA kernels this library has
  * launched in this process so far, over all threads and devices. bench.py reports the difference
@@ -369,7 +378,10 @@ VGT_B200_API int vgt_b200_voxelize_f64(
     const vgt_b200_cloud* clouds, int32_t num_clouds, const vgt_b200_filter_options* filter,
     int device, float* out_occupancy, int32_t* out_counts, double* out_seconds);
 
-/* vgt_b200_voxelize_f64 for float32 clouds (see vgt_b200_cloud_f32). */
+/* vgt_b200_voxelize_f64 for float32 clouds (see vgt_b200_cloud_f32): the same replacement of
+ * DoVoxelizePointClouds (src/.../cpu_pointcloud_voxelization.cpp:133-165) for clouds that arrive
+ * through the reference's PointCloud2 wrapper
+ * (include/.../pointcloud_voxelization_ros_interface.hpp:35-97). */
 VGT_B200_API int vgt_b200_voxelize_f32(
     const float* static_occupancy, int64_t nx, int64_t ny, int64_t nz, double voxel_size,
     const vgt_b200_cloud_f32* clouds, int32_t num_clouds, const vgt_b200_filter_options* filter,
@@ -388,7 +400,8 @@ VGT_B200_API int vgt_b200_raycast_f64_dev(
     double max_range, int64_t nx, int64_t ny, int64_t nz, double voxel_size, int device,
     int32_t* d_counts, void* stream);
 
-/* vgt_b200_raycast_f64_dev for device float[num_points*3] points. */
+/* vgt_b200_raycast_f64_dev for device float[num_points*3] points (DoRaycastPointCloud,
+ * src/.../cpu_pointcloud_voxelization.cpp:167-206, on widened float32 points). */
 VGT_B200_API int vgt_b200_raycast_f32_dev(
     const float* d_points_xyz, int64_t num_points, const double* x_gc /* host, 16 */,
     double max_range, int64_t nx, int64_t ny, int64_t nz, double voxel_size, int device,

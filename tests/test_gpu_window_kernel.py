@@ -22,22 +22,27 @@ pytestmark = pytest.mark.gpu
 ROUTES = [{"VGT_B200_WINDOW_BUDGET": "0"}, {"VGT_B200_WINDOW_BUDGET": "100000"},
           {"VGT_B200_WINDOW_BUDGET": "25"}, {"VGT_B200_ENVELOPE": "lean"},
           {"VGT_B200_WINDOW_PILOT": "0"}, {"VGT_B200_WINDOW_STAGE": "1"},
-          {"VGT_B200_WINDOW_STAGE": "0", "VGT_B200_WINDOW_PILOT": "0"}, {}]
+          {"VGT_B200_WINDOW_STAGE": "0", "VGT_B200_WINDOW_PILOT": "0"},
+          {"VGT_B200_WINDOW_RADIUS_Y": "8"}, {"VGT_B200_WINDOW_RADIUS_Y": "10"}, {}]
 
 
 @pytest.fixture(params=ROUTES, ids=lambda route: ",".join(f"{k}={v}" for k, v in route.items())
                 or "default")
 def route(request):
+    from voxelized_geometry_tools_b200 import _capi
     saved = {key: os.environ.get(key) for key in ("VGT_B200_WINDOW_BUDGET", "VGT_B200_ENVELOPE",
-                                                  "VGT_B200_WINDOW_PILOT", "VGT_B200_WINDOW_STAGE")}
+                                                  "VGT_B200_WINDOW_PILOT", "VGT_B200_WINDOW_STAGE",
+                                                  "VGT_B200_WINDOW_RADIUS_Y")}
     for key in saved:
         os.environ.pop(key, None)
     os.environ.update(request.param)
+    _capi.library().vgt_b200_reload_tuning()    # the switches are read once per process
     yield request.param
     for key, value in saved.items():
         os.environ.pop(key, None)
         if value is not None:
             os.environ[key] = value
+    _capi.library().vgt_b200_reload_tuning()
 
 
 def test_cluttered_grid(shared_library, oracle, route):

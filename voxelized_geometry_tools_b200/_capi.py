@@ -59,6 +59,7 @@ SIGNATURES = {
     "vgt_b200_version": (ctypes.c_char_p, []),
     "vgt_b200_device_count": (_int, []),
     "vgt_b200_kernel_launch_count": (ctypes.c_uint64, []),
+    "vgt_b200_reload_tuning": (None, []),
     "vgt_b200_sdf_f32": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int, _int, _vp, _f32p, _f32p]),
     "vgt_b200_sdf_f32_multi": (_int, [_vp, _i64, _i64, _i64, _dbl, _int, _int,
                                       ctypes.POINTER(ctypes.c_int), _int, _vp, _f32p, _f32p]),

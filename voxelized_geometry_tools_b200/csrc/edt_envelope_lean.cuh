@@ -1,16 +1,15 @@
 // The strided-axis envelope kernel (sm_100a): axes up to 8192 voxels.
 // Included by edt_kernels.cu after edt_device.cuh.
 //
-// Same algorithm and data layout as EnvelopeAxisInPlaceStackKernel (edt_envelope_inplace.cuh):
-// one lane owns one line, a warp owns 32 z-adjacent lines (every row access of the warp is one
+// One lane owns one line, a warp owns 32 z-adjacent lines (every row access of the warp is one
 // 128-byte segment), the Felzenszwalb-Huttenlocher stack of a line lives IN PLACE in the rows of
 // the line that were already consumed. Axes of at most 1024 voxels whose partial distances stay
 // below 2^21 pack an entry into the row itself (f << 10 | v); longer axes / larger distances keep
 // f in the row and v in a uint16 side array addressed exactly like the grid (kSplit, 2 more
-// bytes per voxel of scratch). What differs is the instruction
-// budget. The round-1 profile showed that kernel bound by issued instructions (~280 warp
-// instructions per row of 32 voxels), a third of them in branches taken by 1-4 lanes (run
-// boundaries, sweep advances) and another third in fixed per-row bookkeeping. Here:
+// bytes per voxel of scratch). The first version of this kernel was bound by issued
+// instructions (~280 warp instructions per row of 32 voxels), a third of them in branches taken
+// by 1-4 lanes (run boundaries, sweep advances) and another third in fixed per-row bookkeeping.
+// Here:
 //   * every address is one IMAD.WIDE.U32 (32-bit row index x 32-bit byte stride + 64-bit base);
 //   * phase 1 has ONE pop loop: at a class change the incoming site is the zero-height site of
 //     the boundary, otherwise the voxel's own site; the change-only work is a short branch;
@@ -30,7 +29,6 @@
 #pragma once
 
 #include "edt_device.cuh"
-#include "edt_envelope_inplace.cuh"
 
 namespace vgt_b200
 {
@@ -38,6 +36,13 @@ namespace edt
 {
 namespace
 {
+// One warp per tile of 32 adjacent lines, four tiles per block.
+constexpr int kLineWarpsPerBlock = 4;
+// Packed stack entries (f << 10 | v): axes up to 1024 voxels, partial distances below 2^21.
+constexpr int kInPlacePositionBits = 10;
+constexpr int kInPlaceMaxLength = 1 << kInPlacePositionBits;
+constexpr int64_t kInPlaceMaxInput = (int64_t{1} << (31 - kInPlacePositionBits)) - 1;
+
 // crossing(below, middle) >= crossing(middle, above), cross-multiplied; see MiddleIsHidden.
 template <bool kNarrow>
 __device__ __forceinline__ bool HiddenTest(int32_t below_v, int32_t below_h, int32_t middle_v,

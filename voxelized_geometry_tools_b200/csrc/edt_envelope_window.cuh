@@ -222,7 +222,10 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   // Class bits of the three chunks: bit 3 R - 1 - r' = class of row r' counted from the first
   // row of the previous chunk. The bits of the next chunk enter pair by pair (see below); bits
   // above 3 R are leftovers of older chunks and never reach a window.
-  uint64_t classes = 0;
+  // (one 32-bit register when the three chunks fit, i.e. R <= 10: every class operation is then
+  // a single instruction instead of a 64-bit pair)
+  using ClassWord = typename std::conditional<(3 * kR <= 32), uint32_t, uint64_t>::type;
+  ClassWord classes = 0;
   // The rows of the next chunk as loaded. Rows j, j + 1 (j even) of it are needed from row j of
   // the current chunk on, so they are absorbed (clamped, packed, class bits filed) right there,
   // and each register is reloaded with the row one chunk further after its own row: every load
@@ -410,78 +413,33 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     char* const write_base =
         write_origin + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(base);
     uint32_t best_pairs[kPairs];
-    uint32_t even_best = 0;
     // ---------------------------------------------------------------------------------- phase A
+    // The next chunk (rows base + R .. base + 2 R - 1) joins the register window: clamped, packed
+    // in pairs, class bits filed. Then the loads of the chunk after it are issued: they have
+    // the whole chunk to land.
+#pragma unroll
+    for (int j = 0; j < kR; j += 2)
+    {
+      const uint32_t low_word =
+          kStage ? stage_lane[(absorb_buffer * kR + j) * kWarp] : raw[kStage ? 0 : j];
+      const uint32_t high_word =
+          kStage ? stage_lane[(absorb_buffer * kR + j + 1) * kWarp] : raw[kStage ? 0 : j + 1];
+      uint32_t low = clamped_value(low_word);
+      uint32_t high = clamped_value(high_word);
+      if constexpr (kEdge)
+      {
+        low = (base + j + kR > last_row) ? kSaturated : low;
+        high = (base + j + kR + 1 > last_row) ? kSaturated : high;
+      }
+      next_pairs[j >> 1] = __byte_perm(low, high, 0x5410);
+      classes |= (static_cast<ClassWord>(low_word >> 31) << (kR - 1 - j))
+          | (static_cast<ClassWord>(high_word >> 31) << (kR - 2 - j));
+    }
 #pragma unroll
     for (int j = 0; j < kR; j++)
     {
-      const int q = base + j;
-      if ((j & 1) == 0)
-      {
-        // rows j, j + 1 of the next chunk (rows q + R, q + R + 1 of the line): needed from here on
-        const uint32_t low_word =
-            kStage ? stage_lane[(absorb_buffer * kR + j) * kWarp] : raw[kStage ? 0 : j];
-        const uint32_t high_word =
-            kStage ? stage_lane[(absorb_buffer * kR + j + 1) * kWarp] : raw[kStage ? 0 : j + 1];
-        uint32_t low = clamped_value(low_word);
-        uint32_t high = clamped_value(high_word);
-        if constexpr (kEdge)
-        {
-          low = (q + kR > last_row) ? kSaturated : low;
-          high = (q + kR + 1 > last_row) ? kSaturated : high;
-        }
-        next_pairs[j >> 1] = __byte_perm(low, high, 0x5410);
-        classes |= (static_cast<uint64_t>(low_word >> 31) << (kR - 1 - j))
-            | (static_cast<uint64_t>(high_word >> 31) << (kR - 2 - j));
-      }
-      // (a row past the end of the line: 0, so that it never asks for a search)
-      uint32_t best = 0;
-      if (!kEdge || q <= last_row)  // warp-uniform
-      {
-        // Pairs g = (j >> 1) .. (j >> 1) + R of the 3 R / 2 pairs in registers cover the rows
-        // q - R .. q + R plus one row at distance R + 1 (a true candidate like the others).
-        // Two accumulators: half the dependent chain.
-        uint32_t chains[2] = {0xffffffffu, 0xffffffffu};
-#pragma unroll
-        for (int t = 0; t <= kR; t++)
-        {
-          const int g = (j >> 1) + t;                 // pair index, 0 .. 3 R / 2 - 1
-          const int low_row = 2 * g - kR;             // chunk-relative row of the low half
-          const int d_low = (j > low_row) ? j - low_row : low_row - j;
-          const int d_high = (j > low_row + 1) ? j - low_row - 1 : low_row + 1 - j;
-          const uint32_t offsets =
-              static_cast<uint32_t>(d_low * d_low) | (static_cast<uint32_t>(d_high * d_high) << 16);
-          const uint32_t pair = (g < kPairs)
-              ? previous_pairs[(g < kPairs) ? g : 0]
-              : ((g < 2 * kPairs) ? current_pairs[(g >= kPairs && g < 2 * kPairs) ? g - kPairs : 0]
-                                  : next_pairs[(g >= 2 * kPairs) ? g - 2 * kPairs : 0]);
-          chains[t & 1] = __viaddmin_u16x2(pair, offsets, chains[t & 1]);
-        }
-        const uint32_t best_pair = __vminu2(chains[0], chains[1]);
-        const uint32_t window_best = min(best_pair & 0xffffu, best_pair >> 16);
-        // class window of row q: bit R = row q, bit R - d = row q + d, bit R + d = row q - d
-        const uint32_t window = static_cast<uint32_t>(classes >> (kR - 1 - j));
-        const uint32_t same =
-            static_cast<uint32_t>(static_cast<int32_t>(window << (31 - kR)) >> 31);
-        const uint32_t differs = window ^ same;
-        // rows at distance d on either side folded onto bit R - d; the highest set bit = nearest
-        const uint32_t folded = (differs | (__brev(differs) >> (31 - 2 * kR))) & kSideMask;
-        const int nearest = kR - 31 + __clz(static_cast<int>(folded));
-        // (no opposite-class row inside the window: no such candidate)
-        const uint32_t nearest_squared =
-            (folded != 0u) ? static_cast<uint32_t>(nearest * nearest) : 0xffffu;
-        best = min(window_best, nearest_squared);
-      }
-      if ((j & 1) == 0)
-      {
-        even_best = best;
-      }
-      else
-      {
-        best_pairs[j >> 1] = __byte_perm(even_best, best, 0x5410);
-      }
-      // raw[j] was absorbed (at row j or j - 1): reload it (kStage: fetch row j of the chunk
-      // three ahead into the buffer whose rows were absorbed during the previous chunk)
+      // (kStage: row j of the chunk three ahead goes into the buffer whose rows were absorbed
+      // during the previous chunk)
       const char* const next_row = kEdge
           ? line + static_cast<uint64_t>(stride_bytes)
               * static_cast<uint32_t>(min(base + kAhead * kR + j, last_row))
@@ -500,6 +458,84 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       CommitAsyncCopies();
       fill_buffer = absorb_buffer;
       absorb_buffer = (absorb_buffer == 2) ? 0 : absorb_buffer + 1;
+    }
+    // Every row's window minimum, and (kWithClasses) the nearest opposite-class row inside its
+    // window. Chunks in which every lane's three register chunks are of ONE class - the bulk of
+    // free space and of the inside of obstacles - skip the class arithmetic altogether.
+    const auto window_rows = [&](auto with_classes)
+    {
+      constexpr bool kWithClasses = decltype(with_classes)::value;
+      uint32_t even_best = 0;
+#pragma unroll
+      for (int j = 0; j < kR; j++)
+      {
+        const int q = base + j;
+        // (a row past the end of the line: 0, so that it never asks for a search)
+        uint32_t best = 0;
+        if (!kEdge || q <= last_row)  // warp-uniform
+        {
+          // Pairs g = (j >> 1) .. (j >> 1) + R of the 3 R / 2 pairs in registers cover the rows
+          // q - R .. q + R plus one row at distance R + 1 (a true candidate like the others).
+          // Two accumulators: half the dependent chain.
+          uint32_t chains[2] = {0xffffffffu, 0xffffffffu};
+#pragma unroll
+          for (int t = 0; t <= kR; t++)
+          {
+            const int g = (j >> 1) + t;                 // pair index, 0 .. 3 R / 2 - 1
+            const int low_row = 2 * g - kR;             // chunk-relative row of the low half
+            const int d_low = (j > low_row) ? j - low_row : low_row - j;
+            const int d_high = (j > low_row + 1) ? j - low_row - 1 : low_row + 1 - j;
+            const uint32_t offsets = static_cast<uint32_t>(d_low * d_low)
+                | (static_cast<uint32_t>(d_high * d_high) << 16);
+            const uint32_t pair = (g < kPairs)
+                ? previous_pairs[(g < kPairs) ? g : 0]
+                : ((g < 2 * kPairs)
+                       ? current_pairs[(g >= kPairs && g < 2 * kPairs) ? g - kPairs : 0]
+                       : next_pairs[(g >= 2 * kPairs) ? g - 2 * kPairs : 0]);
+            chains[t & 1] = __viaddmin_u16x2(pair, offsets, chains[t & 1]);
+          }
+          const uint32_t best_pair = __vminu2(chains[0], chains[1]);
+          best = min(best_pair & 0xffffu, best_pair >> 16);
+          if constexpr (kWithClasses)
+          {
+            // class window of row q: bit R = row q, bit R - d = row q + d, bit R + d = row q - d
+            const uint32_t window = static_cast<uint32_t>(classes >> (kR - 1 - j));
+            const uint32_t same =
+                static_cast<uint32_t>(static_cast<int32_t>(window << (31 - kR)) >> 31);
+            const uint32_t differs = window ^ same;
+            // rows at distance d on either side folded onto bit R - d; highest set bit = nearest
+            const uint32_t folded = (differs | (__brev(differs) >> (31 - 2 * kR))) & kSideMask;
+            const int nearest = kR - 31 + __clz(static_cast<int>(folded));
+            // (no opposite-class row inside the window: no such candidate)
+            const uint32_t nearest_squared =
+                (folded != 0u) ? static_cast<uint32_t>(nearest * nearest) : 0xffffu;
+            best = min(best, nearest_squared);
+          }
+        }
+        if ((j & 1) == 0)
+        {
+          even_best = best;
+        }
+        else
+        {
+          best_pairs[j >> 1] = __byte_perm(even_best, best, 0x5410);
+        }
+      }
+    };
+    bool one_class_everywhere = false;
+    if constexpr (!kEdge)
+    {
+      constexpr ClassWord kSpan = (static_cast<ClassWord>(1) << (3 * kR)) - 1;
+      const ClassWord span = classes & kSpan;
+      one_class_everywhere = __all_sync(0xffffffffu, span == 0 || span == kSpan);
+    }
+    if (one_class_everywhere)
+    {
+      window_rows(std::false_type{});
+    }
+    else
+    {
+      window_rows(std::true_type{});
     }
     // ---------------------------------------------------------------------------------- phase B
     // The largest result of this lane's rows: a row is certified iff its result is below kFar.

@@ -1,6 +1,7 @@
 // Host orchestration + C-ABI entry points of the occupancy -> SignedDistanceField path (sm_100a).
-// Device code: edt_device.cuh (z scan, shared-memory envelope fallback, finalize helpers) and
-// edt_envelope_inplace.cuh (the fast envelope kernel). DESIGN.md has the roofline of each kernel.
+// Device code: edt_scan_registers.cuh / edt_device.cuh (z scan, finalize helpers),
+// edt_envelope_window.cuh (the strided passes) and edt_envelope_lean.cuh (the stack kernel behind
+// it). DESIGN.md has the roofline of each kernel.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -16,7 +17,6 @@
 #include "common.cuh"
 #include "host_transfer.cuh"
 #include "edt_device.cuh"
-#include "edt_envelope_inplace.cuh"
 #include "edt_envelope_lean.cuh"
 #include "edt_envelope_window.cuh"
 #include "edt_scan_registers.cuh"
@@ -87,33 +87,6 @@ int LaunchScan(const In* d_in, uint32_t* d_out, int64_t num_lines, int32_t lengt
   ScanContiguousAxisKernel<In><<<static_cast<unsigned>(blocks), kScanWarpsPerBlock * kWarp, smem,
                                  stream>>>(d_in, d_out, num_lines, length, unknown_is_filled); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "ScanContiguousAxisKernel launch");
-  return VGT_B200_OK;
-}
-
-template <int kMode, bool kSplit>
-int LaunchEnvelopeInPlaceStack(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
-                               uint16_t* d_positions, const LineFamily& family,
-                               const FinalizeParams& finalize,
-                               typename OutputOf<kMode>::Key* d_keys, cudaStream_t stream)
-{
-  const int num_words = (family.length + 31) >> 5;
-  const size_t smem = sizeof(uint32_t) * num_words * kWarp * kLineWarpsPerBlock;
-  const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
-  const int64_t blocks = (tiles + kLineWarpsPerBlock - 1) / kLineWarpsPerBlock;
-  if (blocks > 0x7fffffffLL)
-  {
-    return FailInvalid("grid too large for one launch");
-  }
-  auto kernel = EnvelopeAxisInPlaceStackKernel<kMode, kSplit>;
-  if (smem > 48 * 1024)
-  {
-    VGT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)),
-                 "EnvelopeAxisInPlaceStackKernel smem attribute");
-  }
-  kernel<<<static_cast<unsigned>(blocks), kLineWarpsPerBlock * kWarp, smem, stream>>>(
-      d_in, d_out, d_positions, family, finalize, d_keys); NoteKernelLaunch();
-  VGT_CUDA_TRY(cudaGetLastError(), "EnvelopeAxisInPlaceStackKernel launch");
   return VGT_B200_OK;
 }
 
@@ -223,35 +196,68 @@ int LaunchEnvelopeLean(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
   }
 }
 
-// Debug / A-B switch: VGT_B200_ENVELOPE=inplace forces the round-1 kernel, =lean the stack kernel
-// without the window kernel in front of it.
-// (read at every call, so a test can flip it inside one process)
-inline const char* EnvelopeChoice()
+// A/B switches of the strided passes, for experiments and for the tests that force each route.
+// The environment is read ONCE, at the first SDF call of the process; vgt_b200_reload_tuning()
+// re-reads it (tests flip the variables inside one process). Snapshots are immutable and never
+// freed (a reload leaks one small struct), so concurrent calls read them without locking.
+//   VGT_B200_ENVELOPE=lean        the stack kernel alone, no window kernel in front of it
+//   VGT_B200_WINDOW_BUDGET=<pct>  joint-search rounds a warp may spend per row of its tile before
+//                                 it hands the tile to the stack kernel, in percent (2400 = 24
+//                                 per row on average; 0 = never search beyond the registers)
+//   VGT_B200_WINDOW_PILOT=0       no pilot launch in front of the window kernel
+//   VGT_B200_WINDOW_STAGE=0|1     rows ahead by plain loads / through shared memory (cp.async)
+//   VGT_B200_WINDOW_RADIUS_Y=8|10|12  register-window radius of the plain y pass
+struct Tuning
 {
-  const char* value = std::getenv("VGT_B200_ENVELOPE");
-  return value == nullptr ? "" : value;
+  bool window_enabled = true;
+  uint32_t step_rate = 2400u * 128u / 100u;
+  bool pilot = true;
+  int stage = -1;      // -1: each pass its measured best
+  int radius_y = 0;    // 0: the default
+};
+
+inline const Tuning* LoadTuning()
+{
+  Tuning* tuning = new Tuning();
+  const char* envelope = std::getenv("VGT_B200_ENVELOPE");
+  tuning->window_enabled = !(envelope != nullptr && std::strcmp(envelope, "lean") == 0);
+  if (const char* budget = std::getenv("VGT_B200_WINDOW_BUDGET"))
+  {
+    // (capped so that rate x rows of the longest segment stays inside 32 bits)
+    const long percent = std::strtol(budget, nullptr, 10);
+    tuning->step_rate =
+        static_cast<uint32_t>(std::min(std::max(0L, percent), 100000L) * 128 / 100);
+  }
+  const char* pilot = std::getenv("VGT_B200_WINDOW_PILOT");
+  tuning->pilot = !(pilot != nullptr && std::strcmp(pilot, "0") == 0);
+  const char* stage = std::getenv("VGT_B200_WINDOW_STAGE");
+  if (stage != nullptr && (std::strcmp(stage, "0") == 0 || std::strcmp(stage, "1") == 0))
+  {
+    tuning->stage = stage[0] - '0';
+  }
+  if (const char* radius = std::getenv("VGT_B200_WINDOW_RADIUS_Y"))
+  {
+    tuning->radius_y = std::atoi(radius);
+  }
+  return tuning;
 }
 
-inline bool LeanEnvelopeEnabled()
-{
-  return std::strcmp(EnvelopeChoice(), "inplace") != 0;
-}
+std::atomic<const Tuning*> g_tuning{nullptr};
 
-inline bool WindowEnvelopeEnabled()
+inline const Tuning& CurrentTuning()
 {
-  return LeanEnvelopeEnabled() && std::strcmp(EnvelopeChoice(), "lean") != 0;
-}
-
-// Extended-search steps a warp of the window kernel may spend per row of its tile before it
-// hands the tile to the stack kernel, in 1/128 steps (VGT_B200_WINDOW_BUDGET overrides, in
-// percent: 2400 = 24 steps per row on average; 0 = no extended search at all). Rows deeper than
-// max(64, line length / 8) give their tile up at once, whatever the rate.
-inline uint32_t WindowStepRate()
-{
-  const char* value = std::getenv("VGT_B200_WINDOW_BUDGET");
-  const long percent = value == nullptr ? 2400L : std::strtol(value, nullptr, 10);
-  // (capped so that rate x rows of the longest segment stays inside 32 bits)
-  return static_cast<uint32_t>(std::min(std::max(0L, percent), 100000L) * 128 / 100);
+  const Tuning* tuning = g_tuning.load(std::memory_order_acquire);
+  if (tuning == nullptr)
+  {
+    const Tuning* loaded = LoadTuning();
+    if (g_tuning.compare_exchange_strong(tuning, loaded, std::memory_order_acq_rel))
+    {
+      return *loaded;
+    }
+    delete loaded;  // another thread was first
+    return *tuning;
+  }
+  return *tuning;
 }
 
 // Largest finite partial squared distance the lean kernel's 32-bit sentinels leave room for
@@ -288,17 +294,29 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
       family.line_stride * static_cast<int64_t>(sizeof(typename OutputOf<kMode>::Type)));
   derived.last_row = static_cast<uint32_t>(family.length - 1);
   derived.num_words = static_cast<uint32_t>((family.length + 31) >> 5);
-  const uint32_t step_rate = WindowStepRate();
+  const Tuning& tuning = CurrentTuning();
+  const uint32_t step_rate = tuning.step_rate;
   // Lines are cut into segments so that there are about six waves of blocks (and never
   // segments shorter than eight chunks; measured at 512^3: 1.68 ms with one segment per line,
   // 1.49 ms with four): the block scheduler then balances tiles of uneven depth
   // and the last wave is thin. A segment re-reads 2 R rows of its neighbours.
   constexpr int kRadius = (kMode == kEmitPacked) ? kWindowRadiusPacked : kWindowRadiusFinal;
-  const int64_t chunks = (family.length + kRadius - 1) / kRadius;
+  // Rows reach the registers either by plain loads one chunk ahead (the y pass: 0.59 ms against
+  // 0.61 staged at 512^3) or through shared memory with cp.async two chunks ahead (the finalizing
+  // x pass: 0.62 ms against 0.66). VGT_B200_WINDOW_STAGE=0 / 1 forces one variant for both.
+  const bool staged = tuning.stage >= 0 ? tuning.stage == 1 : kMode != kEmitPacked;
+  // (experiment knob: the radius of the plain, unstaged y pass)
+  int radius = kRadius;
+  if (kMode == kEmitPacked && family.out_parts == 0 && !staged
+      && (tuning.radius_y == 8 || tuning.radius_y == 10))
+  {
+    radius = tuning.radius_y;
+  }
+  const int64_t chunks = (family.length + radius - 1) / radius;
   const int64_t wanted_blocks = MultiprocessorCount() * 192 / kWindowWarpsPerBlock;
   int64_t segments = (wanted_blocks + blocks - 1) / blocks;
   segments = std::max<int64_t>(1, std::min<int64_t>(segments, chunks / 8));
-  const int segment_rows = static_cast<int>((chunks + segments - 1) / segments) * kRadius;
+  const int segment_rows = static_cast<int>((chunks + segments - 1) / segments) * radius;
   segments = (family.length + segment_rows - 1) / segment_rows;
   derived.first_segment = 0;
   if (family.out_parts > 1 && family.scatter_base[0] != nullptr)
@@ -312,9 +330,7 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
     derived.first_segment = static_cast<uint32_t>((row / segment_rows) % segments);
   }
   // (VGT_B200_WINDOW_PILOT=0: no pilot, the window kernel works on every tile)
-  const char* pilot_choice = std::getenv("VGT_B200_WINDOW_PILOT");
-  const bool pilot = tiles >= 16 * static_cast<int64_t>(kPilotStride)
-      && !(pilot_choice != nullptr && std::strcmp(pilot_choice, "0") == 0);
+  const bool pilot = tiles >= 16 * static_cast<int64_t>(kPilotStride) && tuning.pilot;
   const auto launch = [&](auto kernel)
   {
     const dim3 threads(kWindowWarpsPerBlock * kWarp);
@@ -331,20 +347,13 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
         std::min<int64_t>(pilot_blocks * kWindowWarpsPerBlock, tiles) * probes_per_line;
     kernel<<<dim3(static_cast<unsigned>(pilot_blocks), static_cast<unsigned>(probes_per_line)),
              threads, 0, stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list,
-                                   std::min(step_rate, kPilotStepRate), 2 * kRadius, kPilotSpacing,
+                                   std::min(step_rate, kPilotStepRate), 2 * radius, kPilotSpacing,
                                    kSelectPilot); NoteKernelLaunch();
     DecideWindowModeKernel<<<1, 1, 0, stream>>>(d_redo_list, static_cast<uint32_t>(pilot_probes)); NoteKernelLaunch();
     kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)), threads, 0,
              stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list, step_rate,
                        segment_rows, segment_rows, kSelectAfterPilot); NoteKernelLaunch();
   };
-  // Rows reach the registers either by plain loads one chunk ahead (the y pass: 0.59 ms against
-  // 0.61 staged at 512^3) or through shared memory with cp.async two chunks ahead (the finalizing
-  // x pass: 0.62 ms against 0.66). VGT_B200_WINDOW_STAGE=0 / 1 forces one variant for both.
-  const char* stage_choice = std::getenv("VGT_B200_WINDOW_STAGE");
-  const bool forced = stage_choice != nullptr
-      && (std::strcmp(stage_choice, "0") == 0 || std::strcmp(stage_choice, "1") == 0);
-  const bool staged = forced ? stage_choice[0] == '1' : kMode != kEmitPacked;
   if constexpr (kMode == kEmitPacked)
   {
     if (family.out_parts > 0)
@@ -357,7 +366,18 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
     }
     else
     {
-      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, false, kWindowBlocksPacked>);
+      if (radius == 8)
+      {
+        launch(EnvelopeAxisWindowKernel<kMode, 8, false, false, 32>);
+      }
+      else if (radius == 10)
+      {
+        launch(EnvelopeAxisWindowKernel<kMode, 10, false, false, 32>);
+      }
+      else
+      {
+        launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, false, kWindowBlocksPacked>);
+      }
     }
   }
   else if (family.out_parts > 0)
@@ -388,9 +408,9 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
 }
 
 // One strided-axis pass. d_in is DESTROYED and must not alias d_out.
-// max_input: largest finite partial squared distance the pass can see. Short axes use packed
-// 32-bit stack entries; longer ones keep the site positions in a stream-ordered uint16 side array.
-// The window kernel runs first and the stack kernel only redoes the tiles it gave up on.
+// max_input: largest finite partial squared distance the pass can see. The window kernel runs
+// first and the stack kernel only redoes the tiles it gave up on (short axes with packed 32-bit
+// stack entries; longer ones keep the site positions in a stream-ordered uint16 side array).
 
 template <int kMode>
 int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
@@ -402,11 +422,16 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
     return FailInvalid("axis of %d voxels is out of range", family.length);
   }
   const bool packed = family.length <= kInPlaceMaxLength && max_input <= kInPlaceMaxInput;
-  const bool lean = LeanEnvelopeEnabled() && family.line_stride * 8 <= 0xffffffffLL
-      && max_input <= kLeanMaxInput;
+  if (family.line_stride * 8 > 0xffffffffLL || max_input > kLeanMaxInput)
+  {
+    // (cannot happen for grids inside VGT_B200_MAX_AXIS: 2 * 8191^2 < 2^28)
+    SetLastError("partial distances up to %lld are outside the range of the integer passes",
+                 static_cast<long long>(max_input));
+    return VGT_B200_ERR_UNSUPPORTED;
+  }
   StreamScratch<uint32_t> redo;
   const uint32_t* d_redo_list = nullptr;
-  if (lean && WindowEnvelopeEnabled())
+  if (CurrentTuning().window_enabled)
   {
     const int64_t tiles = ((family.inner_count + kWarp - 1) / kWarp) * family.num_outer;
     VGT_CUDA_TRY(redo.Allocate(2 * tiles + kRedoList, stream), "envelope redo list");
@@ -418,7 +443,7 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
     }
     d_redo_list = redo.get();
   }
-  if (lean && packed)
+  if (packed)
   {
     // 32-bit pop test when no product of an h difference and a position difference can overflow.
     const int64_t max_h = max_input + Square(family.length - 1);
@@ -430,24 +455,14 @@ int LaunchEnvelope(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
     return LaunchEnvelopeLean<kMode, false, false>(d_in, d_out, nullptr, family, finalize, d_keys,
                                                    stream, d_redo_list);
   }
-  if (packed)
-  {
-    return LaunchEnvelopeInPlaceStack<kMode, false>(d_in, d_out, nullptr, family, finalize,
-                                                    d_keys, stream);
-  }
   // Longer axes / larger distances: site positions go to a stream-ordered uint16 side array
   // (2 bytes per voxel, span = the family's element span).
   const int64_t span = (family.num_outer - 1) * family.outer_stride
       + static_cast<int64_t>(family.length - 1) * family.line_stride + family.inner_count;
   StreamScratch<uint16_t> positions;
   VGT_CUDA_TRY(positions.Allocate(span, stream), "envelope position side array");
-  if (lean)
-  {
-    return LaunchEnvelopeLean<kMode, false, true>(d_in, d_out, positions.get(), family, finalize,
-                                                  d_keys, stream, d_redo_list);
-  }
-  return LaunchEnvelopeInPlaceStack<kMode, true>(d_in, d_out, positions.get(), family, finalize,
-                                                 d_keys, stream);
+  return LaunchEnvelopeLean<kMode, false, true>(d_in, d_out, positions.get(), family, finalize,
+                                                d_keys, stream, d_redo_list);
 }
 
 struct StreamGuard
@@ -1979,6 +1994,11 @@ int vgt_b200_edt_transform_inplace_f64(double* field, int64_t nx, int64_t ny, in
   VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
   KeepPoolMemory(device);
   return TransformFieldInPlace(field, nx, ny, nz);
+}
+
+void vgt_b200_reload_tuning(void)
+{
+  g_tuning.store(LoadTuning(), std::memory_order_release);
 }
 
 int vgt_b200_edt_sq_i32(
