@@ -1383,31 +1383,39 @@ int SdfMultiDevice(const float* h_in, int64_t nx, int64_t ny, int64_t nz, double
   const int64_t plane = ny * nz;
   const int64_t widest_part = (ny + num_devices - 1) / num_devices;
   const int64_t receive_words = nx * widest_part * nz;
-  // Receive buffers: plain cudaMalloc (peer-mapped once access is enabled), owned by this call.
+  // Receive buffers: plain cudaMalloc (peer-mapped once access is enabled; pool memory would
+  // need per-pool access grants). cudaMalloc / cudaFree of half a gigabyte per device and call
+  // costs more than the passes, so one buffer per device is kept for the life of the process
+  // and grows on demand; a call holds the cache lock while it uses them (multi-device calls of
+  // one process run one at a time).
+  static std::mutex receive_mutex;
+  static uint32_t* cached_buffer[64] = {};
+  static size_t cached_words[64] = {};
+  std::lock_guard<std::mutex> receive_lock(receive_mutex);
   std::vector<uint32_t*> receive(static_cast<size_t>(num_devices), nullptr);
-  struct ReceiveGuard
-  {
-    std::vector<uint32_t*>& buffers;
-    const int* devices;
-    ~ReceiveGuard()
-    {
-      for (size_t g = 0; g < buffers.size(); g++)
-      {
-        if (buffers[g] != nullptr)
-        {
-          ScopedDevice scoped(devices[g]);
-          cudaFree(buffers[g]);
-        }
-      }
-    }
-  } receive_guard{receive, devices};
   for (int g = 0; g < num_devices; g++)
   {
-    ScopedDevice scoped(devices[g]);
+    const int device = devices[g];
+    if (device < 0 || device >= 64)
+    {
+      return FailInvalid("device ordinal %d out of range", device);
+    }
+    ScopedDevice scoped(device);
     VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
-    VGT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&receive[static_cast<size_t>(g)]),
-                            sizeof(uint32_t) * static_cast<size_t>(receive_words)),
-                 "receive buffer allocation");
+    if (cached_words[device] < static_cast<size_t>(receive_words))
+    {
+      if (cached_buffer[device] != nullptr)
+      {
+        cudaFree(cached_buffer[device]);
+        cached_buffer[device] = nullptr;
+        cached_words[device] = 0;
+      }
+      VGT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&cached_buffer[device]),
+                              sizeof(uint32_t) * static_cast<size_t>(receive_words)),
+                   "receive buffer allocation");
+      cached_words[device] = static_cast<size_t>(receive_words);
+    }
+    receive[static_cast<size_t>(g)] = cached_buffer[device];
   }
   std::vector<uint64_t> peer_bases(static_cast<size_t>(num_devices));
   for (int g = 0; g < num_devices; g++)
@@ -1436,6 +1444,12 @@ int SdfMultiDevice(const float* h_in, int64_t nx, int64_t ny, int64_t nz, double
     StreamScratch<float> d_sdf;
     StreamScratch<float> d_min_max;
     StagedTransfer transfer;
+    if (num_devices >= 6)
+    {
+      // enough device threads to be the parallel copy workers themselves (the shared workers
+      // serve one caller at a time); with fewer devices the shared workers copy faster
+      transfer.UseCallingThreadOnly();
+    }
     // (runs first on every exit path: nothing is queued when the buffers are released)
     struct DrainOnExit
     {

@@ -35,6 +35,15 @@ public:
     return pool;
   }
 
+  // The same copy on the calling thread alone (callers that are themselves one of several
+  // parallel threads, e.g. the per-device threads of the multi-device entry: the shared workers
+  // serve one caller at a time and would serialise them).
+  static void Copy2DInline(char* dst, size_t dst_pitch, const char* src, size_t src_pitch,
+                           size_t row_bytes, size_t rows)
+  {
+    CopyRange(dst, dst_pitch, src, src_pitch, row_bytes, rows, 0, row_bytes * rows);
+  }
+
   // rows x row_bytes from src (pitch src_pitch) to dst (pitch dst_pitch), split over the workers.
   // Blocks until done.
   void Copy2D(char* dst, size_t dst_pitch, const char* src, size_t src_pitch, size_t row_bytes,
@@ -320,6 +329,9 @@ public:
     return ToHostRows(h_dst, h_pitch, d_src, d_pitch, row_bytes, rows, stream);
   }
 
+  // The host side of the staging runs on the calling thread alone instead of the shared workers.
+  void UseCallingThreadOnly() { inline_copies_ = true; }
+
   // True when ToHost(h_dst, ...) would go through the slots (and therefore block the caller).
   bool WouldStage(const void* host, size_t bytes) { return UseStaging(host, bytes); }
 
@@ -346,8 +358,7 @@ private:
           return waited;
         }
       }
-      HostCopyPool::Instance().Copy2D(slots_.slot(s), row_bytes, h_src + row * h_pitch, h_pitch,
-                                      row_bytes, piece_rows);
+      HostCopy(slots_.slot(s), row_bytes, h_src + row * h_pitch, h_pitch, row_bytes, piece_rows);
       cudaError_t status = Direct(d_dst + row * d_pitch, d_pitch, slots_.slot(s), row_bytes,
                                   row_bytes, piece_rows, cudaMemcpyHostToDevice, stream);
       if (status == cudaSuccess)
@@ -390,8 +401,8 @@ private:
       {
         return waited;
       }
-      HostCopyPool::Instance().Copy2D(h_dst + pending[s].row * h_pitch, h_pitch, slots_.slot(s),
-                                      row_bytes, row_bytes, pending[s].rows);
+      HostCopy(h_dst + pending[s].row * h_pitch, h_pitch, slots_.slot(s), row_bytes, row_bytes,
+               pending[s].rows);
       pending[s].valid = false;
       return cudaSuccess;
     };
@@ -460,6 +471,20 @@ private:
     return cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows, kind, stream);
   }
 
+  void HostCopy(char* dst, size_t dst_pitch, const char* src, size_t src_pitch, size_t row_bytes,
+                size_t rows)
+  {
+    if (inline_copies_)
+    {
+      HostCopyPool::Copy2DInline(dst, dst_pitch, src, src_pitch, row_bytes, rows);
+    }
+    else
+    {
+      HostCopyPool::Instance().Copy2D(dst, dst_pitch, src, src_pitch, row_bytes, rows);
+    }
+  }
+
+  bool inline_copies_ = false;
   StagingSlots slots_;
   bool used_[kStagingSlotsPerCall] = {};
   int next_slot_ = 0;
