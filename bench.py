@@ -45,13 +45,17 @@ PASS_NAMES = ["ScanContiguousAxisRegistersKernel (z)", "EnvelopeAxisWindowKernel
 NCU_TRAFFIC_FILE = REPO / "profiles" / "ncu_traffic.json"
 
 
-def ncu_dram_bytes_per_launch(dims, kernel):
+def ncu_dram_bytes_per_launch(dims, kernel, check_build=True):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
     `ncu --set full` capture of this very workload (profiles/ncu_traffic.json, written by
-    profiles/ncu_traffic.py from the .ncu-rep); None for anything not captured."""
+    profiles/ncu_traffic.py from the .ncu-rep); None for anything not captured, and None when
+    the capture was taken from another build (the table records the hash of the kernel sources)."""
     try:
         table = json.loads(NCU_TRAFFIC_FILE.read_text())
         entry = table["x".join(map(str, dims))][kernel]
+        from voxelized_geometry_tools_b200 import build as cuda_build
+        if check_build and entry.get("sources_sha1") != cuda_build._sources_signature():
+            return None     # captured from another build of the kernels: not this library's traffic
         return float(entry["dram_bytes_read"]) + float(entry["dram_bytes_write"])
     except Exception:
         return None

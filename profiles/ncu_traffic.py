@@ -39,6 +39,12 @@ for row in rows[2:]:
                           "report": Path(report).name}
 path = Path(__file__).resolve().parent / "ncu_traffic.json"
 table = json.loads(path.read_text()) if path.exists() else {}
+# The capture describes ONE build of the library: bench.py attaches these numbers only while the
+# kernel sources still hash to the same value (run this right after the capture, before editing).
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from voxelized_geometry_tools_b200 import build as cuda_build  # noqa: E402
+for entry in out.values():
+    entry["sources_sha1"] = cuda_build._sources_signature()
 table[f"{n}x{n}x{n}"] = out
 path.write_text(json.dumps(table, indent=1) + "\n")
 print(json.dumps(out, indent=1))

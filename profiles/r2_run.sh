@@ -10,7 +10,7 @@ cat gpurun_out/r2_gpu_tests.txt
 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
 tail -c 400 gpurun_out/r2_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference.json 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Kernel$' -c 900 --csv \
     --log-file gpurun_out/r2_launches.csv \
     python bench.py --steps 3 --warmup 3 --skip-cpu --skip-strong > gpurun_out/r2_launches_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'ScanContiguous|EnvelopeAxis' -c 8 \

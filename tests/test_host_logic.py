@@ -127,8 +127,15 @@ def test_bench_finds_the_ncu_traffic_of_every_pass():
     spec.loader.exec_module(bench)
     dims = bench.workload_dims(1)
     for name in bench.PASS_NAMES:
-        traffic = bench.ncu_dram_bytes_per_launch(dims, name)
+        traffic = bench.ncu_dram_bytes_per_launch(dims, name, check_build=False)
         assert traffic is not None, name
         voxels = dims[0] * dims[1] * dims[2]
         # between the algorithmic 8 B/voxel (minus what L2 keeps) and twice that
         assert 0.9 * bench.PASS_BYTES_PER_VOXEL * voxels < traffic < 2 * bench.PASS_BYTES_PER_VOXEL * voxels
+        # the numbers belong to ONE build of the kernels: with the build check on they are
+        # attached iff the table's source hash is the current one
+        import json
+        from voxelized_geometry_tools_b200 import build as cuda_build
+        entry = json.loads(bench.NCU_TRAFFIC_FILE.read_text())["x".join(map(str, dims))][name]
+        checked = bench.ncu_dram_bytes_per_launch(dims, name)
+        assert (checked is not None) == (entry.get("sources_sha1") == cuda_build._sources_signature())
