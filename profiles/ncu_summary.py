@@ -21,7 +21,19 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum ", "dram__bytes_write.su
         "smsp__pcsamp_warps_issue_stalled_mio_throttle ", "smsp__pcsamp_warps_issue_stalled_dispatch_stall ",
         "sm__inst_executed_pipe_fp64", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum ",
         "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum ", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum ",
-        "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum "]
+        "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum ",
+        # which pipe bounds the kernel
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active ",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active ",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active ",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active ",
+        # atomics (the raycast kernel): RED instructions, sectors at L2, share of the RED unit's peak
+        "smsp__inst_executed_op_global_red.sum ", "lts__t_sectors_srcunit_tex_op_red.sum ",
+        "lts__t_sectors_srcunit_tex_op_red.avg.pct_of_peak_sustained_elapsed ",
+        "lts__t_sectors_srcunit_tex_op_red_lookup_hit.sum ",
+        "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed ",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed ",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed "]
 
 report = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True,
