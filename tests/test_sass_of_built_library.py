@@ -53,9 +53,11 @@ def test_window_kernels_use_the_packed_add_min(sass_by_function):
     for name, sass in kernels.items():
         radius = int(re.search(r"EnvelopeAxisWindowKernelILi\dELi(\d+)E", name).group(1))
         packed = sass.count("VIADDMNMX.U16x2")
-        # two unrolled chunk bodies (interior / edge) x R rows x (R + 1) pairs
-        assert packed >= 2 * radius * (radius + 1), (name, packed)
-        assert "VIADDMNMX.U32" in sass, name          # the extended search
+        # three unrolled chunk bodies (interior with / without the class arithmetic, edge) x R
+        # rows x (R + 1) pairs, plus the chunk-joint search (register tier + four rows per side
+        # and round from memory, R / 2 paired add-mins each)
+        assert packed >= 3 * radius * (radius + 1) + 8 * (radius // 2), (name, packed)
+        assert "VIADDMNMX.U32" not in sass, name      # no row-by-row 32-bit search any more
         assert "BREV" in sass and "FLO" in sass, name  # nearest opposite-class row
 
 

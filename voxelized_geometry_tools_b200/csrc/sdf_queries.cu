@@ -10,7 +10,7 @@
 //   ProjectLocationOutOfCollisionToMinimumDistance4d :1159-1203
 //
 // THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false so that every expression below evaluates
-// as written (the numpy restatement in oracle/sdf_queries_oracle.py then matches bit for bit).
+// as written (the numpy restatement the tests check against then matches bit for bit).
 // What is pinned by the reference's own source and what is not:
 //   * the coarse gradient, the axis index selection, the half-cell correction, the fine-gradient
 //     window logic and the projection loop are in-tree arithmetic and are mirrored operation by
@@ -21,7 +21,7 @@
 //     as: ratio = (q - low) / (high - low) clamped to [0, 1]; Interpolate(a, b, r) =
 //     a * (1 - r) + b * r; x first, then y, then z. Another evaluation order changes the last
 //     bits only: the tests state 1e-12 relative as the tolerance of that one function against
-//     the library ("parity unpinned" for it), bit-exact against the restated oracle.
+//     the library ("parity unpinned" for it), bit-exact against the restatement.
 #include <cmath>
 
 #include "common.cuh"
@@ -52,7 +52,7 @@ struct Vec3
 };
 
 // Isometry3d * (p, 1): row r = ((m(r,0)*x + m(r,1)*y) + m(r,2)*z) + m(r,3) -- the fixed order of
-// the front ends (grids.compose_rigid, oracle/ref_shim/Eigen/Geometry).
+// the front ends (grids.compose_rigid).
 __device__ __forceinline__ Vec3 TransformPoint(const double* m, const Vec3& p)
 {
   return Vec3{((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12],

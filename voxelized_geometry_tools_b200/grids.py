@@ -35,7 +35,7 @@ def compose_rigid(a, b) -> np.ndarray:
     ((a[r,0]*b[0,c] + a[r,1]*b[1,c]) + a[r,2]*b[2,c]) + a[r,3]*b[3,c], no fused multiply-add.
     The voxelizer's counts depend on the last bits of X_GC = X_GW * X_WC
     (cpu_pointcloud_voxelization.cpp:172-176), and a BLAS matmul is free to sum in another
-    order; the C++ adapter, the oracle's stand-in for Eigen (oracle/ref_shim/Eigen/Geometry) and
+    order; the C++ adapter, the test suite's stand-in for Eigen (its header states the order) and
     this function all use this order (tests/test_oracle_vs_reference.py pins it)."""
     a = np.asarray(a, dtype=np.float64).reshape(4, 4)
     b = np.asarray(b, dtype=np.float64).reshape(4, 4)
@@ -49,7 +49,7 @@ def compose_rigid(a, b) -> np.ndarray:
 
 def inverse_rigid(transform) -> np.ndarray:
     """Inverse of a rigid transform: R^T and -(R^T t) with t summed left to right, as the
-    oracle's stand-in for Eigen::Isometry3d::inverse() does."""
+    test suite's stand-in for Eigen::Isometry3d::inverse() does."""
     m = np.asarray(transform, dtype=np.float64).reshape(4, 4)
     inverse = np.eye(4)
     for r in range(3):
