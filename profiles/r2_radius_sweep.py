@@ -15,8 +15,11 @@ dev = torch.device("cuda", 0)
 for n in (512, 1024):
     occupancy = synthetic.clustered_spheres_occupancy_torch((n, n, n), dev)
     reference = None
-    for radius in ("12", "10", "8"):
+    for radius, stage in (("12", ""), ("12", "1"), ("12", "2"), ("12", "0")):
         os.environ["VGT_B200_WINDOW_RADIUS_Y"] = radius
+        os.environ.pop("VGT_B200_WINDOW_STAGE", None)
+        if stage:
+            os.environ["VGT_B200_WINDOW_STAGE"] = stage
         _capi.library().vgt_b200_reload_tuning()
         out = torch.empty_like(occupancy)
         min_max = torch.empty(2, device=dev)
@@ -27,7 +30,7 @@ for n in (512, 1024):
         passes = [round(statistics.median(s[i] for s in samples), 4) for i in range(3)]
         if reference is None:
             reference = out.clone()
-        print(n, "radius", radius, "passes", passes, "total", round(sum(passes), 4),
+        print(n, "radius", radius, "stage", stage or "default", "passes", passes, "total", round(sum(passes), 4),
               "same", bool(torch.equal(out, reference)), flush=True)
     del occupancy, reference, out
     torch.cuda.empty_cache()

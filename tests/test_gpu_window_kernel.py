@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
 ROUTES = [{"VGT_B200_WINDOW_BUDGET": "0"}, {"VGT_B200_WINDOW_BUDGET": "100000"},
           {"VGT_B200_WINDOW_BUDGET": "25"}, {"VGT_B200_ENVELOPE": "lean"},
           {"VGT_B200_WINDOW_PILOT": "0"}, {"VGT_B200_WINDOW_STAGE": "1"},
+          {"VGT_B200_WINDOW_STAGE": "2"}, {"VGT_B200_WINDOW_STAGE": "2", "VGT_B200_WINDOW_PILOT": "0"},
           {"VGT_B200_WINDOW_STAGE": "0", "VGT_B200_WINDOW_PILOT": "0"},
           {"VGT_B200_WINDOW_RADIUS_Y": "8"}, {"VGT_B200_WINDOW_RADIUS_Y": "10"}, {}]
 

@@ -62,16 +62,24 @@ def test_window_kernels_use_the_packed_add_min(sass_by_function):
 
 
 def test_staged_window_kernels_use_async_copies(sass_by_function):
+    # kStage (the last template argument): 0 = register prefetch, 1 = per-lane cp.async
+    # (LDGSTS), 2 = cp.async.bulk through the TMA engine (UBLKCP) with mbarrier completion (SYNCS)
     kernels = functions_named(sass_by_function, "EnvelopeAxisWindowKernel")
-    staged = {k: v for k, v in kernels.items() if k.rstrip("_").find("ELb1EEEv") != -1
-              and re.search(r"ELi\d+ELb1EEEv", k)}
-    assert staged, "no staged (kStage = true) window kernel was instantiated"
-    for name, sass in kernels.items():
-        if name in staged:
-            assert "LDGSTS" in sass, name
-            assert "LDGDEPBAR" in sass or "DEPBAR" in sass, name
-        else:
-            assert "LDGSTS" not in sass, name
+    by_stage = {0: [], 1: [], 2: []}
+    for name in kernels:
+        stage = int(re.search(r"ELi\d+ELi(\d)EEEv", name).group(1))
+        by_stage[stage].append(name)
+    assert by_stage[0] and by_stage[1] and by_stage[2], {k: len(v) for k, v in by_stage.items()}
+    for name in by_stage[0]:
+        assert "LDGSTS" not in kernels[name] and "UBLKCP" not in kernels[name], name
+    for name in by_stage[1]:
+        assert "LDGSTS" in kernels[name], name
+        assert "LDGDEPBAR" in kernels[name] or "DEPBAR" in kernels[name], name
+        assert "UBLKCP" not in kernels[name], name
+    for name in by_stage[2]:
+        assert "UBLKCP" in kernels[name], name          # the bulk copies
+        assert "SYNCS" in kernels[name], name           # mbarrier init / arrive / try_wait
+        assert "LDGSTS" not in kernels[name], name
 
 
 def test_z_scan_moves_sixteen_bytes_per_lane(sass_by_function):

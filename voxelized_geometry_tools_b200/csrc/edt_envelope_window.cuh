@@ -94,6 +94,51 @@ __device__ __forceinline__ void WaitForAsyncCopies()
   asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
+// Bulk variant (kStage == 2): the same three chunk buffers, filled by the TMA engine. One
+// cp.async.bulk per row (128 contiguous bytes: the 32 columns of the tile), issued by lane j for
+// row j - ONE predicated instruction per chunk instead of R per-lane copies with their address
+// arithmetic - and one mbarrier per buffer armed with the bytes to expect; the warp waits on the
+// barrier's phase parity where the cp.async variant waits for a copy group. Needs rows that start
+// 16-byte aligned and full tiles (the launcher checks and falls back to kStage == 1).
+__device__ __forceinline__ uint32_t SharedAddress(const void* pointer)
+{
+  return static_cast<uint32_t>(__cvta_generic_to_shared(pointer));
+}
+__device__ __forceinline__ void BarrierInit(uint64_t* barrier, uint32_t arrivals)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SharedAddress(barrier)),
+               "r"(arrivals)
+               : "memory");
+}
+__device__ __forceinline__ void BarrierArriveExpectBytes(uint64_t* barrier, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   SharedAddress(barrier)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void BarrierWait(uint64_t* barrier, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred done;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
+      "@!done bra WAIT_LOOP;\n"
+      "}\n" ::"r"(SharedAddress(barrier)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void BulkCopyRow(uint32_t* shared_row, const void* global_row,
+                                            uint32_t bytes, uint64_t* barrier)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          SharedAddress(shared_row)),
+      "l"(global_row), "r"(bytes), "r"(SharedAddress(barrier))
+      : "memory");
+}
+
 // Deepest row distance the 16-bit joint search looks at: clamped values (0x3fff) plus squared
 // offsets must fit 16 bits and a result is only exact below kSaturated, i.e. up to 127 voxels.
 constexpr int kJointDeepestCap = 120;
@@ -140,7 +185,7 @@ __global__ void DecideWindowModeKernel(uint32_t* redo, uint32_t pilot_probes)
   redo[kRedoCount] = 0u;
 }
 
-template <int kMode, int kR, bool kBorder, bool kSend, int kBlocksPerSm, bool kStage = false>
+template <int kMode, int kR, bool kBorder, bool kSend, int kBlocksPerSm, int kStage = 0>
 __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     EnvelopeAxisWindowKernel(const uint32_t* __restrict__ in,
                              typename OutputOf<kMode>::Type* __restrict__ out, LineFamily family,
@@ -234,14 +279,80 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   // kStage: three chunk buffers of R rows x 32 lanes in shared memory instead (one warp per
   // block); absorb_buffer holds the next chunk, the one after it is in flight, fill_buffer takes
   // the chunk three ahead.
-  __shared__ uint32_t stage[kStage ? 3 * kR * kWarp : 1];
+  __shared__ alignas(128) uint32_t stage[kStage ? 3 * kR * kWarp : 1];
   static_assert(!kStage || kWindowWarpsPerBlock == 1, "the stage buffers are per block");
   uint32_t* const stage_lane = stage + lane;
   int absorb_buffer = 0;
   int fill_buffer = 2;
+  // kStage == 2: one mbarrier per buffer; bit b of wait_parity = the phase parity the next wait
+  // on buffer b looks for, bit b of in_flight = a fill of buffer b has not been waited for yet.
+  __shared__ alignas(8) uint64_t stage_barriers[kStage == 2 ? 3 : 1];
+  uint32_t wait_parity = 0;
+  uint32_t in_flight = 0;
+  if constexpr (kStage == 2)
+  {
+    if (lane == 0)
+    {
+#pragma unroll
+      for (int b = 0; b < 3; b++)
+      {
+        BarrierInit(stage_barriers + b, 1u);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
 
   const auto load_clamped = [&](const int row) { return load_row(min(max(row, 0), last_row)); };
   const auto clamped_value = [&](const uint32_t word) { return min(word & kNone, kSaturated); };
+
+  // kStage: the R rows starting at `first` (kClamp: clamped to the line) go into stage buffer
+  // `buffer`; and the wait for the rows of a buffer to have landed.
+  const auto fill_stage = [&](const int buffer, const int first, auto clamp)
+  {
+    constexpr bool kClamp = decltype(clamp)::value;
+    if constexpr (kStage == 1)
+    {
+#pragma unroll
+      for (int i = 0; i < kR; i++)
+      {
+        const int row = kClamp ? min(first + i, last_row) : first + i;
+        CopyRowAsync(stage_lane + (buffer * kR + i) * kWarp,
+                     line + static_cast<uint64_t>(static_cast<uint32_t>(row)) * stride_bytes);
+      }
+      CommitAsyncCopies();
+    }
+    else if constexpr (kStage == 2)
+    {
+      if (lane == 0)
+      {
+        BarrierArriveExpectBytes(stage_barriers + buffer, kR * kWarp * 4u);
+      }
+      if (lane < kR)
+      {
+        // lane i issues row i: 128 bytes from the tile's first column (line is this lane's own
+        // column; full tiles only, so the tile starts lane columns before it)
+        const int row = kClamp ? min(first + lane, last_row) : first + lane;
+        BulkCopyRow(stage + (buffer * kR + lane) * kWarp,
+                    line - 4 * lane + static_cast<uint64_t>(static_cast<uint32_t>(row)) * stride_bytes,
+                    kWarp * 4u, stage_barriers + buffer);
+      }
+      in_flight |= 1u << buffer;
+    }
+  };
+  const auto wait_for_stage = [&](const int buffer)
+  {
+    if constexpr (kStage == 1)
+    {
+      WaitForAsyncCopies<1>();  // everything but the newest group
+    }
+    else if constexpr (kStage == 2)
+    {
+      BarrierWait(stage_barriers + buffer, (wait_parity >> buffer) & 1u);
+      wait_parity ^= 1u << buffer;
+      in_flight &= ~(1u << buffer);
+    }
+  };
 
   // Extended-search steps of this warp so far (warp-uniform) and whether they have passed the
   // allowance of step_rate / 128 steps per row done (plus a credit of a quarter segment), or a
@@ -406,9 +517,9 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     constexpr int kAhead = kStage ? 3 : 2;
     const char* const read_next =
         line + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(base + kAhead * kR);
-    if constexpr (kStage)
+    if constexpr (kStage != 0)
     {
-      WaitForAsyncCopies<1>();  // everything but the newest group: the next chunk has landed
+      wait_for_stage(absorb_buffer);  // the next chunk has landed
     }
     char* const write_base =
         write_origin + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(base);
@@ -435,29 +546,25 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       classes |= (static_cast<ClassWord>(low_word >> 31) << (kR - 1 - j))
           | (static_cast<ClassWord>(high_word >> 31) << (kR - 2 - j));
     }
-#pragma unroll
-    for (int j = 0; j < kR; j++)
+    if constexpr (kStage != 0)
     {
-      // (kStage: row j of the chunk three ahead goes into the buffer whose rows were absorbed
-      // during the previous chunk)
-      const char* const next_row = kEdge
-          ? line + static_cast<uint64_t>(stride_bytes)
-              * static_cast<uint32_t>(min(base + kAhead * kR + j, last_row))
-          : read_next + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(j);
-      if constexpr (kStage)
-      {
-        CopyRowAsync(stage_lane + (fill_buffer * kR + j) * kWarp, next_row);
-      }
-      else
-      {
-        raw[j] = *reinterpret_cast<const uint32_t*>(next_row);
-      }
-    }
-    if constexpr (kStage)
-    {
-      CommitAsyncCopies();
+      // the chunk three ahead goes into the buffer whose rows were absorbed during the
+      // previous chunk
+      fill_stage(fill_buffer, base + kAhead * kR, std::integral_constant<bool, kEdge>{});
       fill_buffer = absorb_buffer;
       absorb_buffer = (absorb_buffer == 2) ? 0 : absorb_buffer + 1;
+    }
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < kR; j++)
+      {
+        const char* const next_row = kEdge
+            ? line + static_cast<uint64_t>(stride_bytes)
+                * static_cast<uint32_t>(min(base + kAhead * kR + j, last_row))
+            : read_next + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(j);
+        raw[j] = *reinterpret_cast<const uint32_t*>(next_row);
+      }
     }
     // Every row's window minimum, and (kWithClasses) the nearest opposite-class row inside its
     // window. Chunks in which every lane's three register chunks are of ONE class - the bulk of
@@ -742,21 +849,11 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       classes = (classes << 2) | ((low_word >> 31) << 1) | (high_word >> 31);
     }
     classes <<= kR;
-    if constexpr (kStage)
+    if constexpr (kStage != 0)
     {
-      // the next chunk into buffer 0, the one after it into buffer 1, one group each
-#pragma unroll
-      for (int ahead = 0; ahead < 2; ahead++)
-      {
-#pragma unroll
-        for (int i = 0; i < kR; i++)
-        {
-          const int row = min(first_row + (1 + ahead) * kR + i, last_row);
-          CopyRowAsync(stage_lane + (ahead * kR + i) * kWarp,
-                       line + static_cast<uint64_t>(static_cast<uint32_t>(row)) * stride_bytes);
-        }
-        CommitAsyncCopies();
-      }
+      // the next chunk into buffer 0, the one after it into buffer 1
+      fill_stage(0, first_row + kR, std::true_type{});
+      fill_stage(1, first_row + 2 * kR, std::true_type{});
     }
     else
     {
@@ -781,9 +878,21 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       compute_chunk(base, Edge{});
     }
     flush_pending();
-    if constexpr (kStage)
+    // nothing of this warp may still be in flight when it exits
+    if constexpr (kStage == 1)
     {
-      WaitForAsyncCopies<0>();  // nothing of this warp may still be in flight when it exits
+      WaitForAsyncCopies<0>();
+    }
+    else if constexpr (kStage == 2)
+    {
+#pragma unroll
+      for (int b = 0; b < 3; b++)
+      {
+        if ((in_flight >> b) & 1u)  // warp-uniform
+        {
+          wait_for_stage(b);
+        }
+      }
     }
   }
 

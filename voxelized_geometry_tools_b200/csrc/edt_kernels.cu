@@ -205,7 +205,8 @@ int LaunchEnvelopeLean(uint32_t* d_in, typename OutputOf<kMode>::Type* d_out,
 //                                 it hands the tile to the stack kernel, in percent (2400 = 24
 //                                 per row on average; 0 = never search beyond the registers)
 //   VGT_B200_WINDOW_PILOT=0       no pilot launch in front of the window kernel
-//   VGT_B200_WINDOW_STAGE=0|1     rows ahead by plain loads / through shared memory (cp.async)
+//   VGT_B200_WINDOW_STAGE=0|1|2   rows ahead by plain loads / through shared memory with per-lane
+//                                 cp.async / with cp.async.bulk (TMA engine) + mbarrier
 //   VGT_B200_WINDOW_RADIUS_Y=8|10|12  register-window radius of the plain y pass
 struct Tuning
 {
@@ -231,7 +232,8 @@ inline const Tuning* LoadTuning()
   const char* pilot = std::getenv("VGT_B200_WINDOW_PILOT");
   tuning->pilot = !(pilot != nullptr && std::strcmp(pilot, "0") == 0);
   const char* stage = std::getenv("VGT_B200_WINDOW_STAGE");
-  if (stage != nullptr && (std::strcmp(stage, "0") == 0 || std::strcmp(stage, "1") == 0))
+  if (stage != nullptr && (std::strcmp(stage, "0") == 0 || std::strcmp(stage, "1") == 0
+                           || std::strcmp(stage, "2") == 0))
   {
     tuning->stage = stage[0] - '0';
   }
@@ -301,10 +303,22 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   // 1.49 ms with four): the block scheduler then balances tiles of uneven depth
   // and the last wave is thin. A segment re-reads 2 R rows of its neighbours.
   constexpr int kRadius = (kMode == kEmitPacked) ? kWindowRadiusPacked : kWindowRadiusFinal;
-  // Rows reach the registers either by plain loads one chunk ahead (the y pass: 0.59 ms against
-  // 0.61 staged at 512^3) or through shared memory with cp.async two chunks ahead (the finalizing
-  // x pass: 0.62 ms against 0.66). VGT_B200_WINDOW_STAGE=0 / 1 forces one variant for both.
-  const bool staged = tuning.stage >= 0 ? tuning.stage == 1 : kMode != kEmitPacked;
+  // Rows reach the registers by plain loads one chunk ahead (stage 0, the default of both
+  // passes), or through shared memory two chunks ahead: by per-lane cp.async (stage 1), or filled
+  // by the TMA engine with one cp.async.bulk per row and an mbarrier per buffer (stage 2; needs
+  // rows that start 16-byte aligned and full tiles, else it falls back to stage 1). Measured at
+  // 512^3 with the up-front absorb of round 2 (profiles/r2_experiments.md): x pass 0.442 / 0.457
+  // / 0.510 ms, y pass 0.413 / 0.431 / 0.476 ms for stage 0 / 1 / 2 - the passes are bound by
+  // the alu pipe, not by how the rows arrive, and the staged variants add shared-memory reads
+  // and waits. VGT_B200_WINDOW_STAGE=0 / 1 / 2 forces a variant for both passes.
+  const bool bulk_ok = family.inner_count % kWarp == 0 && family.line_stride % 4 == 0
+      && family.outer_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d_in) % 16 == 0;
+  int stage_mode = tuning.stage >= 0 ? tuning.stage : 0;
+  if (stage_mode == 2 && !bulk_ok)
+  {
+    stage_mode = 1;
+  }
+  const bool staged = stage_mode != 0;
   // (experiment knob: the radius of the plain, unstaged y pass)
   int radius = kRadius;
   if (kMode == kEmitPacked && family.out_parts == 0 && !staged
@@ -331,7 +345,10 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   }
   // (VGT_B200_WINDOW_PILOT=0: no pilot, the window kernel works on every tile)
   const bool pilot = tiles >= 16 * static_cast<int64_t>(kPilotStride) && tuning.pilot;
-  const auto launch = [&](auto kernel)
+  // (pilot_kernel: the variant that runs the probe launch. In the probe every lane reads the
+  // family's last column - it stores nothing and only counts search effort -, which the bulk
+  // variant cannot do: its rows arrive as whole tiles. Its probe runs on the cp.async variant.)
+  const auto launch_with_pilot = [&](auto kernel, auto pilot_kernel)
   {
     const dim3 threads(kWindowWarpsPerBlock * kWarp);
     if (!pilot)
@@ -345,8 +362,9 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
     const int64_t probes_per_line = (family.length + kPilotSpacing - 1) / kPilotSpacing;
     const int64_t pilot_probes =
         std::min<int64_t>(pilot_blocks * kWindowWarpsPerBlock, tiles) * probes_per_line;
-    kernel<<<dim3(static_cast<unsigned>(pilot_blocks), static_cast<unsigned>(probes_per_line)),
-             threads, 0, stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list,
+    pilot_kernel<<<dim3(static_cast<unsigned>(pilot_blocks),
+                        static_cast<unsigned>(probes_per_line)),
+                   threads, 0, stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list,
                                    std::min(step_rate, kPilotStepRate), 2 * radius, kPilotSpacing,
                                    kSelectPilot); NoteKernelLaunch();
     DecideWindowModeKernel<<<1, 1, 0, stream>>>(d_redo_list, static_cast<uint32_t>(pilot_probes)); NoteKernelLaunch();
@@ -354,15 +372,22 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
              stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list, step_rate,
                        segment_rows, segment_rows, kSelectAfterPilot); NoteKernelLaunch();
   };
+  const auto launch = [&](auto kernel) { launch_with_pilot(kernel, kernel); };
   if constexpr (kMode == kEmitPacked)
   {
     if (family.out_parts > 0)
     {
       launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, true, kWindowBlocksPacked>);
     }
+    else if (stage_mode == 2)
+    {
+      launch_with_pilot(
+          EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, false, 32, 2>,
+          EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, false, 32, 1>);
+    }
     else if (staged)
     {
-      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, false, 32, true>);
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusPacked, false, false, 32, 1>);
     }
     else
     {
@@ -386,18 +411,28 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   }
   else if (finalize.add_virtual_border != 0)
   {
-    if (staged)
+    if (stage_mode == 2)
     {
-      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, false, 32, true>);
+      launch_with_pilot(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, false, 32, 2>,
+                        EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, false, 32, 1>);
+    }
+    else if (staged)
+    {
+      launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, false, 32, 1>);
     }
     else
     {
       launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, true, false, kWindowBlocksFinal>);
     }
   }
+  else if (stage_mode == 2)
+  {
+    launch_with_pilot(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, false, 32, 2>,
+                      EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, false, 32, 1>);
+  }
   else if (staged)
   {
-    launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, false, 32, true>);
+    launch(EnvelopeAxisWindowKernel<kMode, kWindowRadiusFinal, false, false, 32, 1>);
   }
   else
   {
