@@ -238,8 +238,13 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   asm volatile("" : "+l"(write_origin));
   const uint32_t out_stride_bytes = family.out_stride_bytes;
 
-  Out lane_min = PositiveInfinity<Out>();
-  Out lane_max = -PositiveInfinity<Out>();
+  // Finalize mode: the largest squared distance this lane has emitted for a free voxel (low
+  // half) and for a filled voxel (high half). The magnitude is monotone in the squared distance,
+  // so these two are what the lane contributes to Lock()'s maximum and minimum; every emitted
+  // value is finite and below kSaturated (anything else gives the tile up), hence 16 bits, and a
+  // finite value means both classes exist, so the smallest free / filled values cannot be the
+  // extrema. 0 = no voxel of that class emitted (a real squared distance is at least 1).
+  uint32_t lane_extrema = 0;
   int32_t border_yz = 0x7fffffff;
   if constexpr (kBorder)
   {
@@ -384,29 +389,6 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   char* send_origin = nullptr;
   int next_part_start = first_row;
 
-  // Finalize mode: the magnitude of row q comes from a table load; it is consumed (signed,
-  // stored, folded into min / max) one row later, behind the next row's window work.
-  Out pending_magnitude = Out(0);
-  char* pending_at = nullptr;
-  uint32_t pending_filled = 0;
-  bool pending = false;
-  const auto flush_pending = [&]()
-  {
-    if constexpr (kMode != kEmitPacked)
-    {
-      if (pending)
-      {
-        const Out value = pending_filled ? -pending_magnitude : pending_magnitude;
-        if (active)
-        {
-          __stcs(reinterpret_cast<Out*>(pending_at), value);
-        }
-        lane_min = (value < lane_min) ? value : lane_min;
-        lane_max = (value > lane_max) ? value : lane_max;
-      }
-    }
-  };
-
   // one row of the output; write_base = address of the chunk's first output row
   const auto emit_row = [&](const int q, const int j, char* const write_base, const uint32_t filled,
                             uint32_t squared)
@@ -463,6 +445,7 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       }
       write_at = send_origin + static_cast<uint64_t>(static_cast<uint32_t>(q)) * out_stride_bytes;
     }
+    // (the finalizing pass emits whole chunks: emit_finalized)
     if constexpr (kMode == kEmitPacked)
     {
       if (active)
@@ -470,8 +453,24 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
         __stcs(reinterpret_cast<uint32_t*>(write_at), (filled << 31) | squared);
       }
     }
-    else
+  };
+
+  // Finalize mode, a whole chunk: the virtual border, R magnitude look-ups in flight together
+  // (the per-call table holds (Out)(sqrt((double)s) * resolution) for every s below kSaturated at
+  // least, see MagnitudeTable::Build: every value this kernel emits is inside it), then sign,
+  // store and the two integer extrema.
+  const auto emit_finalized = [&](const int base, char* const write_base, const uint32_t* best,
+                                  auto edge)
+  {
+    constexpr bool kEdge = decltype(edge)::value;
+    const Out* const table = static_cast<const Out*>(finalize.magnitude_table);
+    Out magnitudes[kR];
+    uint32_t squares[kR];
+#pragma unroll
+    for (int j = 0; j < kR; j++)
     {
+      const int q = base + j;
+      uint32_t squared = (j & 1) ? (best[j >> 1] >> 16) : (best[j >> 1] & 0xffffu);
       if constexpr (kBorder)
       {
         int32_t border = border_yz;
@@ -484,21 +483,30 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
           squared = min(squared, static_cast<uint32_t>(border * border));
         }
       }
-      // this row's magnitude is requested first, then the previous row is finished
-      Out magnitude;
-      if (squared < finalize.magnitude_table_size)
+      squares[j] = squared;
+      magnitudes[j] = Out(0);
+      if (!kEdge || q <= last_row)  // warp-uniform
       {
-        magnitude = __ldg(static_cast<const Out*>(finalize.magnitude_table) + squared);
+        magnitudes[j] = __ldg(table + squared);
       }
-      else
+    }
+#pragma unroll
+    for (int j = 0; j < kR; j++)
+    {
+      const int q = base + j;
+      if (!kEdge || q <= last_row)  // warp-uniform
       {
-        magnitude = SignedDistanceOf<Out>(0u, squared, finalize.resolution);
+        const uint32_t filled = static_cast<uint32_t>(classes >> (2 * kR - 1 - j)) & 1u;
+        const Out value = filled ? -magnitudes[j] : magnitudes[j];
+        if (active)
+        {
+          __stcs(reinterpret_cast<Out*>(write_base + static_cast<uint64_t>(out_stride_bytes)
+                                                        * static_cast<uint32_t>(j)),
+                 value);
+        }
+        // free: the low half, filled: the high half (one multiply on the fma pipe)
+        lane_extrema = __vmaxu2(lane_extrema, squares[j] * (filled * 0xffffu + 1u));
       }
-      flush_pending();
-      pending_magnitude = magnitude;
-      pending_at = write_at;
-      pending_filled = filled;
-      pending = true;
     }
   };
 
@@ -799,16 +807,24 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     // ---------------------------------------------------------------------------------- phase C
     if (!over_budget)
     {
-#pragma unroll
-      for (int j = 0; j < kR; j++)
+      if constexpr (kMode == kEmitPacked)
       {
-        const int q = base + j;
-        if (!kEdge || q <= last_row)  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < kR; j++)
         {
-          const uint32_t filled = static_cast<uint32_t>(classes >> (2 * kR - 1 - j)) & 1u;
-          const uint32_t squared = (j & 1) ? (best_pairs[j >> 1] >> 16) : (best_pairs[j >> 1] & 0xffffu);
-          emit_row(q, j, write_base, filled, squared);
+          const int q = base + j;
+          if (!kEdge || q <= last_row)  // warp-uniform
+          {
+            const uint32_t filled = static_cast<uint32_t>(classes >> (2 * kR - 1 - j)) & 1u;
+            const uint32_t squared =
+                (j & 1) ? (best_pairs[j >> 1] >> 16) : (best_pairs[j >> 1] & 0xffffu);
+            emit_row(q, j, write_base, filled, squared);
+          }
         }
+      }
+      else
+      {
+        emit_finalized(base, write_base, best_pairs, edge);
       }
     }
     // the next chunk becomes the current one
@@ -877,7 +893,6 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     {
       compute_chunk(base, Edge{});
     }
-    flush_pending();
     // nothing of this warp may still be in flight when it exits
     if constexpr (kStage == 1)
     {
@@ -931,6 +946,15 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       return;
     }
     using Key = typename OutputOf<kMode>::Key;
+    // the lane's extrema as values: +magnitude of its deepest free voxel, -magnitude of its
+    // deepest filled voxel (neutral elements where the lane emitted none of a class)
+    const Out* const table = static_cast<const Out*>(finalize.magnitude_table);
+    const uint32_t deepest_free = lane_extrema & 0xffffu;
+    const uint32_t deepest_filled = lane_extrema >> 16;
+    const Out lane_max =
+        deepest_free != 0u ? __ldg(table + deepest_free) : -PositiveInfinity<Out>();
+    const Out lane_min =
+        deepest_filled != 0u ? -__ldg(table + deepest_filled) : PositiveInfinity<Out>();
     Key key_min = OrderedKey(lane_min);
     Key key_max = OrderedKey(lane_max);
 #pragma unroll

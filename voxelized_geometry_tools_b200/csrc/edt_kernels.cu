@@ -612,7 +612,10 @@ class MagnitudeTable
 public:
   int Build(int64_t nx, int64_t ny, int64_t nz, double resolution, cudaStream_t stream)
   {
-    const int64_t largest = Square(nx - 1) + Square(ny - 1) + Square(nz - 1);
+    // (never fewer than kSaturated + 1 entries: the window kernel looks every value it emits up
+    // without a bound check, and those are below kSaturated)
+    const int64_t largest = std::max<int64_t>(Square(nx - 1) + Square(ny - 1) + Square(nz - 1),
+                                              static_cast<int64_t>(kSaturated));
     size_ = static_cast<uint32_t>(std::min(largest + 1, kMagnitudeTableMaxEntries));
     VGT_CUDA_TRY(table_.Allocate(size_, stream), "magnitude table allocation");
     const unsigned threads = 256;
