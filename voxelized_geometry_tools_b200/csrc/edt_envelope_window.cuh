@@ -139,6 +139,18 @@ __device__ __forceinline__ void BulkCopyRow(uint32_t* shared_row, const void* gl
       : "memory");
 }
 
+// classes = (classes << 1) | (class bit of word): one funnel shift per 32 bits of the class word.
+__device__ __forceinline__ void AppendClassBit(uint32_t& classes, const uint32_t word)
+{
+  classes = __funnelshift_l(word, classes, 1);
+}
+__device__ __forceinline__ void AppendClassBit(uint64_t& classes, const uint32_t word)
+{
+  const uint32_t low = static_cast<uint32_t>(classes);
+  const uint32_t high = __funnelshift_l(low, static_cast<uint32_t>(classes >> 32), 1);
+  classes = (static_cast<uint64_t>(high) << 32) | __funnelshift_l(word, low, 1);
+}
+
 // Deepest row distance the 16-bit joint search looks at: clamped values (0x3fff) plus squared
 // offsets must fit 16 bits and a result is only exact below kSaturated, i.e. up to 127 voxels.
 constexpr int kJointDeepestCap = 120;
@@ -270,8 +282,9 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   constexpr int kPairs = kR / 2;
   uint32_t previous_pairs[kPairs], current_pairs[kPairs], next_pairs[kPairs];
   // Class bits of the three chunks: bit 3 R - 1 - r' = class of row r' counted from the first
-  // row of the previous chunk. The bits of the next chunk enter pair by pair (see below); bits
-  // above 3 R are leftovers of older chunks and never reach a window.
+  // row of the previous chunk (once the next chunk has been absorbed at the start of a chunk:
+  // every absorbed row shifts its bit in at the bottom); bits above 3 R are leftovers of older
+  // chunks and never reach a window.
   // (one 32-bit register when the three chunks fit, i.e. R <= 10: every class operation is then
   // a single instruction instead of a 64-bit pair)
   using ClassWord = typename std::conditional<(3 * kR <= 32), uint32_t, uint64_t>::type;
@@ -551,8 +564,8 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
         high = (base + j + kR + 1 > last_row) ? kSaturated : high;
       }
       next_pairs[j >> 1] = __byte_perm(low, high, 0x5410);
-      classes |= (static_cast<ClassWord>(low_word >> 31) << (kR - 1 - j))
-          | (static_cast<ClassWord>(high_word >> 31) << (kR - 2 - j));
+      AppendClassBit(classes, low_word);
+      AppendClassBit(classes, high_word);
     }
     if constexpr (kStage != 0)
     {
@@ -580,26 +593,28 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     const auto window_rows = [&](auto with_classes)
     {
       constexpr bool kWithClasses = decltype(with_classes)::value;
-      uint32_t even_best = 0;
 #pragma unroll
-      for (int j = 0; j < kR; j++)
+      for (int j = 0; j < kR; j += 2)
       {
-        const int q = base + j;
-        // (a row past the end of the line: 0, so that it never asks for a search)
-        uint32_t best = 0;
-        if (!kEdge || q <= last_row)  // warp-uniform
+        // rows j and j + 1 together: their two accumulators are transposed into (low halves,
+        // high halves) so that ONE paired minimum finishes both and leaves them packed
+        uint32_t row_pair[2];
+        uint32_t nearest_pair[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
         {
-          // Pairs g = (j >> 1) .. (j >> 1) + R of the 3 R / 2 pairs in registers cover the rows
-          // q - R .. q + R plus one row at distance R + 1 (a true candidate like the others).
-          // Two accumulators: half the dependent chain.
+          const int jr = j + r;
+          // Pairs g = (jr >> 1) .. (jr >> 1) + R of the 3 R / 2 pairs in registers cover the
+          // rows q - R .. q + R plus one row at distance R + 1 (a true candidate like the
+          // others). Two accumulators: half the dependent chain.
           uint32_t chains[2] = {0xffffffffu, 0xffffffffu};
 #pragma unroll
           for (int t = 0; t <= kR; t++)
           {
-            const int g = (j >> 1) + t;                 // pair index, 0 .. 3 R / 2 - 1
+            const int g = (jr >> 1) + t;                // pair index, 0 .. 3 R / 2 - 1
             const int low_row = 2 * g - kR;             // chunk-relative row of the low half
-            const int d_low = (j > low_row) ? j - low_row : low_row - j;
-            const int d_high = (j > low_row + 1) ? j - low_row - 1 : low_row + 1 - j;
+            const int d_low = (jr > low_row) ? jr - low_row : low_row - jr;
+            const int d_high = (jr > low_row + 1) ? jr - low_row - 1 : low_row + 1 - jr;
             const uint32_t offsets = static_cast<uint32_t>(d_low * d_low)
                 | (static_cast<uint32_t>(d_high * d_high) << 16);
             const uint32_t pair = (g < kPairs)
@@ -609,12 +624,11 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
                        : next_pairs[(g >= 2 * kPairs) ? g - 2 * kPairs : 0]);
             chains[t & 1] = __viaddmin_u16x2(pair, offsets, chains[t & 1]);
           }
-          const uint32_t best_pair = __vminu2(chains[0], chains[1]);
-          best = min(best_pair & 0xffffu, best_pair >> 16);
+          row_pair[r] = __vminu2(chains[0], chains[1]);
           if constexpr (kWithClasses)
           {
             // class window of row q: bit R = row q, bit R - d = row q + d, bit R + d = row q - d
-            const uint32_t window = static_cast<uint32_t>(classes >> (kR - 1 - j));
+            const uint32_t window = static_cast<uint32_t>(classes >> (kR - 1 - jr));
             const uint32_t same =
                 static_cast<uint32_t>(static_cast<int32_t>(window << (31 - kR)) >> 31);
             const uint32_t differs = window ^ same;
@@ -622,19 +636,21 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
             const uint32_t folded = (differs | (__brev(differs) >> (31 - 2 * kR))) & kSideMask;
             const int nearest = kR - 31 + __clz(static_cast<int>(folded));
             // (no opposite-class row inside the window: no such candidate)
-            const uint32_t nearest_squared =
-                (folded != 0u) ? static_cast<uint32_t>(nearest * nearest) : 0xffffu;
-            best = min(best, nearest_squared);
+            nearest_pair[r] = (folded != 0u) ? static_cast<uint32_t>(nearest * nearest) : 0xffffu;
           }
         }
-        if ((j & 1) == 0)
+        uint32_t both = __vminu2(__byte_perm(row_pair[0], row_pair[1], 0x5410),
+                                 __byte_perm(row_pair[0], row_pair[1], 0x7632));
+        if constexpr (kWithClasses)
         {
-          even_best = best;
+          both = __vminu2(both, __byte_perm(nearest_pair[0], nearest_pair[1], 0x5410));
         }
-        else
+        if constexpr (kEdge)
         {
-          best_pairs[j >> 1] = __byte_perm(even_best, best, 0x5410);
+          // (a row past the end of the line: 0, so that it never asks for a search)
+          both = (base + j > last_row) ? 0u : ((base + j + 1 > last_row) ? (both & 0xffffu) : both);
         }
+        best_pairs[j >> 1] = both;
       }
     };
     bool one_class_everywhere = false;
@@ -834,7 +850,7 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       previous_pairs[i] = current_pairs[i];
       current_pairs[i] = next_pairs[i];
     }
-    classes <<= kR;
+    // (the class word moves on by itself: absorbing the next chunk shifts R bits in)
   };
 
   {
@@ -864,7 +880,6 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       current_pairs[i >> 1] = __byte_perm(low, high, 0x5410);
       classes = (classes << 2) | ((low_word >> 31) << 1) | (high_word >> 31);
     }
-    classes <<= kR;
     if constexpr (kStage != 0)
     {
       // the next chunk into buffer 0, the one after it into buffer 1
