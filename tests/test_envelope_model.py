@@ -286,10 +286,10 @@ def brev32(x):
     return int(format(x & 0xFFFFFFFF, "032b")[::-1], 2)
 
 
-SATURATED = 0x3FFF
+SATURATED = 0x7800
 
 
-DEEPEST_CAP = 120
+DEEPEST_CAP = 168
 
 
 def window_line(classes, values, radius, step_budget=None, segment_rows=None, deepest=None):
@@ -460,3 +460,29 @@ def test_window_line_smooth_and_budget():
     assert solved > 100
     # one class, no values at all: the window is saturated, the line is given up
     assert window_line([0] * 50, [NONE] * 50, 8)[0] is None
+
+
+def test_window_line_deep_pockets_stay_inside_sixteen_bits():
+    # long lines with pockets up to and beyond the depth cap: the model asserts that every sum
+    # of the joint search fits 16 bits; lines within the cap come out exact, deeper ones give up
+    rng = random.Random(9)
+    solved = gave_up = 0
+    for _ in range(60):
+        n = rng.choice([300, 420, 520])
+        wall = rng.randint(0, 40)
+        depth = rng.choice([90, 140, 165, 200, 260])
+        # one class; small values near the two ends of a pocket of the given depth, large inside
+        values = []
+        for i in range(n):
+            edge = min(abs(i - wall), abs(i - (wall + 2 * depth)))
+            values.append(1 + rng.randint(0, 3) if edge < 2 else 100000 + rng.randint(0, 50))
+        classes = [0] * n
+        want = brute_line(classes, values)
+        for radius in (8, 12):
+            got, _ = window_line(classes, values, radius)
+            assert got is None or got == want
+            solved += got is not None
+            gave_up += got is None
+            if max(want) < 150 * 150:
+                assert got == want, (n, wall, depth, radius)
+    assert solved > 20 and gave_up > 5

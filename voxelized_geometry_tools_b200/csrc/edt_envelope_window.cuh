@@ -70,8 +70,9 @@ constexpr uint32_t kSelectPilot = 1;
 constexpr uint32_t kSelectAfterPilot = 2;
 constexpr uint32_t kPilotStride = 8;
 constexpr int kPilotSpacing = 256;
-// Values in the register window are clamped to this (16-bit halves; + (R + 1)^2 must fit).
-constexpr uint32_t kSaturated = 0x3fffu;
+// Values in the register window are clamped to this (16-bit halves; the squared offsets of the
+// joint search must still fit on top of it, see kJointDeepestCap).
+constexpr uint32_t kSaturated = 0x7800u;
 
 // Staged variant (kStage): the rows of the chunks ahead travel global -> shared memory with
 // cp.async (4 bytes per lane and row, each lane later reads back only what it copied itself, so
@@ -151,9 +152,13 @@ __device__ __forceinline__ void AppendClassBit(uint64_t& classes, const uint32_t
   classes = (static_cast<uint64_t>(high) << 32) | __funnelshift_l(word, low, 1);
 }
 
-// Deepest row distance the 16-bit joint search looks at: clamped values (0x3fff) plus squared
-// offsets must fit 16 bits and a result is only exact below kSaturated, i.e. up to 127 voxels.
-constexpr int kJointDeepestCap = 120;
+// Deepest row distance the 16-bit joint search looks at: clamped values (kSaturated) plus squared
+// offsets must fit 16 bits and a result is only exact below kSaturated (0x7800: 175 voxels).
+// The furthest candidate of a round is kJointDeepestCap + R - 1 rows from its row:
+// (168 + 13)^2 + 0x7800 = 63481 < 65536.
+constexpr int kJointDeepestCap = 168;
+static_assert((kJointDeepestCap + 13) * (kJointDeepestCap + 13) + static_cast<int>(kSaturated) < 65536,
+              "the joint search must stay inside 16 bits");
 // "No opposite-class row in the neighbouring chunk" for the joint search: far enough that its
 // square beats no real candidate, small enough that (kNoRow + R)^2 fits 16 bits.
 constexpr uint32_t kNoRow = 200u;
