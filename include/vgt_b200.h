@@ -330,6 +330,16 @@ VGT_B200_API int vgt_b200_sdf_project_out_of_collision_dev(
     double minimum_distance, double stepsize_multiplier, int64_t max_steps, int device,
     double* d_projected_xyz, uint8_t* d_valid, void* stream);
 
+/* Replaces SignedDistanceField::ComputeLocalExtremaMap
+ * (include/voxelized_geometry_tools/signed_distance_field.hpp:1207-1231 with :360-476, :478-545):
+ * for every cell the centre (grid frame) of the cell its gradient walk ends at, +inf when the walk leaves the grid. Walks that run into a loop take the
+ * cell where the first walk of that basin (in storage order, as the reference's sequential loop
+ * starts them) enters the loop, so the result equals the reference's memoised sequential result.
+ *   d_extrema_xyz   device double[nx*ny*nz*3] (VoxelGrid<Eigen::Vector3d> raw data)
+ * Grids of fewer than 2^31 cells; uses 32 bytes of stream-ordered scratch per cell. */
+VGT_B200_API int vgt_b200_sdf_local_extrema_map_dev(
+    const vgt_b200_sdf_view* sdf, int device, double* d_extrema_xyz, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Point cloud voxelization
  * ------------------------------------------------------------------------------------------- */

@@ -8,10 +8,17 @@
 
 #include <cmath>
 #include <cstdint>
+#include <functional>
+#include <memory>
 #include <stdexcept>
 #include <vector>
 
 #include <Eigen/Geometry>
+#include <common_robotics_utilities/serialization.hpp>
+
+#ifndef CRU_UNUSED
+#define CRU_UNUSED(x) (void)(x)
+#endif
 
 namespace common_robotics_utilities
 {
@@ -112,11 +119,70 @@ class VoxelGridBase
 {
 public:
   VoxelGridBase() = default;
+  // (the out-of-bounds value of the real class is only ever handed back by accessors the
+  // reference's SDF code does not use; kept so the constructors match)
+  VoxelGridBase(const Eigen::Isometry3d& origin_transform, const VoxelGridSizes& sizes,
+                const T& default_value, const T&)
+      : VoxelGridBase(origin_transform, sizes, default_value) {}
+  VoxelGridBase(const VoxelGridSizes& sizes, const T& default_value, const T&)
+      : VoxelGridBase(Eigen::Isometry3d::Identity(), sizes, default_value) {}
   VoxelGridBase(const Eigen::Isometry3d& origin_transform, const VoxelGridSizes& sizes,
                 const T& default_value)
       : origin_transform_(origin_transform), sizes_(sizes),
         data_(static_cast<size_t>(sizes.TotalVoxels()), default_value), initialized_(true) {}
   virtual ~VoxelGridBase() {}
+
+  // (signed_distance_field.hpp derives from the grid and implements these)
+  using ScalarTypeSerializer = serialization::Serializer<T>;
+  using ScalarTypeDeserializer = serialization::Deserializer<T>;
+  Eigen::Vector3d VoxelSizes() const
+  {
+    return Eigen::Vector3d(sizes_.VoxelXSize(), sizes_.VoxelXSize(), sizes_.VoxelXSize());
+  }
+  Eigen::Vector4d GridIndexToLocationInGridFrame(int64_t x, int64_t y, int64_t z) const
+  {
+    return GridIndexToLocationInGridFrame(GridIndex(x, y, z));
+  }
+  GridIndex LocationToGridIndex4d(const Eigen::Vector4d& location) const
+  {
+    return LocationInGridFrameToGridIndex4d(InverseOriginTransform() * location);
+  }
+  GridIndex LocationToGridIndex3d(const Eigen::Vector3d& location) const
+  {
+    return LocationToGridIndex4d(Eigen::Vector4d(location(0), location(1), location(2), 1.0));
+  }
+  bool CheckLocationInBounds4d(const Eigen::Vector4d& location) const
+  {
+    return CheckGridIndexInBounds(LocationToGridIndex4d(location));
+  }
+  bool CheckLocationInBounds(const Eigen::Vector3d& location) const
+  {
+    return CheckGridIndexInBounds(LocationToGridIndex3d(location));
+  }
+  bool CheckLocationInBounds(double x, double y, double z) const
+  {
+    return CheckLocationInBounds4d(Eigen::Vector4d(x, y, z, 1.0));
+  }
+  GridIndex LocationToGridIndex(double x, double y, double z) const
+  {
+    return LocationToGridIndex4d(Eigen::Vector4d(x, y, z, 1.0));
+  }
+  Eigen::Vector4d GridIndexToLocation(const GridIndex& index) const
+  {
+    return origin_transform_ * GridIndexToLocationInGridFrame(index);
+  }
+  Eigen::Vector4d GridIndexToLocation(int64_t x, int64_t y, int64_t z) const
+  {
+    return GridIndexToLocation(GridIndex(x, y, z));
+  }
+  uint64_t SerializeSelf(std::vector<uint8_t>&, const ScalarTypeSerializer&) const
+  {
+    throw std::runtime_error("serialization is not part of the oracle");
+  }
+  uint64_t DeserializeSelf(const std::vector<uint8_t>&, uint64_t, const ScalarTypeDeserializer&)
+  {
+    throw std::runtime_error("serialization is not part of the oracle");
+  }
 
   bool IsInitialized() const { return initialized_; }
   bool HasUniformVoxelSize() const { return sizes_.UniformVoxelSize(); }
@@ -193,6 +259,17 @@ public:
 
 protected:
   virtual bool OnMutableAccess(int64_t, int64_t, int64_t) { return true; }
+  virtual bool OnMutableRawAccess() { return true; }
+  virtual std::unique_ptr<VoxelGridBase<T, BackingStore>> DoClone() const { return nullptr; }
+  virtual uint64_t DerivedSerializeSelf(std::vector<uint8_t>&, const ScalarTypeSerializer&) const
+  {
+    return 0;
+  }
+  virtual uint64_t DerivedDeserializeSelf(const std::vector<uint8_t>&, uint64_t,
+                                          const ScalarTypeDeserializer&)
+  {
+    return 0;
+  }
 
 private:
   Eigen::Isometry3d origin_transform_;
@@ -205,3 +282,18 @@ template <typename T>
 using VoxelGrid = VoxelGridBase<T, std::vector<T>>;
 }  // namespace voxel_grid
 }  // namespace common_robotics_utilities
+
+namespace std
+{
+template <>
+struct hash<common_robotics_utilities::voxel_grid::GridIndex>
+{
+  size_t operator()(const common_robotics_utilities::voxel_grid::GridIndex& index) const
+  {
+    // (any hash will do: the reference only uses the map as a set of visited cells)
+    size_t h = std::hash<int64_t>()(index.X());
+    h = h * 1000003u + std::hash<int64_t>()(index.Y());
+    return h * 1000003u + std::hash<int64_t>()(index.Z());
+  }
+};
+}  // namespace std

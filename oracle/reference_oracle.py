@@ -183,3 +183,49 @@ def isometry_inverse(a) -> np.ndarray:
     _voxelizer_lib().vgt_ref_isometry_inverse(a_cm.ctypes.data_as(_f64p),
                                               out.ctypes.data_as(_f64p))
     return np.ascontiguousarray(out.T)
+
+
+# ---- the reference's own SignedDistanceField query members (ref_shim/ref_sdf_queries_entry.cpp)
+QUERY_ESTIMATE_DISTANCE, QUERY_COARSE_GRADIENT, QUERY_FINE_GRADIENT, QUERY_PROJECT = 0, 1, 2, 3
+
+
+def _origin_column_major(origin_transform):
+    origin = np.eye(4) if origin_transform is None else np.asarray(origin_transform, np.float64)
+    return np.ascontiguousarray(origin.T).reshape(16)      # column-major = rows of the transpose
+
+
+def sdf_query(field, resolution: float, origin_transform, kind: int, points, a=0.0, b=0.0):
+    """(values [count, 1 or 3], status [count]: 0 no value, 1 value, 2 the reference threw)."""
+    handle = lib()
+    handle.vgt_ref_sdf_query.argtypes = [
+        _f32p, _i64, _i64, _i64, ctypes.c_double, _f64p, _int, ctypes.c_double, ctypes.c_double,
+        _f64p, _i64, _f64p, ctypes.POINTER(ctypes.c_uint8)]
+    field = np.ascontiguousarray(field, dtype=np.float32)
+    points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    origin = _origin_column_major(origin_transform)
+    width = 1 if kind == QUERY_ESTIMATE_DISTANCE else 3
+    values = np.zeros((len(points), width), dtype=np.float64)
+    status = np.zeros(len(points), dtype=np.uint8)
+    code = handle.vgt_ref_sdf_query(
+        field.ctypes.data_as(_f32p), *field.shape, float(resolution),
+        origin.ctypes.data_as(_f64p), int(kind), float(a), float(b),
+        points.ctypes.data_as(_f64p), len(points), values.ctypes.data_as(_f64p),
+        status.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    if code != 0:
+        raise RuntimeError("reference SDF query failed")
+    return values, status
+
+
+def sdf_local_extrema_map(field, resolution: float, origin_transform=None) -> np.ndarray:
+    handle = lib()
+    handle.vgt_ref_sdf_local_extrema_map.argtypes = [
+        _f32p, _i64, _i64, _i64, ctypes.c_double, _f64p, _f64p]
+    field = np.ascontiguousarray(field, dtype=np.float32)
+    origin = _origin_column_major(origin_transform)
+    out = np.empty(field.shape + (3,), dtype=np.float64)
+    code = handle.vgt_ref_sdf_local_extrema_map(
+        field.ctypes.data_as(_f32p), *field.shape, float(resolution),
+        origin.ctypes.data_as(_f64p), out.ctypes.data_as(_f64p))
+    if code != 0:
+        raise RuntimeError("reference ComputeLocalExtremaMap failed")
+    return out

@@ -11,6 +11,8 @@ ScalarType values), one point at a time, written to follow the reference stateme
       :903-1025  GetIndexCoarseGradient / GetGridAlignedIndexCoarseGradient
       :1051-1092 GetLocationFineGradient, :213-255 ComputeAxisFineGradient
       :1159-1203 ProjectLocationOutOfCollisionToMinimumDistance4d
+      :1207-1231 ComputeLocalExtremaMap, :360-480 FollowGradientsToLocalExtremaUnsafe,
+                 :482-534 GradientIsEffectiveFlat / GetNextFromGradient
 
 PARITY STATUS. The reference has no test or golden vector for any of these members (they are
 exercised only by example/*.cpp), and the trilinear blend itself is
@@ -216,3 +218,59 @@ class SdfOracle:
                 if steps >= max_steps:
                     return THROWS, [0.0, 0.0, 0.0]
         return VALUE, location
+
+    # ---- local extrema map
+    def _effectively_flat(self, g):
+        step = self.res * 0.06125
+        return abs(g[0]) <= step and abs(g[1]) <= step and abs(g[2]) <= step
+
+    def _next_from_gradient(self, index, g):
+        if self.sdf[index] < 0.0:
+            g = [c * -1.0 for c in g]
+        step = self.res * 0.06125
+        moved = list(index)
+        for axis in range(3):
+            if g[axis] > step:
+                moved[axis] += 1
+            elif g[axis] < -step:
+                moved[axis] -= 1
+        return tuple(moved)
+
+    def _centre_in_grid_frame(self, index):
+        return [self.res * (float(c) + 0.5) for c in index]
+
+    def local_extrema_map(self):
+        """The sequential, memoising loop of the reference, cell by cell in storage order."""
+        unset = -math.inf
+        extrema = np.full((self.nx, self.ny, self.nz, 3), unset, dtype=np.float64)
+        for x in range(self.nx):
+            for y in range(self.ny):
+                for z in range(self.nz):
+                    if not np.any(extrema[x, y, z] == unset):
+                        continue
+                    g = self.coarse_gradient_at_index(x, y, z, True)[1]
+                    if self._effectively_flat(g):
+                        extrema[x, y, z] = self._centre_in_grid_frame((x, y, z))
+                        continue
+                    path = {(x, y, z): 1}
+                    current = (x, y, z)
+                    while True:
+                        current = self._next_from_gradient(current, g)
+                        if path.setdefault(current, 0) != 0:
+                            found = self._centre_in_grid_frame(current)
+                            break
+                        if not self._in_bounds(current):
+                            found = [math.inf, math.inf, math.inf]
+                            break
+                        path[current] = 1
+                        if not np.any(extrema[current] == unset):
+                            found = list(extrema[current])
+                            break
+                        g = self.coarse_gradient_at_index(*current, True)[1]
+                        if self._effectively_flat(g):
+                            found = self._centre_in_grid_frame(current)
+                            break
+                    for cell in path:
+                        if self._in_bounds(cell):
+                            extrema[cell] = found
+        return extrema

@@ -121,3 +121,47 @@ def test_query_properties_on_a_flat_wall(shared_library):
     assert out[2, 0] > 0.8 and out[2, 1] == 0.8 and out[2, 2] == 0.8
     with pytest.raises(ValueError):
         field.EstimateLocationDistance(torch.zeros((4, 2), dtype=torch.float64, device=dev))
+
+
+def test_local_extrema_map_of_an_sdf(scene):
+    got = scene["gpu"].ComputeLocalExtremaMap().cpu().numpy()
+    want = scene["oracle"].local_extrema_map()
+    np.testing.assert_array_equal(got, want)
+    assert np.isinf(got).any() and np.isfinite(got).any()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_local_extrema_map_with_loops(shared_library, seed):
+    """A rough random field: plenty of walks that close loops (two cells pointing at each other
+    and longer ones), where the result depends on the order the reference starts its walks in."""
+    import torch
+    from voxelized_geometry_tools_b200 import device as vdev
+    from oracle import sdf_queries_oracle
+    rng = np.random.default_rng(seed)
+    dims, res = (14, 11, 13), 0.1
+    field = rng.normal(size=dims).astype(np.float32) * 0.3
+    field[rng.random(dims) < 0.1] = 0.0
+    if seed == 2:
+        field[2:5, 2:5, 2:5] = np.inf      # inf - inf = NaN gradients: cells that stay put
+    pose = _posed(rng) if seed else np.eye(4)
+    checker = sdf_queries_oracle.SdfOracle(field, res, pose)
+    # the field has loops (otherwise this test checks nothing new)
+    loops = 0
+    for start in np.ndindex(*dims):
+        seen, current = {start}, start
+        while True:
+            g = checker.coarse_gradient_at_index(*current, True)[1]
+            if checker._effectively_flat(g):
+                break
+            current = checker._next_from_gradient(current, g)
+            if not checker._in_bounds(current):
+                break
+            if current in seen:
+                loops += 1
+                break
+            seen.add(current)
+    assert loops > 20
+    dev = torch.device("cuda", 0)
+    device_sdf = vdev.DeviceSignedDistanceField(torch.from_numpy(field).to(dev), res, pose)
+    got = device_sdf.ComputeLocalExtremaMap().cpu().numpy()
+    np.testing.assert_array_equal(got, checker.local_extrema_map())

@@ -100,6 +100,7 @@ SIGNATURES = {
                                                 _vp, _vp, _vp]),
     "vgt_b200_sdf_fine_gradient_dev": (_int, [ctypes.POINTER(SdfView), _vp, _i64, _dbl, _int, _vp,
                                               _vp, _vp]),
+    "vgt_b200_sdf_local_extrema_map_dev": (_int, [ctypes.POINTER(SdfView), _int, _vp, _vp]),
     "vgt_b200_sdf_project_out_of_collision_dev": (_int, [ctypes.POINTER(SdfView), _vp, _i64, _dbl,
                                                          _dbl, _i64, _int, _vp, _vp, _vp]),
     "vgt_b200_voxelize_f64": (_int, [_vp, _i64, _i64, _i64, _dbl, ctypes.POINTER(Cloud),

@@ -614,7 +614,9 @@ int TimeAdapter(const int64_t n)
     pieces.Lock();
     const auto t4 = Clock::now();
     pieces.Unlock();
+#ifdef VGT_B200_SDF_HAS_LOCK_WITH_KNOWN_EXTREMA
     pieces.LockWithKnownExtrema(lo, hi);
+#endif
     const auto t5 = Clock::now();
     if (!(pieces.GetImmutableRawData() == sdf.GetImmutableRawData())) { return 1; }
     if (rep > 0)

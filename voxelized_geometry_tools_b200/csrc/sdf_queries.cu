@@ -425,6 +425,185 @@ __global__ void ProjectOutOfCollisionKernel(SdfView view, const double* __restri
   valid[i] = status;
 }
 
+// ------------------------------------------------------------------------------------------------
+// ComputeLocalExtremaMap (signed_distance_field.hpp:1207-1231 with :360-476, :478-545): every cell
+// follows the coarse gradient (edge gradients on; uphill outside obstacles, downhill inside) one
+// of its 26 neighbours at a time until it reaches a cell with an effectively flat gradient (its
+// own centre is the extremum), leaves the grid (+inf), or runs into a loop.
+//
+// The reference walks the cells one after the other in storage order and memoises: a walk stops
+// at the first cell that already has a value, and a walk that closes a loop takes the centre of
+// the first cell it visits twice. For cells that drain into a flat cell or off the grid the
+// result does not depend on that order (every walk ends at the same terminal). For cells that
+// drain into a loop it does: the whole basin gets the centre of the cell where the FIRST walk of
+// that basin (the one from its smallest cell index, the walks being started in index order)
+// enters the loop. The parallel version reproduces exactly that:
+//   1. successor of every cell (itself = terminal; a marker = off the grid);
+//   2. pointer jumping, ceil(log2 V) + 1 rounds: the cell each cell ends at, and the smallest
+//      cell index met on the way (for a cell on a loop: the smallest index of the loop = its id);
+//   3. per loop: the smallest cell index of its basin (atomicMin);
+//   4. per loop: one thread replays the walk from that cell and finds the entry cell;
+//   5. every cell writes the centre of its terminal / its loop's entry cell.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kOffGrid = 0xffffffffu;
+
+__global__ void ExtremaSuccessorKernel(SdfView view, uint32_t* __restrict__ successor)
+{
+  const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t count = view.nx * view.ny * view.nz;
+  if (cell >= count)
+  {
+    return;
+  }
+  const int64_t z = cell % view.nz;
+  const int64_t y = (cell / view.nz) % view.ny;
+  const int64_t x = cell / (view.nz * view.ny);
+  Vec3 gradient;
+  CoarseGradientAtIndex(view, x, y, z, true, &gradient);
+  // GradientIsEffectiveFlat (:478-492) and GetNextFromGradient (:494-534)
+  const double step = view.resolution * 0.06125;
+  uint32_t next = static_cast<uint32_t>(cell);
+  const bool flat = fabs(gradient.x) <= step && fabs(gradient.y) <= step && fabs(gradient.z) <= step;
+  if (!flat)
+  {
+    if (StoredFloat(view, x, y, z) < 0.0f)
+    {
+      gradient = Vec3{gradient.x * -1.0, gradient.y * -1.0, gradient.z * -1.0};
+    }
+    int64_t nx = x, ny = y, nz = z;
+    if (gradient.x > step) { nx += 1; } else if (gradient.x < -step) { nx -= 1; }
+    if (gradient.y > step) { ny += 1; } else if (gradient.y < -step) { ny -= 1; }
+    if (gradient.z > step) { nz += 1; } else if (gradient.z < -step) { nz -= 1; }
+    next = InBounds(view, nx, ny, nz)
+        ? static_cast<uint32_t>((nx * view.ny + ny) * view.nz + nz)
+        : kOffGrid;
+  }
+  successor[cell] = next;
+}
+
+// One round of pointer jumping: target' = target[target], lowest' = min(lowest, lowest[target]).
+__global__ void ExtremaJumpKernel(const uint32_t* __restrict__ target_in,
+                                  const uint32_t* __restrict__ lowest_in, int64_t count,
+                                  uint32_t* __restrict__ target_out,
+                                  uint32_t* __restrict__ lowest_out)
+{
+  const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= count)
+  {
+    return;
+  }
+  const uint32_t target = target_in[cell];
+  uint32_t lowest = lowest_in[cell];
+  uint32_t next = target;
+  if (target != kOffGrid)
+  {
+    next = target_in[target];
+    lowest = min(lowest, lowest_in[target]);
+  }
+  target_out[cell] = next;
+  lowest_out[cell] = lowest;
+}
+
+// After the jumps target[c] is a terminal (successor == itself), off the grid, or a cell on a
+// loop; for the latter lowest[target[c]] is the loop's id. Smallest basin cell per loop.
+__global__ void ExtremaBasinKernel(const uint32_t* __restrict__ successor,
+                                   const uint32_t* __restrict__ target,
+                                   const uint32_t* __restrict__ lowest, int64_t count,
+                                   uint32_t* __restrict__ basin_first)
+{
+  const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= count)
+  {
+    return;
+  }
+  const uint32_t end = target[cell];
+  if (end != kOffGrid && successor[end] != end)
+  {
+    atomicMin(basin_first + lowest[end], static_cast<uint32_t>(cell));
+  }
+}
+
+// One thread per loop (the thread of the basin's smallest cell): replays the reference's walk
+// from that cell, stamping the cells it visits, until it steps on a stamped cell: the entry.
+__global__ void ExtremaEntryKernel(const uint32_t* __restrict__ successor,
+                                   const uint32_t* __restrict__ target,
+                                   const uint32_t* __restrict__ lowest,
+                                   const uint32_t* __restrict__ basin_first, int64_t count,
+                                   uint32_t* __restrict__ stamp, uint32_t* __restrict__ entry)
+{
+  const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= count)
+  {
+    return;
+  }
+  const uint32_t end = target[cell];
+  if (end == kOffGrid || successor[end] == end)
+  {
+    return;
+  }
+  const uint32_t loop = lowest[end];
+  if (basin_first[loop] != static_cast<uint32_t>(cell))
+  {
+    return;
+  }
+  // (the walks of different loops never share a cell, so the stamps need no loop id)
+  uint32_t current = static_cast<uint32_t>(cell);
+  stamp[current] = 1u;
+  while (true)
+  {
+    current = successor[current];
+    if (stamp[current] != 0u)
+    {
+      entry[loop] = current;
+      return;
+    }
+    stamp[current] = 1u;
+  }
+}
+
+__global__ void ExtremaWriteKernel(SdfView view, const uint32_t* __restrict__ successor,
+                                   const uint32_t* __restrict__ target,
+                                   const uint32_t* __restrict__ lowest,
+                                   const uint32_t* __restrict__ entry,
+                                   double* __restrict__ extrema)
+{
+  const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t count = view.nx * view.ny * view.nz;
+  if (cell >= count)
+  {
+    return;
+  }
+  uint32_t end = target[cell];
+  const double infinity = __longlong_as_double(0x7ff0000000000000LL);
+  double ex = infinity, ey = infinity, ez = infinity;
+  if (end != kOffGrid)
+  {
+    if (successor[end] != end)
+    {
+      end = entry[lowest[end]];
+    }
+    const int64_t z = end % view.nz;
+    const int64_t y = (end / view.nz) % view.ny;
+    const int64_t x = end / (view.nz * view.ny);
+    // GridIndexToLocationInGridFrame
+    ex = view.resolution * (static_cast<double>(x) + 0.5);
+    ey = view.resolution * (static_cast<double>(y) + 0.5);
+    ez = view.resolution * (static_cast<double>(z) + 0.5);
+  }
+  extrema[3 * cell] = ex;
+  extrema[3 * cell + 1] = ey;
+  extrema[3 * cell + 2] = ez;
+}
+
+__global__ void FillWordsKernel(uint32_t* words, int64_t count, uint32_t value, bool iota)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count)
+  {
+    words[i] = iota ? static_cast<uint32_t>(i) : value;
+  }
+}
+
 // Inverse of a rigid transform in the front ends' fixed order (grids.inverse_rigid).
 void InverseRigid(const double* m, double* out)
 {
@@ -562,6 +741,74 @@ int vgt_b200_sdf_fine_gradient_dev(
   FineGradientKernel<<<Blocks(num_points), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       view, d_points_xyz, num_points, nominal_window_size, d_gradients_xyz, d_valid); NoteKernelLaunch();
   VGT_CUDA_TRY(cudaGetLastError(), "FineGradientKernel launch");
+  return VGT_B200_OK;
+}
+
+int vgt_b200_sdf_local_extrema_map_dev(
+    const vgt_b200_sdf_view* sdf, int device, double* d_extrema_xyz, void* stream)
+{
+  SdfView view;
+  const int status = MakeView(sdf, &view);
+  if (status != VGT_B200_OK)
+  {
+    return status;
+  }
+  if (d_extrema_xyz == nullptr)
+  {
+    return FailInvalid("null extrema buffer");
+  }
+  const int64_t count = view.nx * view.ny * view.nz;
+  if (count >= 0x7fffffffLL)
+  {
+    return FailInvalid("grids of 2^31 cells or more are not supported by the extrema map");
+  }
+  ScopedDevice scoped(device);
+  VGT_CUDA_TRY(scoped.Status(), "cudaSetDevice");
+  KeepPoolMemory(device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StreamScratch<uint32_t> successor, target_a, target_b, lowest_a, lowest_b, basin_first, entry,
+      stamp;
+  for (StreamScratch<uint32_t>* buffer :
+       {&successor, &target_a, &target_b, &lowest_a, &lowest_b, &basin_first, &entry, &stamp})
+  {
+    VGT_CUDA_TRY(buffer->Allocate(count, s), "extrema map scratch allocation");
+  }
+  const unsigned blocks = Blocks(count);
+  ExtremaSuccessorKernel<<<blocks, kThreads, 0, s>>>(view, successor.get()); NoteKernelLaunch();
+  VGT_CUDA_TRY(cudaMemcpyAsync(target_a.get(), successor.get(), sizeof(uint32_t) * count,
+                               cudaMemcpyDeviceToDevice, s),
+               "copy successors");
+  FillWordsKernel<<<blocks, kThreads, 0, s>>>(lowest_a.get(), count, 0u, true); NoteKernelLaunch();
+  FillWordsKernel<<<blocks, kThreads, 0, s>>>(basin_first.get(), count, 0xffffffffu, false); NoteKernelLaunch();
+  VGT_CUDA_TRY(cudaMemsetAsync(stamp.get(), 0, sizeof(uint32_t) * count, s), "stamp reset");
+  uint32_t* target_in = target_a.get();
+  uint32_t* target_out = target_b.get();
+  uint32_t* lowest_in = lowest_a.get();
+  uint32_t* lowest_out = lowest_b.get();
+  int rounds = 1;
+  while ((int64_t{1} << rounds) < count)
+  {
+    rounds++;
+  }
+  for (int round = 0; round <= rounds; round++)
+  {
+    ExtremaJumpKernel<<<blocks, kThreads, 0, s>>>(target_in, lowest_in, count, target_out,
+                                                  lowest_out); NoteKernelLaunch();
+    uint32_t* swap = target_in;
+    target_in = target_out;
+    target_out = swap;
+    swap = lowest_in;
+    lowest_in = lowest_out;
+    lowest_out = swap;
+  }
+  ExtremaBasinKernel<<<blocks, kThreads, 0, s>>>(successor.get(), target_in, lowest_in, count,
+                                                 basin_first.get()); NoteKernelLaunch();
+  ExtremaEntryKernel<<<blocks, kThreads, 0, s>>>(successor.get(), target_in, lowest_in,
+                                                 basin_first.get(), count, stamp.get(),
+                                                 entry.get()); NoteKernelLaunch();
+  ExtremaWriteKernel<<<blocks, kThreads, 0, s>>>(view, successor.get(), target_in, lowest_in,
+                                                 entry.get(), d_extrema_xyz); NoteKernelLaunch();
+  VGT_CUDA_TRY(cudaGetLastError(), "local extrema map kernels");
   return VGT_B200_OK;
 }
 

@@ -263,3 +263,14 @@ class DeviceSignedDistanceField:
                                       stepsize_multiplier: float = 1.0 / 10.0):
         return self.ProjectLocationOutOfCollisionToMinimumDistance(points, 0.0,
                                                                    stepsize_multiplier)
+
+    def ComputeLocalExtremaMap(self) -> torch.Tensor:
+        """float64 [nx, ny, nz, 3]: per cell the grid-frame centre of the cell its gradient walk
+        ends at, +inf when it leaves the grid (signed_distance_field.hpp:1207-1231)."""
+        device = self.sdf.device
+        extrema = torch.empty(tuple(self.sdf.shape) + (3,), dtype=torch.float64, device=device)
+        code = _capi.library().vgt_b200_sdf_local_extrema_map_dev(
+            ctypes.byref(self._view), device.index or 0, extrema.data_ptr(),
+            _stream_handle(device))
+        _capi.check(code)
+        return extrema
