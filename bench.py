@@ -557,6 +557,11 @@ def run_ours(args):
     if not distributed:
         other_map_types = bench_tagged_map(local_rank, include_cpu=not args.skip_cpu)
 
+    # ---- the mesh rasterizer (an occupancy producer in front of the path) ----
+    mesh = None
+    if not distributed and not args.skip_voxelizer:
+        mesh = bench_mesh_rasterizer(dev, include_cpu=not args.skip_cpu)
+
     strong = None
     if not args.skip_strong:
         if n_gpus == 8:
@@ -606,9 +611,107 @@ def run_ours(args):
             line["other_configs"] = other_configs
         if other_map_types is not None:
             line["other_map_types"] = other_map_types
+        if mesh is not None:
+            line["mesh_rasterizer"] = mesh
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
+
+
+def _icosphere(subdivisions, radius, centre):
+    """A subdivided icosahedron: (vertices float64 [n, 3], triangles int32 [20 * 4^s, 3])."""
+    import numpy as np
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    vertices = [np.array(v, dtype=np.float64) / np.linalg.norm(v) for v in (
+        (-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t),
+        (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1))]
+    faces = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4),
+             (11, 10, 2), (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8),
+             (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    for _ in range(subdivisions):
+        cache, refined = {}, []
+
+        def midpoint(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = vertices[a] + vertices[b]
+                vertices.append(m / np.linalg.norm(m))
+                cache[key] = len(vertices) - 1
+            return cache[key]
+
+        for a, b, c in faces:
+            ab, bc, ca = midpoint(a, b), midpoint(b, c), midpoint(c, a)
+            refined += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        faces = refined
+    return (np.array(vertices) * radius + np.array(centre, dtype=np.float64),
+            np.array(faces, dtype=np.int32))
+
+
+def bench_mesh_rasterizer(dev, include_cpu=True):
+    """mesh_rasterizer::RasterizeMesh (mesh_rasterizer.cpp:205-230): a sphere of 81920 triangles
+    into a device-resident 512^3 map (vgt_b200_rasterize_mesh_dev, CUDA events), the host entry
+    on a 256^3 map, and the reference's CPU rasterizer on the same mesh beside them."""
+    import ctypes as ct
+    import numpy as np
+    import torch
+    from voxelized_geometry_tools_b200 import _capi
+    lib = _capi.library()
+    n, resolution = 512, 0.01
+    vertices, triangles = _icosphere(6, 2.2, (2.56, 2.56, 2.56))
+    d_vertices = torch.from_numpy(vertices).to(dev)
+    d_triangles = torch.from_numpy(triangles).to(dev)
+    occupancy = torch.zeros((n, n, n), dtype=torch.float32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    identity = np.ascontiguousarray(np.eye(4).T).reshape(16)
+    pointer = identity.ctypes.data_as(ct.POINTER(ct.c_double))
+    stream = torch.cuda.current_stream(dev)
+    times = []
+    for _ in range(6):
+        begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        begin.record(stream)
+        _capi.check(lib.vgt_b200_rasterize_mesh_dev(
+            d_vertices.data_ptr(), len(vertices), d_triangles.data_ptr(), len(triangles),
+            occupancy.data_ptr(), 4, n, n, n, resolution, pointer, pointer, 1,
+            dev.index or 0, flags.data_ptr(), stream.cuda_stream))
+        end.record(stream)
+        end.synchronize()
+        times.append(begin.elapsed_time(end))
+    _capi.check(lib.vgt_b200_rasterize_status(int(flags.item())))
+    kernel_ms = statistics.median(times[1:])
+    result = {"mesh": f"icosphere, {len(triangles)} triangles, {len(vertices)} vertices",
+              "grid": f"{n}^3 @ {resolution} m (device-resident)",
+              "kernel_ms": kernel_ms,
+              "mtriangles_per_s": len(triangles) / (kernel_ms * 1e-3) / 1e6,
+              "cells_filled": int((occupancy == 1.0).sum().item())}
+    # host entry (pageable numpy map in and out) on a 256^3 map
+    small = 256
+    host_map = np.zeros((small, small, small), dtype=np.float32)
+    half_vertices = vertices * 0.5
+    calls = []
+    for _ in range(3):
+        begin = time.perf_counter()
+        _capi.check(lib.vgt_b200_rasterize_mesh_f64(
+            half_vertices.ctypes.data, len(vertices), triangles.ctypes.data, len(triangles),
+            host_map.ctypes.data, 4, small, small, small, resolution, pointer, pointer, 1,
+            dev.index or 0))
+        calls.append(time.perf_counter() - begin)
+    result["host_entry"] = {"api": "vgt_b200_rasterize_mesh_f64 (256^3 pageable map in and out)",
+                            "ms_per_call": statistics.median(calls) * 1e3}
+    if include_cpu:
+        from oracle import oracle, reference_oracle
+        cpu_map = np.zeros((small, small, small), dtype=np.float32)
+        begin = time.perf_counter()
+        if reference_oracle.available():
+            reference_oracle.rasterize_mesh(half_vertices, triangles, cpu_map, resolution, None,
+                                            False, threads=host_threads())
+            kind, cores = "reference", host_threads()
+        else:
+            oracle.rasterize_mesh(half_vertices, triangles, cpu_map, resolution, None, True)
+            kind, cores = "port", 1
+        result["cpu"] = {"ms": (time.perf_counter() - begin) * 1e3, "kind": kind, "cores": cores,
+                         "grid": f"{small}^3", "equals_device_result": bool(
+                             np.array_equal(cpu_map, host_map))}
+    return result
 
 
 def bench_tagged_map(device_index, include_cpu=True):

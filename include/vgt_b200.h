@@ -41,7 +41,12 @@ enum
   VGT_B200_ERR_INVALID_ARGUMENT = 1,
   /* maps to std::runtime_error (cuda.cu:26-33 "[msg] Cuda error [str]", dev_pcv.hpp:34-46) */
   VGT_B200_ERR_DEVICE = 2,
-  VGT_B200_ERR_UNSUPPORTED = 3
+  VGT_B200_ERR_UNSUPPORTED = 3,
+  /* maps to std::runtime_error("Triangle is not contained by occupancy map")
+   * (mesh_rasterizer.cpp:191-196) */
+  VGT_B200_ERR_NOT_CONTAINED = 4,
+  /* maps to std::out_of_range (vertices.at() / triangles.at(), mesh_rasterizer.cpp:122-125) */
+  VGT_B200_ERR_OUT_OF_RANGE = 5
 };
 
 /* "no opposite-class voxel anywhere": the reference's +inf squared distance. */
@@ -339,6 +344,41 @@ VGT_B200_API int vgt_b200_sdf_project_out_of_collision_dev(
  * Grids of fewer than 2^31 cells; uses 32 bytes of stream-ordered scratch per cell. */
 VGT_B200_API int vgt_b200_sdf_local_extrema_map_dev(
     const vgt_b200_sdf_view* sdf, int device, double* d_extrema_xyz, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mesh rasterizer (an occupancy producer in front of the SDF path)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces mesh_rasterizer::RasterizeMesh (src/voxelized_geometry_tools/mesh_rasterizer.cpp:205-230,
+ * per triangle :105-203) for OccupancyMap (cell_bytes 4) and OccupancyComponentMap (cell_bytes 8,
+ * the float occupancy first): every cell whose centre is within sqrt(3)/2 voxels of a triangle
+ * (the reference's conservative closest-point test, evaluated in its operation order) gets
+ * occupancy 1.0; all other cell contents are left as they are.
+ *   vertices_xyz    double[num_vertices*3], the frame the map's origin transform maps into
+ *   triangles       int32[num_triangles*3] vertex indices
+ *   cells           host, nx*ny*nz cells of cell_bytes, x slowest, modified in place
+ *   x_wg, x_gw      the map's origin transform and its inverse, 4x4 column-major (Eigen .data())
+ *   enforce_contains  a touched cell outside the map is an error (VGT_B200_ERR_NOT_CONTAINED;
+ *                   the reference throws at the first one, so the map contents after an error
+ *                   are unspecified there and here)
+ * A triangle naming a missing vertex gives VGT_B200_ERR_OUT_OF_RANGE. */
+VGT_B200_API int vgt_b200_rasterize_mesh_f64(
+    const double* vertices_xyz, int64_t num_vertices, const int32_t* triangles,
+    int64_t num_triangles, void* cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz,
+    double resolution, const double* x_wg, const double* x_gw, int enforce_contains, int device);
+
+/* The same on device-resident arrays, asynchronous on `stream` (RasterizeMeshImpl,
+ * mesh_rasterizer.cpp:205-230). d_flags is one device int the kernel ORs its findings into;
+ * read it back after the stream has finished and pass it to vgt_b200_rasterize_status. */
+VGT_B200_API int vgt_b200_rasterize_mesh_dev(
+    const double* d_vertices_xyz, int64_t num_vertices, const int32_t* d_triangles,
+    int64_t num_triangles, void* d_cells, int cell_bytes, int64_t nx, int64_t ny, int64_t nz,
+    double resolution, const double* x_wg /* host, 16 */, const double* x_gw /* host, 16 */,
+    int enforce_contains, int device, int* d_flags, void* stream);
+
+/* The status (and error text) for a flag word of vgt_b200_rasterize_mesh_dev: the two throw
+ * sites of RasterizeTriangleImpl (mesh_rasterizer.cpp:122-125 and :191-196). */
+VGT_B200_API int vgt_b200_rasterize_status(int flags);
 
 /* ---------------------------------------------------------------------------------------------
  * Point cloud voxelization

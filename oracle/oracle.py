@@ -52,7 +52,8 @@ def _host_signature() -> str:
 
 def _sources_signature() -> str:
     digest = hashlib.sha1()
-    for name in ("edt_oracle.cpp", "voxelizer_oracle.cpp", "Makefile"):
+    for name in ("edt_oracle.cpp", "voxelizer_oracle.cpp", "mesh_rasterizer_oracle.cpp",
+                 "Makefile"):
         digest.update((_HERE / name).read_bytes())
     return digest.hexdigest()
 
@@ -112,6 +113,11 @@ def lib() -> ctypes.CDLL:
         handle.vgt_oracle_filter_f32.argtypes = [
             _c_i32p, ctypes.c_int32, _i64, ctypes.c_double, ctypes.c_int32,
             ctypes.c_int32, _int, _c_f32p]
+        handle.vgt_oracle_rasterize_mesh_f64.argtypes = [
+            _c_f64p, _i64, _c_i32p, _i64, _c_f32p, _i64, _i64, _i64, ctypes.c_double, _c_f64p,
+            _c_f64p, _int]
+        handle.vgt_oracle_mesh_map_extent_f64.argtypes = [
+            _c_f64p, _i64, ctypes.c_double, ctypes.POINTER(_i64), _c_f64p]
         _lib = handle
     return _lib
 
@@ -305,3 +311,53 @@ def voxelize(static_occupancy, clouds, voxel_size: float, percent_seen_free: flo
                             outlier_points_threshold, num_cameras_seen_free,
                             threads)
     return filtered, counts
+
+
+# ---- mesh rasterizer (mesh_rasterizer_oracle.cpp)
+RASTERIZE_OK, RASTERIZE_NOT_CONTAINED, RASTERIZE_BAD_INDEX = 0, 2, 3
+
+
+def _inverse_rigid_fixed_order(m):
+    """Inverse of a rigid 4x4 in the stand-in Eigen's order (ref_shim/Eigen/Geometry)."""
+    m = np.asarray(m, dtype=np.float64)
+    out = np.eye(4)
+    out[:3, :3] = m[:3, :3].T
+    for r in range(3):
+        out[r, 3] = -((out[r, 0] * m[0, 3] + out[r, 1] * m[1, 3]) + out[r, 2] * m[2, 3])
+    return out
+
+
+def rasterize_mesh(vertices, triangles, occupancy, resolution: float, origin_transform=None,
+                   enforce_contains: bool = False):
+    """Sets the cells of `occupancy` (float32 [nx, ny, nz], modified in place) the triangles
+    touch to 1.0; returns the status code (RASTERIZE_*)."""
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+    triangles = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+    assert occupancy.dtype == np.float32 and occupancy.flags.c_contiguous
+    origin = np.eye(4) if origin_transform is None else np.asarray(origin_transform, np.float64)
+    x_wg = np.ascontiguousarray(origin.T).reshape(-1)
+    x_gw = np.ascontiguousarray(_inverse_rigid_fixed_order(origin).T).reshape(-1)
+    return int(lib().vgt_oracle_rasterize_mesh_f64(
+        vertices.ctypes.data_as(_c_f64p), len(vertices), triangles.ctypes.data_as(_c_i32p),
+        len(triangles), occupancy.ctypes.data_as(_c_f32p), *occupancy.shape, float(resolution),
+        x_wg.ctypes.data_as(_c_f64p), x_gw.ctypes.data_as(_c_f64p), int(enforce_contains)))
+
+
+def mesh_map_extent(vertices, resolution: float):
+    """(dims, origin translation) of the map RasterizeMeshIntoOccupancyMap builds."""
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+    dims = (_i64 * 3)()
+    translation = np.zeros(3, dtype=np.float64)
+    _check(lib().vgt_oracle_mesh_map_extent_f64(
+        vertices.ctypes.data_as(_c_f64p), len(vertices), float(resolution), dims,
+        translation.ctypes.data_as(_c_f64p)), "mesh map extent")
+    return tuple(int(d) for d in dims), translation
+
+
+def rasterize_mesh_into_occupancy_map(vertices, triangles, resolution: float):
+    dims, translation = mesh_map_extent(vertices, resolution)
+    origin = np.eye(4)
+    origin[:3, 3] = translation
+    occupancy = np.zeros(dims, dtype=np.float32)
+    code = rasterize_mesh(vertices, triangles, occupancy, resolution, origin, True)
+    return occupancy, origin, code

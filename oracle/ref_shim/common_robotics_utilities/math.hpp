@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY -- stand-in for common_robotics_utilities/math.hpp with the one
-// function signed_distance_field.hpp calls. The real library is not in the reference tree
+// function signed_distance_field.hpp calls and the one mesh_rasterizer.cpp calls. The real library is not in the reference tree
 // (unvendored, unpinned), so this blend is a RESTATEMENT, the same one that
 // oracle/sdf_queries_oracle.py and csrc/sdf_queries.cu state: per axis the ratio
 // (query - low) / (high - low) clamped to [0, 1] (NaN passes through), each blend in the form
@@ -43,6 +43,25 @@ inline T TrilinearInterpolate(
   const T m = Interpolate(mm, pm, ry);
   const T p = Interpolate(mp, pp, ry);
   return Interpolate(m, p, rz);
+}
+// VectorProjection / VectorRejection (restated like the blend above: the component of `vector`
+// along `base_vector` is (base . vector / base . base) * base, zero for a zero base; the
+// rejection is vector minus that).
+inline Eigen::Vector3d VectorProjection(const Eigen::Vector3d& base_vector,
+                                        const Eigen::Vector3d& vector)
+{
+  const double base_squared_norm = base_vector.squaredNorm();
+  if (base_squared_norm > 0.0)
+  {
+    return base_vector * (base_vector.dot(vector) / base_squared_norm);
+  }
+  return Eigen::Vector3d(0.0, 0.0, 0.0);
+}
+
+inline Eigen::Vector3d VectorRejection(const Eigen::Vector3d& base_vector,
+                                       const Eigen::Vector3d& vector)
+{
+  return vector - VectorProjection(base_vector, vector);
 }
 }  // namespace math
 }  // namespace common_robotics_utilities

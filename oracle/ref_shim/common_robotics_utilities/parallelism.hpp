@@ -67,6 +67,13 @@ void StaticParallelForRangeLoop(
   const int64_t total = range_end - range_start;
   const int64_t base = total / threads;
   const int64_t extra = total % threads;
+  if (threads == 1)
+  {
+    // no parallel region: an exception thrown by the functor reaches the caller (the mesh
+    // rasterizer throws from inside its loop)
+    functor(ThreadWorkRange(range_start, range_end, 0));
+    return;
+  }
 #ifdef _OPENMP
 #pragma omp parallel for num_threads(threads) schedule(static)
 #endif

@@ -3,12 +3,22 @@
 // tracking grids is built from one prototype, cpu_pointcloud_voxelization.cpp:146-149).
 #pragma once
 
+#include <algorithm>
 #include <atomic>
+#include <stdexcept>
 
 namespace common_robotics_utilities
 {
 namespace utility
 {
+// (mesh_rasterizer.cpp:55: restated as min(max, max(min, value)), so a NaN value gives `min`)
+template <typename T>
+inline T ClampValue(const T& value, const T& min, const T& max)
+{
+  if (max < min) { throw std::invalid_argument("min > max"); }
+  return std::min(max, std::max(min, value));
+}
+
 template <typename T, std::memory_order kOrder>
 class CopyableMoveableAtomic
 {

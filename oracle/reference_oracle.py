@@ -229,3 +229,43 @@ def sdf_local_extrema_map(field, resolution: float, origin_transform=None) -> np
     if code != 0:
         raise RuntimeError("reference ComputeLocalExtremaMap failed")
     return out
+
+
+# ---- the reference's own mesh rasterizer (ref_shim/ref_mesh_rasterizer_entry.cpp)
+def rasterize_mesh(vertices, triangles, occupancy, resolution: float, origin_transform=None,
+                   enforce_contains: bool = False, threads: int = 1) -> int:
+    handle = lib()
+    handle.vgt_ref_rasterize_mesh.argtypes = [
+        _f64p, _i64, ctypes.POINTER(ctypes.c_int32), _i64, _f32p, _i64, _i64, _i64,
+        ctypes.c_double, _f64p, _int, _int]
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+    triangles = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+    assert occupancy.dtype == np.float32 and occupancy.flags.c_contiguous
+    origin = _origin_column_major(origin_transform)
+    return int(handle.vgt_ref_rasterize_mesh(
+        vertices.ctypes.data_as(_f64p), len(vertices),
+        triangles.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(triangles),
+        occupancy.ctypes.data_as(_f32p), *occupancy.shape, float(resolution),
+        origin.ctypes.data_as(_f64p), int(enforce_contains), int(threads)))
+
+
+def rasterize_mesh_into_occupancy_map(vertices, triangles, resolution: float, threads: int = 1):
+    """(occupancy [nx, ny, nz], origin 4x4, status) of RasterizeMeshIntoOccupancyMap."""
+    handle = lib()
+    handle.vgt_ref_rasterize_mesh_into_map.argtypes = [
+        _f64p, _i64, ctypes.POINTER(ctypes.c_int32), _i64, ctypes.c_double, _int,
+        ctypes.POINTER(_i64), _f64p, _f32p, _i64]
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+    triangles = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+    dims = (_i64 * 3)()
+    origin = np.zeros(16, dtype=np.float64)
+    args = (vertices.ctypes.data_as(_f64p), len(vertices),
+            triangles.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(triangles),
+            float(resolution), int(threads), dims, origin.ctypes.data_as(_f64p))
+    code = int(handle.vgt_ref_rasterize_mesh_into_map(*args, None, 0))
+    if code != 0:
+        return None, None, code
+    occupancy = np.zeros(tuple(int(d) for d in dims), dtype=np.float32)
+    code = int(handle.vgt_ref_rasterize_mesh_into_map(
+        *args, occupancy.ctypes.data_as(_f32p), occupancy.size))
+    return occupancy, origin.reshape(4, 4).T.copy(), code

@@ -16,6 +16,8 @@ OK = 0
 ERR_INVALID_ARGUMENT = 1
 ERR_DEVICE = 2
 ERR_UNSUPPORTED = 3
+ERR_NOT_CONTAINED = 4
+ERR_OUT_OF_RANGE = 5
 SQ_INF = 2 ** 31 - 1
 
 _f32p = ctypes.POINTER(ctypes.c_float)
@@ -115,6 +117,11 @@ SIGNATURES = {
                                         _vp]),
     "vgt_b200_filter_dev": (_int, [_vp, ctypes.c_int32, _i64, ctypes.POINTER(FilterOptions), _int,
                                    _vp, _vp]),
+    "vgt_b200_rasterize_mesh_f64": (_int, [_vp, _i64, _vp, _i64, _vp, _int, _i64, _i64, _i64, _dbl,
+                                           _f64p, _f64p, _int, _int]),
+    "vgt_b200_rasterize_mesh_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _int, _i64, _i64, _i64, _dbl,
+                                           _f64p, _f64p, _int, _int, _vp, _vp]),
+    "vgt_b200_rasterize_status": (_int, [_int]),
 }
 
 _library = None
@@ -153,6 +160,8 @@ def check(code: int) -> None:
         raise ValueError(message)        # std::invalid_argument
     if code == ERR_UNSUPPORTED:
         raise NotImplementedError(message)
+    if code == ERR_OUT_OF_RANGE:
+        raise IndexError(message)        # std::out_of_range
     raise RuntimeError(message)          # std::runtime_error
 
 

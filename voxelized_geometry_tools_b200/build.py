@@ -33,6 +33,8 @@ TRANSLATION_UNITS = [
     ("voxelizer_kernels.cu", ["-fmad=false"]),
     # the SDF queries evaluate the reference's double expressions as written
     ("sdf_queries.cu", ["-fmad=false"]),
+    # the mesh rasterizer's "cell touched" test is a double comparison mirrored as written
+    ("mesh_rasterizer.cu", ["-fmad=false"]),
 ]
 
 

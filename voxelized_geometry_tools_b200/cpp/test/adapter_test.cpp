@@ -20,6 +20,7 @@
 #include <string>
 
 #include <Eigen/Geometry>
+#include <voxelized_geometry_tools/mesh_rasterizer.hpp>
 #include <voxelized_geometry_tools/occupancy_component_map.hpp>
 #include <voxelized_geometry_tools/occupancy_map.hpp>
 #include <voxelized_geometry_tools/pointcloud_voxelization.hpp>
@@ -29,6 +30,7 @@
 #include <voxelized_geometry_tools/tagged_object_occupancy_map.hpp>
 
 #include "b200_cell_map_signed_distance_fields.hpp"
+#include "b200_mesh_rasterizer.hpp"
 #include "b200_pointcloud_voxelization.hpp"
 #include "b200_signed_distance_field_generation.hpp"
 
@@ -646,6 +648,105 @@ int TimeAdapter(const int64_t n)
   return 0;
 }
 
+// Port of test/mesh_rasterization_test.cpp (TestOccupancyMap :20-66, TestOccupancyComponentMap
+// :68-114) through the adapter, then the adapter against the reference's own CPU rasterizer
+// (linked in from the reference's mesh_rasterizer.cpp) on a closed mesh, cell for cell.
+template <typename MapType>
+void CheckReferenceTriangle(const MapType& occupancy_map)
+{
+  const auto occupancy = [&](const int64_t x, const int64_t y, const int64_t z)
+  { return occupancy_map.GetIndexImmutable(x, y, z).Value().Occupancy(); };
+  for (int64_t x = 0; x < occupancy_map.NumXVoxels(); x++)
+  {
+    for (int64_t y = 0; y < occupancy_map.NumYVoxels(); y++)
+    {
+      EXPECT_TRUE(occupancy(x, y, 0) == 0.0f);
+      if (x == 0 || y == 0 || y >= (occupancy_map.NumYVoxels() - x))
+      {
+        EXPECT_TRUE(occupancy(x, y, 1) == 0.0f);
+      }
+      else
+      {
+        EXPECT_TRUE(occupancy(x, y, 1) == 1.0f);
+      }
+    }
+  }
+}
+
+void MeshRasterizerTest()
+{
+  namespace gpu = mesh_rasterizer::b200;
+  const DegreeOfParallelism parallelism = DegreeOfParallelism::None();
+  const std::vector<Eigen::Vector3d> vertices = {
+      Eigen::Vector3d(0.0, 0.0, 0.0), Eigen::Vector3d(1.0, 0.0, 0.0),
+      Eigen::Vector3d(0.0, 1.0, 0.0)};
+  const std::vector<Eigen::Vector3i> triangles = {Eigen::Vector3i(0, 1, 2)};
+  CheckReferenceTriangle(
+      gpu::RasterizeMeshIntoOccupancyMap(vertices, triangles, 0.125, parallelism));
+  CheckReferenceTriangle(
+      gpu::RasterizeMeshIntoOccupancyComponentMap(vertices, triangles, 0.125, parallelism));
+
+  // an octahedron with its faces split once: device == the reference's CPU rasterizer
+  std::vector<Eigen::Vector3d> solid = {
+      Eigen::Vector3d(0.7, 0.0, 0.0), Eigen::Vector3d(-0.6, 0.0, 0.1),
+      Eigen::Vector3d(0.0, 0.5, 0.0), Eigen::Vector3d(0.1, -0.8, 0.0),
+      Eigen::Vector3d(0.0, 0.05, 0.9), Eigen::Vector3d(0.0, 0.0, -0.4)};
+  const std::vector<Eigen::Vector3i> faces = {
+      Eigen::Vector3i(0, 2, 4), Eigen::Vector3i(2, 1, 4), Eigen::Vector3i(1, 3, 4),
+      Eigen::Vector3i(3, 0, 4), Eigen::Vector3i(2, 0, 5), Eigen::Vector3i(1, 2, 5),
+      Eigen::Vector3i(3, 1, 5), Eigen::Vector3i(0, 3, 5)};
+  for (const double resolution : {0.05, 0.03125})
+  {
+    const auto device_map = gpu::RasterizeMeshIntoOccupancyMap(solid, faces, resolution,
+                                                               parallelism);
+    const auto cpu_map = mesh_rasterizer::RasterizeMeshIntoOccupancyMap(solid, faces, resolution,
+                                                                        parallelism);
+    EXPECT_TRUE(device_map.NumXVoxels() == cpu_map.NumXVoxels()
+                && device_map.NumYVoxels() == cpu_map.NumYVoxels()
+                && device_map.NumZVoxels() == cpu_map.NumZVoxels());
+    int64_t filled = 0, different = 0;
+    for (int64_t i = 0; i < cpu_map.NumTotalVoxels(); i++)
+    {
+      const float want = cpu_map.GetDataIndexImmutable(i).Occupancy();
+      filled += (want == 1.0f) ? 1 : 0;
+      different += (device_map.GetDataIndexImmutable(i).Occupancy() != want) ? 1 : 0;
+    }
+    EXPECT_TRUE(filled > 500);
+    EXPECT_TRUE(different == 0);
+  }
+
+  // RasterizeMesh / RasterizeTriangle into an existing map; errors as the reference throws them
+  const auto sizes = VoxelGridSizes::FromGridSizes(0.1, Eigen::Vector3d(1.0, 1.0, 1.0));
+  OccupancyMap small_map(Eigen::Isometry3d::FromTranslation(0.0, 0.0, 0.0), "world", sizes,
+                         OccupancyCell(0.0f));
+  OccupancyMap cpu_small = small_map;
+  gpu::RasterizeMesh(solid, faces, small_map, false, parallelism);
+  mesh_rasterizer::RasterizeMesh(solid, faces, cpu_small, false, parallelism);
+  int64_t different = 0;
+  for (int64_t i = 0; i < cpu_small.NumTotalVoxels(); i++)
+  {
+    different += (small_map.GetDataIndexImmutable(i).Occupancy()
+                  != cpu_small.GetDataIndexImmutable(i).Occupancy()) ? 1 : 0;
+  }
+  EXPECT_TRUE(different == 0);
+  bool threw = false;
+  try { gpu::RasterizeMesh(solid, faces, small_map, true, parallelism); }
+  catch (const std::runtime_error&) { threw = true; }
+  EXPECT_TRUE(threw);        // the solid leaves the unit map
+  threw = false;
+  try { gpu::RasterizeTriangle(solid, faces, faces.size(), small_map, false); }
+  catch (const std::out_of_range&) { threw = true; }
+  EXPECT_TRUE(threw);
+  threw = false;
+  try { gpu::RasterizeMesh(solid, {Eigen::Vector3i(0, 1, 6)}, small_map, false, parallelism); }
+  catch (const std::out_of_range&) { threw = true; }
+  EXPECT_TRUE(threw);
+  threw = false;
+  try { gpu::RasterizeMeshIntoOccupancyMap(solid, faces, 0.0, parallelism); }
+  catch (const std::invalid_argument&) { threw = true; }
+  EXPECT_TRUE(threw);
+}
+
 int main(int argc, char** argv)
 {
   if (vgt_b200_device_count() < 1)
@@ -664,6 +765,7 @@ int main(int argc, char** argv)
   CellMapTests<double>();
   TransformTest();
   FactoryTest();
+  MeshRasterizerTest();
   if (g_failures == 0)
   {
     std::printf("ADAPTER_TEST_OK\n");
