@@ -318,6 +318,7 @@ def window_line(classes, values, radius, step_budget=None, segment_rows=None, de
 
     out = [0] * n
     mask_r = (1 << radius) - 1
+    garbage = random.Random(n)
     if segment_rows is None:
         segment_rows = ((n + chunk - 1) // chunk) * chunk
     assert segment_rows % chunk == 0
@@ -340,6 +341,12 @@ def window_line(classes, values, radius, step_budget=None, segment_rows=None, de
         for base in range(first_row, end_row, chunk):
             composite = (ca << (2 * chunk)) | (cb << chunk) | cn
             rows = a + b + nx  # chunk-relative row r at index r + chunk
+            # (bits above 3 R: leftovers of older chunks in the kernel's class word - anything)
+            composite |= garbage.getrandbits(8) << (3 * chunk)
+            shift = max(3 * chunk - 32, 0)
+            boundaries = composite ^ (composite >> 1)
+            boundaries_low = boundaries & 0xFFFFFFFF
+            boundaries_reversed = brev32((boundaries >> shift) & 0xFFFFFFFF)
             # ---- phase A
             best = [0] * chunk
             for j in range(chunk):
@@ -350,14 +357,17 @@ def window_line(classes, values, radius, step_budget=None, segment_rows=None, de
                 for g in range(j >> 1, (j >> 1) + radius + 1):
                     for index in (2 * g, 2 * g + 1):
                         acc = min(acc, u16(rows[index] + (index - chunk - j) ** 2))
-                x = (composite >> (chunk - 1 - j)) & 0xFFFFFFFF
-                query_class = (x >> radius) & 1
+                query_class = (composite >> (2 * chunk - 1 - j)) & 1
                 assert query_class == classes[q]
-                diff = x ^ (0xFFFFFFFF if query_class else 0)
-                both = ((diff & mask_r) | (brev32(diff) >> (31 - 2 * radius))) & mask_r
-                e = radius - 31 + clz32(both)
-                # (no opposite-class row inside the window: no such candidate)
-                best[j] = min(acc, e * e) if both else acc
+                # boundary bits (bit t: the rows at bits t and t + 1 differ); the nearest
+                # opposite-class row after / before the row at bit p from one shift and one
+                # count of leading zeros per side; min with R = none inside the window
+                p = 2 * chunk - 1 - j
+                after = clz32((boundaries_low << (32 - p)) & 0xFFFFFFFF)
+                before = clz32((boundaries_reversed << (p - shift)) & 0xFFFFFFFF)
+                index = min(after, before, radius)
+                e_squared = (index + 1) ** 2 if index < radius else 0xFFFF
+                best[j] = min(acc, e_squared)
             # ---- phase B
             if max(best) >= far:
                 chunk_class = (cb >> (chunk - 1)) & 1

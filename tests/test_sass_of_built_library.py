@@ -1,8 +1,9 @@
 """CPU: the SASS of the built library carries the instructions the design relies on (cuobjdump
 reads the sm_100a cubin without a GPU). A regression here means the compiler no longer emits what
 DESIGN.md section 3 describes, whatever the timings say later:
-  * the window kernels' candidate search is VIADDMNMX.U16x2 (two rows per instruction) and the
-    extended search VIADDMNMX.U32, no integer min emulation;
+  * the window kernels' candidate search is VIADDMNMX.U16x2 (two rows per instruction), the
+    nearest opposite-class row comes from FLO + VIMNMX3 + SHFL, and the bookkeeping around them
+    (addresses, shifts, bit extraction) is multiplies on the fma pipe;
   * the staged window kernels fetch their rows with LDGSTS (cp.async) and wait on LDGDEPBAR /
     DEPBAR groups, the others with plain loads;
   * the z scan moves 16 bytes per lane and instruction;
@@ -57,8 +58,13 @@ def test_window_kernels_use_the_packed_add_min(sass_by_function):
         # rows x (R + 1) pairs, plus the chunk-joint search (register tier + four rows per side
         # and round from memory, R / 2 paired add-mins each)
         assert packed >= 3 * radius * (radius + 1) + 8 * (radius // 2), (name, packed)
-        assert "VIADDMNMX.U32" not in sass, name      # no row-by-row 32-bit search any more
-        assert "BREV" in sass and "FLO" in sass, name  # nearest opposite-class row
+        # nearest opposite-class row: boundary word reversed once per chunk, one count of
+        # leading zeros per side, a three-way minimum and a look-up across the warp
+        assert "BREV" in sass and "FLO" in sass, name
+        assert "SHFL.IDX" in sass and "VIMNMX3" in sass, name
+        # row addresses, bit extraction and shifts by constants run on the fma pipe: multiplies
+        # by powers of two read from constant bank 3 (ptxas cannot fold them back into shifts)
+        assert len(re.findall(r"IMAD(\.HI)?(\.U32)? R\d+, R\d+, (c\[0x3\]|UR\d+)", sass)) >= 4 * radius, name
 
 
 def test_staged_window_kernels_use_async_copies(sass_by_function):

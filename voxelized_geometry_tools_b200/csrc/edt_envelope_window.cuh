@@ -140,18 +140,6 @@ __device__ __forceinline__ void BulkCopyRow(uint32_t* shared_row, const void* gl
       : "memory");
 }
 
-// classes = (classes << 1) | (class bit of word): one funnel shift per 32 bits of the class word.
-__device__ __forceinline__ void AppendClassBit(uint32_t& classes, const uint32_t word)
-{
-  classes = __funnelshift_l(word, classes, 1);
-}
-__device__ __forceinline__ void AppendClassBit(uint64_t& classes, const uint32_t word)
-{
-  const uint32_t low = static_cast<uint32_t>(classes);
-  const uint32_t high = __funnelshift_l(low, static_cast<uint32_t>(classes >> 32), 1);
-  classes = (static_cast<uint64_t>(high) << 32) | __funnelshift_l(word, low, 1);
-}
-
 // Deepest row distance the 16-bit joint search looks at: clamped values (kSaturated) plus squared
 // offsets must fit 16 bits and a result is only exact below kSaturated (0x7800: 175 voxels).
 // The furthest candidate of a round is kJointDeepestCap + R - 1 rows from its row:
@@ -162,6 +150,61 @@ static_assert((kJointDeepestCap + 13) * (kJointDeepestCap + 13) + static_cast<in
 // "No opposite-class row in the neighbouring chunk" for the joint search: far enough that its
 // square beats no real candidate, small enough that (kNoRow + R)^2 fits 16 bits.
 constexpr uint32_t kNoRow = 200u;
+
+// The window kernel is bound by the alu pipe (VIADDMNMX, LOP3, SHF, PRMT, VIMNMX, IADD3, LEA);
+// the fma pipe next to it is nearly idle. Address arithmetic, shifts by constants and bit
+// extraction can all be written as integer multiplies, which run on the fma pipe - but ptxas
+// turns a multiply by a constant power of two back into a shift or LEA. So the multipliers come
+// from constant memory, which ptxas cannot fold and which an IMAD takes as a direct operand.
+__constant__ uint32_t kSmallNumbers[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+__constant__ uint32_t kPowersOfTwo[32] = {
+    1u << 0,  1u << 1,  1u << 2,  1u << 3,  1u << 4,  1u << 5,  1u << 6,  1u << 7,
+    1u << 8,  1u << 9,  1u << 10, 1u << 11, 1u << 12, 1u << 13, 1u << 14, 1u << 15,
+    1u << 16, 1u << 17, 1u << 18, 1u << 19, 1u << 20, 1u << 21, 1u << 22, 1u << 23,
+    1u << 24, 1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30, 1u << 31};
+
+// base + stride * row as ONE wide multiply-add instead of a 64-bit add chain.
+template <typename Pointer>
+__device__ __forceinline__ Pointer OffsetRows(Pointer base, uint32_t stride_bytes, uint32_t row)
+{
+  uint64_t address;
+  asm("mad.wide.u32 %0, %1, %2, %3;"
+      : "=l"(address)
+      : "r"(stride_bytes), "r"(row), "l"(reinterpret_cast<uint64_t>(base)));
+  return reinterpret_cast<Pointer>(address);
+}
+// (row known at compile time, 0 .. 15)
+template <int kRow, typename Pointer>
+__device__ __forceinline__ Pointer OffsetRowsBy(Pointer base, uint32_t stride_bytes)
+{
+  static_assert(kRow >= 0 && kRow < 16, "kSmallNumbers");
+  return OffsetRows(base, stride_bytes, kSmallNumbers[kRow]);
+}
+// word << kBits and word >> kBits on the fma pipe
+template <int kBits>
+__device__ __forceinline__ uint32_t ShiftLeftByMultiply(uint32_t word)
+{
+  static_assert(kBits >= 0 && kBits < 32, "kPowersOfTwo");
+  return word * kPowersOfTwo[kBits];
+}
+template <int kBits>
+__device__ __forceinline__ uint32_t ShiftRightByMultiply(uint32_t word)
+{
+  static_assert(kBits >= 1 && kBits <= 32, "kPowersOfTwo");
+  return __umulhi(word, kPowersOfTwo[32 - kBits]);
+}
+
+// Number of leading zero bits; 0xffffffff when the word is 0 (one FLO).
+__device__ __forceinline__ uint32_t LeadingZeros(uint32_t word)
+{
+  uint32_t count;
+  asm("bfind.shiftamt.u32 %0, %1;" : "=r"(count) : "r"(word));
+  return count;
+}
+
+// Accumulators per row of the window minimum (the R rows of a chunk are independent chains
+// already; more than one accumulator per row costs a merge per row).
+constexpr int kWindowChains = 1;
 
 // Calls f(std::integral_constant<int, 0>{}) ... f(std::integral_constant<int, kCount - 1>{}).
 template <int kCount, int kIndex = 0, typename F>
@@ -234,14 +277,22 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   }
   const uint32_t outer = tile_index / tiles_per_outer;
   const uint32_t wanted_column = (tile_index - outer * tiles_per_outer) * kWarp + lane;
-  // (the pilot stores nothing)
-  const bool active = wanted_column < static_cast<uint32_t>(family.inner_count)
-      && block_select != kSelectPilot;
-  // Lanes past the last column shadow the last one (loads only), so that the whole warp stays
-  // converged for the votes.
-  const uint32_t column = active ? wanted_column : static_cast<uint32_t>(family.inner_count - 1);
+  // Lanes past the last column shadow the last one, so that the whole warp stays converged for
+  // the votes: they compute and store exactly what the lane of that column stores, to the same
+  // addresses (no predicate on the stores). The pilot stores nothing - it skips phase C - and
+  // all its lanes read the family's last column (one sector per row).
+  const bool probe_only = block_select == kSelectPilot;
+  const uint32_t column = probe_only
+      ? static_cast<uint32_t>(family.inner_count - 1)
+      : min(wanted_column, static_cast<uint32_t>(family.inner_count - 1));
   const int64_t first = static_cast<int64_t>(outer) * family.outer_stride + column;
-  const uint32_t stride_bytes = family.stride_bytes;
+  // The two strides live in per-lane registers that ptxas cannot prove uniform (the top bit of
+  // the lane's column is 0: a family has fewer than 2^31 columns): otherwise it forms
+  // stride * row in the uniform datapath and adds the product to the lane's pointer with a
+  // two-instruction 64-bit add on the alu pipe; this way a row address is one IMAD.WIDE on the
+  // fma pipe.
+  const uint32_t lane_zero = column >> 31;
+  const uint32_t stride_bytes = family.stride_bytes + lane_zero;
   // (pinned in registers: the compiler otherwise re-derives both from the kernel parameters at
   // every use inside the unrolled chunk bodies)
   const char* line = reinterpret_cast<const char*>(in + first);
@@ -253,7 +304,7 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   };
   char* write_origin = reinterpret_cast<char*>(out + first);
   asm volatile("" : "+l"(write_origin));
-  const uint32_t out_stride_bytes = family.out_stride_bytes;
+  const uint32_t out_stride_bytes = family.out_stride_bytes + lane_zero;
 
   // Finalize mode: the largest squared distance this lane has emitted for a free voxel (low
   // half) and for a filled voxel (high half). The magnitude is monotone in the squared distance,
@@ -262,6 +313,21 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   // finite value means both classes exist, so the smallest free / filled values cannot be the
   // extrema. 0 = no voxel of that class emitted (a real squared distance is at least 1).
   uint32_t lane_extrema = 0;
+  // Float output: the extrema straight from the bits of the emitted values. As signed integers
+  // every positive float is above every negative one and positive floats order like their bits:
+  // the signed maximum is the largest free value (still negative: no free voxel emitted). As
+  // unsigned integers negative floats are above positive ones and order by magnitude: the
+  // unsigned maximum is the most negative filled value (sign bit clear: no filled voxel).
+  int32_t largest_signed = static_cast<int32_t>(0x80000000u);
+  uint32_t largest_unsigned = 0u;
+  // The squared distance to the nearest opposite-class row as a look-up across the warp: lane d - 1
+  // holds d^2 for d = 1 .. R and 0xffff ("no such row") otherwise, once in the low half (even
+  // rows) and once in the high half (odd rows), the other half 0xffff, so that one three-way
+  // paired minimum merges both rows of a pair.
+  const uint32_t lane_square = (lane < kR) ? static_cast<uint32_t>((lane + 1) * (lane + 1)) : 0xffffu;
+  uint32_t squares_low_half = 0xffff0000u | lane_square;
+  uint32_t squares_high_half = (lane_square << 16) | 0xffffu;
+  asm volatile("" : "+r"(squares_low_half), "+r"(squares_high_half));
   int32_t border_yz = 0x7fffffff;
   if constexpr (kBorder)
   {
@@ -408,10 +474,9 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   int next_part_start = first_row;
 
   // one row of the output; write_base = address of the chunk's first output row
-  const auto emit_row = [&](const int q, const int j, char* const write_base, const uint32_t filled,
-                            uint32_t squared)
+  const auto emit_row = [&](const int q, const int j, char* const write_base, const uint32_t word)
   {
-    char* write_at = write_base + static_cast<uint64_t>(out_stride_bytes) * static_cast<uint32_t>(j);
+    char* write_at = OffsetRows(write_base, out_stride_bytes, kSmallNumbers[j]);
     if constexpr (kSend)
     {
       // Send layout (see LineFamily): row q is at send_origin + q * out_stride_bytes; the origin
@@ -466,10 +531,7 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     // (the finalizing pass emits whole chunks: emit_finalized)
     if constexpr (kMode == kEmitPacked)
     {
-      if (active)
-      {
-        __stcs(reinterpret_cast<uint32_t*>(write_at), (filled << 31) | squared);
-      }
+      __stcs(reinterpret_cast<uint32_t*>(write_at), word);
     }
   };
 
@@ -481,14 +543,16 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
                                   auto edge)
   {
     constexpr bool kEdge = decltype(edge)::value;
-    const Out* const table = static_cast<const Out*>(finalize.magnitude_table);
+    // (a per-lane pointer, see lane_zero: the look-up address is one IMAD.WIDE)
+    const Out* const table = static_cast<const Out*>(finalize.magnitude_table) + lane_zero;
     Out magnitudes[kR];
     uint32_t squares[kR];
 #pragma unroll
     for (int j = 0; j < kR; j++)
     {
       const int q = base + j;
-      uint32_t squared = (j & 1) ? (best[j >> 1] >> 16) : (best[j >> 1] & 0xffffu);
+      // (the odd row of a pair comes down by a multiply: fma pipe)
+      uint32_t squared = (j & 1) ? ShiftRightByMultiply<16>(best[j >> 1]) : (best[j >> 1] & 0xffffu);
       if constexpr (kBorder)
       {
         int32_t border = border_yz;
@@ -505,25 +569,53 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       magnitudes[j] = Out(0);
       if (!kEdge || q <= last_row)  // warp-uniform
       {
-        magnitudes[j] = __ldg(table + squared);
+        magnitudes[j] = __ldg(OffsetRows(table, kSmallNumbers[sizeof(Out)], squared));
       }
     }
-#pragma unroll
-    for (int j = 0; j < kR; j++)
+    if constexpr (sizeof(Out) == 4)
     {
-      const int q = base + j;
-      if (!kEdge || q <= last_row)  // warp-uniform
+      uint32_t bits[kR];
+#pragma unroll
+      for (int j = 0; j < kR; j++)
       {
-        const uint32_t filled = static_cast<uint32_t>(classes >> (2 * kR - 1 - j)) & 1u;
-        const Out value = filled ? -magnitudes[j] : magnitudes[j];
-        if (active)
+        // the class of row j in bit 31, flipped into the sign of the magnitude (never zero)
+        const uint32_t sign = static_cast<uint32_t>(classes) * kPowersOfTwo[32 - 2 * kR + j];
+        bits[j] = __float_as_uint(magnitudes[j]) ^ (sign & 0x80000000u);
+        if (!kEdge || base + j <= last_row)  // warp-uniform
         {
-          __stcs(reinterpret_cast<Out*>(write_base + static_cast<uint64_t>(out_stride_bytes)
-                                                        * static_cast<uint32_t>(j)),
-                 value);
+          __stcs(reinterpret_cast<uint32_t*>(
+                     OffsetRows(write_base, out_stride_bytes, kSmallNumbers[j])),
+                 bits[j]);
         }
-        // free: the low half, filled: the high half (one multiply on the fma pipe)
-        lane_extrema = __vmaxu2(lane_extrema, squares[j] * (filled * 0xffffu + 1u));
+        else
+        {
+          bits[j] = bits[0];  // (row 0 of a chunk is always inside the line)
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kR; j += 2)
+      {
+        largest_signed = __vimax3_s32(largest_signed, static_cast<int32_t>(bits[j]),
+                                      static_cast<int32_t>(bits[j + 1]));
+        largest_unsigned = __vimax3_u32(largest_unsigned, bits[j], bits[j + 1]);
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < kR; j++)
+      {
+        const int q = base + j;
+        if (!kEdge || q <= last_row)  // warp-uniform
+        {
+          const uint32_t filled = static_cast<uint32_t>(classes >> (2 * kR - 1 - j)) & 1u;
+          const Out value = filled ? -magnitudes[j] : magnitudes[j];
+          __stcs(reinterpret_cast<Out*>(
+                     OffsetRows(write_base, out_stride_bytes, kSmallNumbers[j])),
+                 value);
+          // free: the low half, filled: the high half (one multiply on the fma pipe)
+          lane_extrema = __vmaxu2(lane_extrema, squares[j] * (filled * 0xffffu + 1u));
+        }
       }
     }
   };
@@ -554,6 +646,9 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     // The next chunk (rows base + R .. base + 2 R - 1) joins the register window: clamped, packed
     // in pairs, class bits filed. Then the loads of the chunk after it are issued: they have
     // the whole chunk to land.
+    // (multiplies instead of masks, shifts and funnel shifts: they run on the fma pipe. Twice a
+    // word drops its class bit; the doubled values are clamped, packed and halved together.)
+    uint32_t chunk_classes = 0;
 #pragma unroll
     for (int j = 0; j < kR; j += 2)
     {
@@ -561,16 +656,24 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
           kStage ? stage_lane[(absorb_buffer * kR + j) * kWarp] : raw[kStage ? 0 : j];
       const uint32_t high_word =
           kStage ? stage_lane[(absorb_buffer * kR + j + 1) * kWarp] : raw[kStage ? 0 : j + 1];
-      uint32_t low = clamped_value(low_word);
-      uint32_t high = clamped_value(high_word);
+      uint32_t low = min(ShiftLeftByMultiply<1>(low_word), 2u * kSaturated);
+      uint32_t high = min(ShiftLeftByMultiply<1>(high_word), 2u * kSaturated);
       if constexpr (kEdge)
       {
-        low = (base + j + kR > last_row) ? kSaturated : low;
-        high = (base + j + kR + 1 > last_row) ? kSaturated : high;
+        low = (base + j + kR > last_row) ? 2u * kSaturated : low;
+        high = (base + j + kR + 1 > last_row) ? 2u * kSaturated : high;
       }
-      next_pairs[j >> 1] = __byte_perm(low, high, 0x5410);
-      AppendClassBit(classes, low_word);
-      AppendClassBit(classes, high_word);
+      next_pairs[j >> 1] = ShiftRightByMultiply<1>(__byte_perm(low, high, 0x5410));
+      chunk_classes = chunk_classes * kPowersOfTwo[1] + ShiftRightByMultiply<31>(low_word);
+      chunk_classes = chunk_classes * kPowersOfTwo[1] + ShiftRightByMultiply<31>(high_word);
+    }
+    if constexpr (sizeof(ClassWord) == 4)
+    {
+      classes = classes * kPowersOfTwo[kR] + chunk_classes;
+    }
+    else
+    {
+      classes = (classes << kR) | chunk_classes;
     }
     if constexpr (kStage != 0)
     {
@@ -586,9 +689,9 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       for (int j = 0; j < kR; j++)
       {
         const char* const next_row = kEdge
-            ? line + static_cast<uint64_t>(stride_bytes)
-                * static_cast<uint32_t>(min(base + kAhead * kR + j, last_row))
-            : read_next + static_cast<uint64_t>(stride_bytes) * static_cast<uint32_t>(j);
+            ? OffsetRows(line, stride_bytes,
+                         static_cast<uint32_t>(min(base + kAhead * kR + j, last_row)))
+            : OffsetRows(read_next, stride_bytes, kSmallNumbers[j]);
         raw[j] = *reinterpret_cast<const uint32_t*>(next_row);
       }
     }
@@ -598,6 +701,24 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     const auto window_rows = [&](auto with_classes)
     {
       constexpr bool kWithClasses = decltype(with_classes)::value;
+      // Boundary bits of the class word: bit t = the row at bit t and the (earlier) row at bit
+      // t + 1 are of different classes. For the row at bit p, the nearest opposite-class row
+      // AFTER it is the highest boundary bit below p, the nearest one BEFORE it the lowest
+      // boundary bit at or above p, i.e. the highest bit of the reversed word below 32 - p. Each
+      // side: one shift that drops the bits beyond the row (a multiply, fma pipe) and one
+      // count of leading zeros = distance - 1 (xu pipe); then ONE three-way minimum with R
+      // (= "none inside the window") and a look-up across the warp.
+      // kShift: with a 64-bit class word (3 R > 32) the earlier side looks at bits kShift ..
+      // kShift + 31.
+      constexpr int kShift = (3 * kR > 32) ? 3 * kR - 32 : 0;
+      uint32_t boundaries_low = 0;
+      uint32_t boundaries_reversed = 0;
+      if constexpr (kWithClasses)
+      {
+        const ClassWord boundaries = classes ^ (classes >> 1);
+        boundaries_low = static_cast<uint32_t>(boundaries);
+        boundaries_reversed = __brev(static_cast<uint32_t>(boundaries >> kShift));
+      }
 #pragma unroll
       for (int j = 0; j < kR; j += 2)
       {
@@ -611,8 +732,13 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
           const int jr = j + r;
           // Pairs g = (jr >> 1) .. (jr >> 1) + R of the 3 R / 2 pairs in registers cover the
           // rows q - R .. q + R plus one row at distance R + 1 (a true candidate like the
-          // others). Two accumulators: half the dependent chain.
-          uint32_t chains[2] = {0xffffffffu, 0xffffffffu};
+          // others).
+          uint32_t chains[kWindowChains];
+#pragma unroll
+          for (int c = 0; c < kWindowChains; c++)
+          {
+            chains[c] = 0xffffffffu;
+          }
 #pragma unroll
           for (int t = 0; t <= kR; t++)
           {
@@ -627,28 +753,36 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
                 : ((g < 2 * kPairs)
                        ? current_pairs[(g >= kPairs && g < 2 * kPairs) ? g - kPairs : 0]
                        : next_pairs[(g >= 2 * kPairs) ? g - 2 * kPairs : 0]);
-            chains[t & 1] = __viaddmin_u16x2(pair, offsets, chains[t & 1]);
+            chains[t % kWindowChains] = __viaddmin_u16x2(pair, offsets, chains[t % kWindowChains]);
           }
-          row_pair[r] = __vminu2(chains[0], chains[1]);
+          row_pair[r] = chains[0];
+#pragma unroll
+          for (int c = 1; c < kWindowChains; c++)
+          {
+            row_pair[r] = __vminu2(row_pair[r], chains[c]);
+          }
           if constexpr (kWithClasses)
           {
-            // class window of row q: bit R = row q, bit R - d = row q + d, bit R + d = row q - d
-            const uint32_t window = static_cast<uint32_t>(classes >> (kR - 1 - jr));
-            const uint32_t same =
-                static_cast<uint32_t>(static_cast<int32_t>(window << (31 - kR)) >> 31);
-            const uint32_t differs = window ^ same;
-            // rows at distance d on either side folded onto bit R - d; highest set bit = nearest
-            const uint32_t folded = (differs | (__brev(differs) >> (31 - 2 * kR))) & kSideMask;
-            const int nearest = kR - 31 + __clz(static_cast<int>(folded));
-            // (no opposite-class row inside the window: no such candidate)
-            nearest_pair[r] = (folded != 0u) ? static_cast<uint32_t>(nearest * nearest) : 0xffffu;
+            // the row sits at bit p of the class word
+            const int p = 2 * kR - 1 - jr;
+            const uint32_t after = LeadingZeros(boundaries_low * kPowersOfTwo[32 - p]);
+            const uint32_t before = LeadingZeros(boundaries_reversed * kPowersOfTwo[p - kShift]);
+            // squared, in the half of its row (0xffff in the other half and for "none")
+            nearest_pair[r] = __shfl_sync(0xffffffffu, r == 0 ? squares_low_half : squares_high_half,
+                                          __vimin3_u32(after, before, static_cast<uint32_t>(kR)));
           }
         }
-        uint32_t both = __vminu2(__byte_perm(row_pair[0], row_pair[1], 0x5410),
-                                 __byte_perm(row_pair[0], row_pair[1], 0x7632));
+        uint32_t both;
         if constexpr (kWithClasses)
         {
-          both = __vminu2(both, __byte_perm(nearest_pair[0], nearest_pair[1], 0x5410));
+          both = __vimin3_u16x2(__byte_perm(row_pair[0], row_pair[1], 0x5410),
+                                __byte_perm(row_pair[0], row_pair[1], 0x7632),
+                                __vminu2(nearest_pair[0], nearest_pair[1]));
+        }
+        else
+        {
+          both = __vminu2(__byte_perm(row_pair[0], row_pair[1], 0x5410),
+                          __byte_perm(row_pair[0], row_pair[1], 0x7632));
         }
         if constexpr (kEdge)
         {
@@ -826,20 +960,26 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       }
     }
     // ---------------------------------------------------------------------------------- phase C
-    if (!over_budget)
+    if (!over_budget && !probe_only)
     {
       if constexpr (kMode == kEmitPacked)
       {
+        // the class bits of this chunk's rows: row j at bit R - 1 - j
+        const uint32_t chunk_only = static_cast<uint32_t>(classes >> kR) & kSideMask;
 #pragma unroll
         for (int j = 0; j < kR; j++)
         {
           const int q = base + j;
           if (!kEdge || q <= last_row)  // warp-uniform
           {
-            const uint32_t filled = static_cast<uint32_t>(classes >> (2 * kR - 1 - j)) & 1u;
-            const uint32_t squared =
-                (j & 1) ? (best_pairs[j >> 1] >> 16) : (best_pairs[j >> 1] & 0xffffu);
-            emit_row(q, j, write_base, filled, squared);
+            // the class of row j moved to bit 31 with zeros in the low half (a multiply); the
+            // squared distance of an odd row comes down by a multiply too, and ONE logic
+            // operation assembles the word (values stay below 0x8000: bit 15 is clear)
+            const uint32_t filled = chunk_only * kPowersOfTwo[32 - kR + j];
+            const uint32_t pair = best_pairs[j >> 1];
+            const uint32_t word = (j & 1) ? ((filled & 0x80000000u) | ShiftRightByMultiply<16>(pair))
+                                          : ((filled | pair) & 0x8000ffffu);
+            emit_row(q, j, write_base, word);
           }
         }
       }
@@ -969,12 +1109,21 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
     // the lane's extrema as values: +magnitude of its deepest free voxel, -magnitude of its
     // deepest filled voxel (neutral elements where the lane emitted none of a class)
     const Out* const table = static_cast<const Out*>(finalize.magnitude_table);
-    const uint32_t deepest_free = lane_extrema & 0xffffu;
-    const uint32_t deepest_filled = lane_extrema >> 16;
-    const Out lane_max =
-        deepest_free != 0u ? __ldg(table + deepest_free) : -PositiveInfinity<Out>();
-    const Out lane_min =
-        deepest_filled != 0u ? -__ldg(table + deepest_filled) : PositiveInfinity<Out>();
+    Out lane_max;
+    Out lane_min;
+    if constexpr (sizeof(Out) == 4)
+    {
+      lane_max = largest_signed >= 0 ? __int_as_float(largest_signed) : -PositiveInfinity<Out>();
+      lane_min = (largest_unsigned >> 31) != 0u ? __uint_as_float(largest_unsigned)
+                                                : PositiveInfinity<Out>();
+    }
+    else
+    {
+      const uint32_t deepest_free = lane_extrema & 0xffffu;
+      const uint32_t deepest_filled = lane_extrema >> 16;
+      lane_max = deepest_free != 0u ? __ldg(table + deepest_free) : -PositiveInfinity<Out>();
+      lane_min = deepest_filled != 0u ? -__ldg(table + deepest_filled) : PositiveInfinity<Out>();
+    }
     Key key_min = OrderedKey(lane_min);
     Key key_max = OrderedKey(lane_max);
 #pragma unroll
