@@ -202,6 +202,14 @@ __device__ __forceinline__ uint32_t LeadingZeros(uint32_t word)
   return count;
 }
 
+// Build-time experiment switches (profiles/r2_experiments.md records the outcomes).
+#ifndef VGT_WINDOW_ONE_CLASS_PATH
+#define VGT_WINDOW_ONE_CLASS_PATH 0
+#endif
+#ifndef VGT_WINDOW_SHIFT_CHAINS
+#define VGT_WINDOW_SHIFT_CHAINS 1
+#endif
+
 // Accumulators per row of the window minimum (the R rows of a chunk are independent chains
 // already; more than one accumulator per row costs a merge per row).
 constexpr int kWindowChains = 1;
@@ -320,6 +328,19 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   // unsigned maximum is the most negative filled value (sign bit clear: no filled voxel).
   int32_t largest_signed = static_cast<int32_t>(0x80000000u);
   uint32_t largest_unsigned = 0u;
+  // Finalize mode: the head of the magnitude table (squares below kFar, all a certified chunk
+  // can emit) copied into shared memory once per block.
+  __shared__ Out near_magnitudes[(kMode != kEmitPacked) ? kFar : 1];
+  if constexpr (kMode != kEmitPacked)
+  {
+    static_assert(kWindowWarpsPerBlock == 1, "one copy per warp: only __syncwarp orders it");
+    const Out* const table = static_cast<const Out*>(finalize.magnitude_table);
+    for (uint32_t i = lane; i < kFar; i += kWarp)
+    {
+      near_magnitudes[i] = __ldg(table + i);
+    }
+    __syncwarp();
+  }
   // The squared distance to the nearest opposite-class row as a look-up across the warp: lane d - 1
   // holds d^2 for d = 1 .. R and 0xffff ("no such row") otherwise, once in the low half (even
   // rows) and once in the high half (odd rows), the other half 0xffff, so that one three-way
@@ -540,9 +561,13 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   // least, see MagnitudeTable::Build: every value this kernel emits is inside it), then sign,
   // store and the two integer extrema.
   const auto emit_finalized = [&](const int base, char* const write_base, const uint32_t* best,
-                                  auto edge)
+                                  auto edge, auto near)
   {
     constexpr bool kEdge = decltype(edge)::value;
+    // kNear: every row of the chunk certified itself (all squares below kFar): the magnitudes
+    // come from the block's copy of the head of the table in shared memory - a 32-bit address,
+    // one multiply-add - instead of a 64-bit address into the global table
+    constexpr bool kNear = decltype(near)::value;
     // (a per-lane pointer, see lane_zero: the look-up address is one IMAD.WIDE)
     const Out* const table = static_cast<const Out*>(finalize.magnitude_table) + lane_zero;
     Out magnitudes[kR];
@@ -569,7 +594,15 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       magnitudes[j] = Out(0);
       if (!kEdge || q <= last_row)  // warp-uniform
       {
-        magnitudes[j] = __ldg(OffsetRows(table, kSmallNumbers[sizeof(Out)], squared));
+        if constexpr (kNear)
+        {
+          magnitudes[j] = *reinterpret_cast<const Out*>(
+              reinterpret_cast<const char*>(near_magnitudes) + squared * kSmallNumbers[sizeof(Out)]);
+        }
+        else
+        {
+          magnitudes[j] = __ldg(OffsetRows(table, kSmallNumbers[sizeof(Out)], squared));
+        }
       }
     }
     if constexpr (sizeof(Out) == 4)
@@ -656,16 +689,19 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
           kStage ? stage_lane[(absorb_buffer * kR + j) * kWarp] : raw[kStage ? 0 : j];
       const uint32_t high_word =
           kStage ? stage_lane[(absorb_buffer * kR + j + 1) * kWarp] : raw[kStage ? 0 : j + 1];
-      uint32_t low = min(ShiftLeftByMultiply<1>(low_word), 2u * kSaturated);
-      uint32_t high = min(ShiftLeftByMultiply<1>(high_word), 2u * kSaturated);
+      // (one wide multiply by two: the low word is twice the value, the high word the class bit)
+      const uint64_t low_wide = static_cast<uint64_t>(low_word) * kPowersOfTwo[1];
+      const uint64_t high_wide = static_cast<uint64_t>(high_word) * kPowersOfTwo[1];
+      uint32_t low = min(static_cast<uint32_t>(low_wide), 2u * kSaturated);
+      uint32_t high = min(static_cast<uint32_t>(high_wide), 2u * kSaturated);
       if constexpr (kEdge)
       {
         low = (base + j + kR > last_row) ? 2u * kSaturated : low;
         high = (base + j + kR + 1 > last_row) ? 2u * kSaturated : high;
       }
       next_pairs[j >> 1] = ShiftRightByMultiply<1>(__byte_perm(low, high, 0x5410));
-      chunk_classes = chunk_classes * kPowersOfTwo[1] + ShiftRightByMultiply<31>(low_word);
-      chunk_classes = chunk_classes * kPowersOfTwo[1] + ShiftRightByMultiply<31>(high_word);
+      chunk_classes = chunk_classes * kPowersOfTwo[1] + static_cast<uint32_t>(low_wide >> 32);
+      chunk_classes = chunk_classes * kPowersOfTwo[1] + static_cast<uint32_t>(high_wide >> 32);
     }
     if constexpr (sizeof(ClassWord) == 4)
     {
@@ -719,6 +755,23 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
         boundaries_low = static_cast<uint32_t>(boundaries);
         boundaries_reversed = __brev(static_cast<uint32_t>(boundaries >> kShift));
       }
+      // (VGT_WINDOW_SHIFT_CHAINS: the shifted boundary words of the R rows as two chains of
+      // doublings - one constant instead of 2 R different ones)
+      uint32_t after_words[kR];
+      uint32_t before_words[kR];
+      if constexpr (kWithClasses && VGT_WINDOW_SHIFT_CHAINS != 0)
+      {
+        // row j sits at bit p = 2 R - 1 - j: "after" shifts by 32 - p = 33 - 2 R + j (grows
+        // with j), "before" by p - kShift (grows towards row 0)
+        after_words[0] = boundaries_low * kPowersOfTwo[33 - 2 * kR];
+        before_words[kR - 1] = boundaries_reversed * kPowersOfTwo[kR - kShift];
+#pragma unroll
+        for (int j = 1; j < kR; j++)
+        {
+          after_words[j] = after_words[j - 1] * kPowersOfTwo[1];
+          before_words[kR - 1 - j] = before_words[kR - j] * kPowersOfTwo[1];
+        }
+      }
 #pragma unroll
       for (int j = 0; j < kR; j += 2)
       {
@@ -765,8 +818,11 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
           {
             // the row sits at bit p of the class word
             const int p = 2 * kR - 1 - jr;
-            const uint32_t after = LeadingZeros(boundaries_low * kPowersOfTwo[32 - p]);
-            const uint32_t before = LeadingZeros(boundaries_reversed * kPowersOfTwo[p - kShift]);
+            const uint32_t after = LeadingZeros(
+                VGT_WINDOW_SHIFT_CHAINS != 0 ? after_words[jr] : boundaries_low * kPowersOfTwo[32 - p]);
+            const uint32_t before = LeadingZeros(
+                VGT_WINDOW_SHIFT_CHAINS != 0 ? before_words[jr]
+                                             : boundaries_reversed * kPowersOfTwo[p - kShift]);
             // squared, in the half of its row (0xffff in the other half and for "none")
             nearest_pair[r] = __shfl_sync(0xffffffffu, r == 0 ? squares_low_half : squares_high_half,
                                           __vimin3_u32(after, before, static_cast<uint32_t>(kR)));
@@ -793,7 +849,7 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       }
     };
     bool one_class_everywhere = false;
-    if constexpr (!kEdge)
+    if constexpr (!kEdge && VGT_WINDOW_ONE_CLASS_PATH != 0)
     {
       constexpr ClassWord kSpan = (static_cast<ClassWord>(1) << (3 * kR)) - 1;
       const ClassWord span = classes & kSpan;
@@ -820,7 +876,8 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       return max(worst_pair & 0xffffu, worst_pair >> 16);
     };
     uint32_t worst = worst_of_lane();
-    if (__any_sync(0xffffffffu, worst >= kFar))
+    const bool searched = __any_sync(0xffffffffu, worst >= kFar);
+    if (searched)
     {
       // A lane with an uncertified row has no opposite-class row within R of that row, so all
       // its rows of this chunk are of one class, the class of row `base`. (Lanes whose chunk is
@@ -985,7 +1042,14 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       }
       else
       {
-        emit_finalized(base, write_base, best_pairs, edge);
+        if (!kEdge && !searched)  // warp-uniform
+        {
+          emit_finalized(base, write_base, best_pairs, edge, std::true_type{});
+        }
+        else
+        {
+          emit_finalized(base, write_base, best_pairs, edge, std::false_type{});
+        }
       }
     }
     // the next chunk becomes the current one

@@ -215,6 +215,7 @@ struct Tuning
   bool pilot = true;
   int stage = -1;      // -1: each pass its measured best
   int radius_y = 0;    // 0: the default
+  int blocks_per_sm = 192;  // window kernel: blocks per multiprocessor the segmenting aims at
 };
 
 inline const Tuning* LoadTuning()
@@ -240,6 +241,10 @@ inline const Tuning* LoadTuning()
   if (const char* radius = std::getenv("VGT_B200_WINDOW_RADIUS_Y"))
   {
     tuning->radius_y = std::atoi(radius);
+  }
+  if (const char* blocks = std::getenv("VGT_B200_WINDOW_BLOCKS_PER_SM"))
+  {
+    tuning->blocks_per_sm = std::min(std::max(std::atoi(blocks), 1), 4096);
   }
   return tuning;
 }
@@ -327,7 +332,8 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
     radius = tuning.radius_y;
   }
   const int64_t chunks = (family.length + radius - 1) / radius;
-  const int64_t wanted_blocks = MultiprocessorCount() * 192 / kWindowWarpsPerBlock;
+  const int64_t wanted_blocks =
+      static_cast<int64_t>(MultiprocessorCount()) * tuning.blocks_per_sm / kWindowWarpsPerBlock;
   int64_t segments = (wanted_blocks + blocks - 1) / blocks;
   segments = std::max<int64_t>(1, std::min<int64_t>(segments, chunks / 8));
   const int segment_rows = static_cast<int>((chunks + segments - 1) / segments) * radius;
