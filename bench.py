@@ -332,6 +332,69 @@ def strong_scaling_1024(sharded, vdev, synthetic, dev, rank, world, steps):
             / (peak * world)}
 
 
+def config5_2048(sharded, vdev, synthetic, dev, rank, world, steps):
+    """BASELINE config 5 at 8 GPUs: the 2048^3 clustered-spheres grid (8.6 Gvoxel), slab-sharded,
+    generated on the devices; device-timed like the main line, and checked against a one-GPU run
+    of the whole grid on rank 0 (exact checksums of the float bit patterns, slab by slab)."""
+    import torch
+    import torch.distributed as dist
+    dims = (2048, 2048, 2048)
+    resolution = 0.01
+
+    def checksum(sdf):
+        bits = sdf.contiguous().view(torch.int32).to(torch.int64)
+        weights = torch.arange(bits.numel(), device=bits.device, dtype=torch.int64).view_as(bits) % 1021
+        return int(bits.sum().item()), int((bits * (weights + 1)).sum().item())
+
+    plan = sharded.ShardedSignedDistanceField(dims, rank=rank, world_size=world)
+    occupancy = synthetic.clustered_spheres_occupancy_torch(dims, dev, x_range=plan.x_range)
+    sdf, min_max = plan.extract(occupancy, resolution)
+    torch.cuda.synchronize(dev)
+    mine = checksum(sdf)
+    del sdf
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    for _ in range(2):
+        plan.extract(occupancy, resolution)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        plan.extract(occupancy, resolution)
+    stop.record()
+    torch.cuda.synchronize(dev)
+    ms = start.elapsed_time(stop) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    del occupancy
+    torch.cuda.empty_cache()
+    same = None
+    if rank == 0:
+        whole = synthetic.clustered_spheres_occupancy_torch(dims, dev)
+        torch.cuda.empty_cache()
+        single, single_min_max = vdev.signed_distance_field(whole, resolution)
+        del whole
+        same = single_min_max.tolist() == min_max.tolist()
+        for peer in range(world):
+            y0, y1 = sharded.split_range(dims[1], world, peer)
+            same = same and checksum(single[:, y0:y1, :]) == tuple(gathered[peer])
+        del single
+        torch.cuda.empty_cache()
+    dist.barrier()
+    voxels = float(dims[0]) * dims[1] * dims[2]
+    peak, _ = measured_peaks()
+    nvlink_bytes = 4.0 * voxels / world * (world - 1) / world
+    return {"config": "2048^3 occupancy -> SDF<float> @0.01 m across 8 GPUs (BASELINE config 5)",
+            "n_gpus": world, "ms_per_step": ms, "value": voxels / (ms * 1e-3) / 1e9,
+            "unit": "Gvoxels/s", "equals_single_gpu": same,
+            "hbm_roofline_frac_24B": SDF_BYTES_PER_VOXEL * voxels / (ms * 1e-3) / 1e9
+            / (peak * world),
+            "nvlink_floor_ms": nvlink_bytes / 770e9 * 1e3,
+            "hbm_floor_ms": SDF_BYTES_PER_VOXEL * voxels / world / (peak * 1e9) * 1e3}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -577,6 +640,15 @@ def run_ours(args):
             strong = strong_scaling_1024(sharded, vdev, synthetic, dev, rank, n_gpus,
                                          max(3, min(args.steps, 10)))
 
+    config5 = None
+    if distributed and n_gpus == 8 and not args.skip_config5:
+        occupancy = None  # (drops the bench grid)
+        torch.cuda.empty_cache()
+        try:
+            config5 = config5_2048(sharded, vdev, synthetic, dev, rank, n_gpus, 5)
+        except Exception as error:  # the main line must survive a failure here
+            config5 = {"error": repr(error)[:300]}
+
     cpu_baseline = None
     if rank == 0 and not distributed and not args.skip_cpu:
         full = cpu_reference_arm(2, 1, dims)
@@ -605,6 +677,8 @@ def run_ours(args):
             line["parity"] = parity
         if strong is not None:
             line["strong_scaling_1024"] = strong
+        if config5 is not None:
+            line["config5_2048"] = config5
         if voxelizer is not None:
             line["voxelizer"] = voxelizer
         if other_configs is not None:
@@ -925,6 +999,8 @@ def main():
     parser.add_argument("--skip-voxelizer", action="store_true")
     parser.add_argument("--skip-parity", action="store_true",
                         help="N > 1: skip the sharded == single-GPU / oracle checks")
+    parser.add_argument("--skip-config5", action="store_true",
+                        help="N = 8 only: skip the 2048^3 grid of BASELINE config 5")
     parser.add_argument("--skip-strong", action="store_true",
                         help="skip the 1024^3 strong-scaling leg (BASELINE config 4)")
     parser.add_argument("--exchange", default="auto", choices=["auto", "peer_store", "nccl"])

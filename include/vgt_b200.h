@@ -461,6 +461,62 @@ VGT_B200_API int vgt_b200_filter_dev(
     const int32_t* d_counts, int32_t num_grids, int64_t num_voxels,
     const vgt_b200_filter_options* filter, int device, float* d_occupancy, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * On-disk formats: the reference's own grid files, so that results
+ * computed here round-trip through
+ *   SignedDistanceField<T>::SaveToFile / LoadFromFile ("SDFZ" / "SDFR";
+ *     include/voxelized_geometry_tools/signed_distance_field.hpp:622-722, members :551-596) and
+ *   OccupancyMap::SaveToFile / LoadFromFile ("CMGZ" / "CMGR";
+ *     src/voxelized_geometry_tools/occupancy_map.cpp:100-193, members :56-84, cells :23-46).
+ * Host functions (no device needed, except _save_dev). The bytes between the magic and the
+ * derived members are common_robotics_utilities' VoxelGridBase form, restated in
+ * csrc/grid_files.cu (that library is not in the reference tree: parity unpinned at that layer).
+ * Errors are VGT_B200_ERR_INVALID_ARGUMENT with the reference's messages ("File does not exist",
+ * "File is too small", "File has invalid header [....]").
+ * ---------------------------------------------------------------------------------------------- */
+enum
+{
+  VGT_B200_GRID_FILE_SDF_F32 = 0,   /* SignedDistanceField<float>:  float cells  */
+  VGT_B200_GRID_FILE_SDF_F64 = 1,   /* SignedDistanceField<double>: double cells */
+  VGT_B200_GRID_FILE_OCCUPANCY = 2  /* OccupancyMap: one float per cell          */
+};
+
+typedef struct vgt_b200_grid_file_info
+{
+  int64_t nx, ny, nz;
+  double voxel_size[3];               /* must be uniform (sdf.hpp:612-620) */
+  double origin_transform[16];         /* 4x4 column-major, rigid */
+  double inverse_origin_transform[16]; /* filled by probe / load; save computes it */
+  double default_value;
+  double oob_value;
+  int32_t initialized;
+  int32_t locked;                      /* SDF only (sdf.hpp:558-559, 579-592) */
+  int64_t frame_length;                /* filled by probe / load */
+  int64_t payload_bytes;               /* filled by probe / load: size of the serialized grid */
+} vgt_b200_grid_file_info;
+
+/* SaveToFile (sdf.hpp:643-668, occupancy_map.cpp:116-141): cells = host T[nx*ny*nz], x slowest. */
+VGT_B200_API int vgt_b200_grid_file_save(
+    const char* path, int kind, int compress, const void* cells,
+    const vgt_b200_grid_file_info* info, const char* frame);
+
+/* SaveToFile (signed_distance_field.hpp:643-668) for a grid that lives on `device` (copied out
+ * on `stream`, which is synchronised). */
+VGT_B200_API int vgt_b200_grid_file_save_dev(
+    const char* path, int kind, int compress, const void* d_cells,
+    const vgt_b200_grid_file_info* info, const char* frame, int device, void* stream);
+
+/* LoadFromFile in two steps (sdf.hpp:670-722, occupancy_map.cpp:143-193): probe fills `info`
+ * and the frame name (truncated to frame_capacity - 1 characters), load also copies the cells
+ * into the caller's buffer of cell_capacity cells. */
+VGT_B200_API int vgt_b200_grid_file_probe(
+    const char* path, int kind, vgt_b200_grid_file_info* info, char* frame,
+    int64_t frame_capacity);
+/* LoadFromFile (signed_distance_field.hpp:670-722, occupancy_map.cpp:143-193), second step. */
+VGT_B200_API int vgt_b200_grid_file_load(
+    const char* path, int kind, void* cells, int64_t cell_capacity,
+    vgt_b200_grid_file_info* info, char* frame, int64_t frame_capacity);
+
 #ifdef __cplusplus
 }
 #endif

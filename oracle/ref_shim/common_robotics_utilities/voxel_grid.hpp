@@ -120,16 +120,17 @@ class VoxelGridBase
 public:
   VoxelGridBase() = default;
   // (the out-of-bounds value of the real class is only ever handed back by accessors the
-  // reference's SDF code does not use; kept so the constructors match)
+  // reference's SDF code does not use; kept for the constructors and the serialized form)
   VoxelGridBase(const Eigen::Isometry3d& origin_transform, const VoxelGridSizes& sizes,
-                const T& default_value, const T&)
-      : VoxelGridBase(origin_transform, sizes, default_value) {}
-  VoxelGridBase(const VoxelGridSizes& sizes, const T& default_value, const T&)
-      : VoxelGridBase(Eigen::Isometry3d::Identity(), sizes, default_value) {}
+                const T& default_value, const T& oob_value)
+      : origin_transform_(origin_transform), sizes_(sizes),
+        data_(static_cast<size_t>(sizes.TotalVoxels()), default_value), initialized_(true),
+        default_value_(default_value), oob_value_(oob_value) {}
+  VoxelGridBase(const VoxelGridSizes& sizes, const T& default_value, const T& oob_value)
+      : VoxelGridBase(Eigen::Isometry3d::Identity(), sizes, default_value, oob_value) {}
   VoxelGridBase(const Eigen::Isometry3d& origin_transform, const VoxelGridSizes& sizes,
                 const T& default_value)
-      : origin_transform_(origin_transform), sizes_(sizes),
-        data_(static_cast<size_t>(sizes.TotalVoxels()), default_value), initialized_(true) {}
+      : VoxelGridBase(origin_transform, sizes, default_value, default_value) {}
   virtual ~VoxelGridBase() {}
 
   // (signed_distance_field.hpp derives from the grid and implements these)
@@ -175,14 +176,80 @@ public:
   {
     return GridIndexToLocation(GridIndex(x, y, z));
   }
-  uint64_t SerializeSelf(std::vector<uint8_t>&, const ScalarTypeSerializer&) const
+  // The grid's serialized form. PARITY UNPINNED (the real class is not in the reference tree,
+  // see serialization.hpp): initialized flag, origin transform, inverse origin transform, the
+  // cells as a vector, the sizes (three voxel sizes, three voxel counts), the default and the
+  // out-of-bounds value; then whatever the derived class appends.
+  uint64_t SerializeSelf(std::vector<uint8_t>& buffer,
+                         const ScalarTypeSerializer& value_serializer) const
   {
-    throw std::runtime_error("serialization is not part of the oracle");
+    const size_t start = buffer.size();
+    serialization::SerializeMemcpyable<uint8_t>(static_cast<uint8_t>(initialized_), buffer);
+    serialization::SerializeIsometry3d(origin_transform_, buffer);
+    serialization::SerializeIsometry3d(origin_transform_.inverse(), buffer);
+    serialization::SerializeVectorLike<T, BackingStore>(data_, buffer, value_serializer);
+    serialization::SerializeMemcpyable<double>(sizes_.VoxelXSize(), buffer);
+    serialization::SerializeMemcpyable<double>(sizes_.VoxelXSize(), buffer);
+    serialization::SerializeMemcpyable<double>(sizes_.VoxelXSize(), buffer);
+    serialization::SerializeMemcpyable<int64_t>(sizes_.NumXVoxels(), buffer);
+    serialization::SerializeMemcpyable<int64_t>(sizes_.NumYVoxels(), buffer);
+    serialization::SerializeMemcpyable<int64_t>(sizes_.NumZVoxels(), buffer);
+    value_serializer(default_value_, buffer);
+    value_serializer(oob_value_, buffer);
+    DerivedSerializeSelf(buffer, value_serializer);
+    return buffer.size() - start;
   }
-  uint64_t DeserializeSelf(const std::vector<uint8_t>&, uint64_t, const ScalarTypeDeserializer&)
+  uint64_t DeserializeSelf(const std::vector<uint8_t>& buffer, uint64_t starting_offset,
+                           const ScalarTypeDeserializer& value_deserializer)
   {
-    throw std::runtime_error("serialization is not part of the oracle");
+    uint64_t position = starting_offset;
+    const auto initialized = serialization::DeserializeMemcpyable<uint8_t>(buffer, position);
+    position += initialized.BytesRead();
+    const auto origin = serialization::DeserializeIsometry3d(buffer, position);
+    position += origin.BytesRead();
+    const auto inverse = serialization::DeserializeIsometry3d(buffer, position);
+    position += inverse.BytesRead();
+    const auto data =
+        serialization::DeserializeVectorLike<T, BackingStore>(buffer, position, value_deserializer);
+    position += data.BytesRead();
+    double voxel_sizes[3];
+    int64_t counts[3];
+    for (double& size : voxel_sizes)
+    {
+      const auto item = serialization::DeserializeMemcpyable<double>(buffer, position);
+      size = item.Value();
+      position += item.BytesRead();
+    }
+    for (int64_t& count : counts)
+    {
+      const auto item = serialization::DeserializeMemcpyable<int64_t>(buffer, position);
+      count = item.Value();
+      position += item.BytesRead();
+    }
+    const auto default_value = value_deserializer(buffer, position);
+    position += default_value.BytesRead();
+    const auto oob_value = value_deserializer(buffer, position);
+    position += oob_value.BytesRead();
+    if (voxel_sizes[0] != voxel_sizes[1] || voxel_sizes[0] != voxel_sizes[2])
+    {
+      throw std::invalid_argument("the stand-in grid keeps one voxel size");
+    }
+    initialized_ = initialized.Value() != 0;
+    origin_transform_ = origin.Value();
+    sizes_ = VoxelGridSizes::FromVoxelCounts(voxel_sizes[0],
+                                             Vector3i64(counts[0], counts[1], counts[2]));
+    data_ = data.Value();
+    if (static_cast<int64_t>(data_.size()) != sizes_.TotalVoxels())
+    {
+      throw std::invalid_argument("serialized grid holds the wrong number of cells");
+    }
+    default_value_ = default_value.Value();
+    oob_value_ = oob_value.Value();
+    position += DerivedDeserializeSelf(buffer, position, value_deserializer);
+    return position - starting_offset;
   }
+  const T& DefaultValue() const { return default_value_; }
+  const T& OobValue() const { return oob_value_; }
 
   bool IsInitialized() const { return initialized_; }
   bool HasUniformVoxelSize() const { return sizes_.UniformVoxelSize(); }
@@ -276,6 +343,8 @@ private:
   VoxelGridSizes sizes_;
   BackingStore data_;
   bool initialized_ = false;
+  T default_value_{};
+  T oob_value_{};
 };
 
 template <typename T>

@@ -54,6 +54,19 @@ class FilterOptions(ctypes.Structure):
                 ("num_cameras_seen_free", ctypes.c_int32)]
 
 
+class GridFileInfo(ctypes.Structure):
+    """struct vgt_b200_grid_file_info."""
+    _fields_ = [("nx", _i64), ("ny", _i64), ("nz", _i64), ("voxel_size", _dbl * 3),
+                ("origin_transform", _dbl * 16), ("inverse_origin_transform", _dbl * 16),
+                ("default_value", _dbl), ("oob_value", _dbl), ("initialized", ctypes.c_int32),
+                ("locked", ctypes.c_int32), ("frame_length", _i64), ("payload_bytes", _i64)]
+
+
+GRID_FILE_SDF_F32 = 0
+GRID_FILE_SDF_F64 = 1
+GRID_FILE_OCCUPANCY = 2
+
+
 # name -> (restype, argtypes); must list every symbol include/vgt_b200.h declares
 # (tests/test_capi_symbols.py cross-checks this table against the header).
 SIGNATURES = {
@@ -122,6 +135,15 @@ SIGNATURES = {
     "vgt_b200_rasterize_mesh_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _int, _i64, _i64, _i64, _dbl,
                                            _f64p, _f64p, _int, _int, _vp, _vp]),
     "vgt_b200_rasterize_status": (_int, [_int]),
+    "vgt_b200_grid_file_save": (_int, [ctypes.c_char_p, _int, _int, _vp,
+                                       ctypes.POINTER(GridFileInfo), ctypes.c_char_p]),
+    "vgt_b200_grid_file_save_dev": (_int, [ctypes.c_char_p, _int, _int, _vp,
+                                           ctypes.POINTER(GridFileInfo), ctypes.c_char_p, _int,
+                                           _vp]),
+    "vgt_b200_grid_file_probe": (_int, [ctypes.c_char_p, _int, ctypes.POINTER(GridFileInfo),
+                                        ctypes.c_char_p, _i64]),
+    "vgt_b200_grid_file_load": (_int, [ctypes.c_char_p, _int, _vp, _i64,
+                                       ctypes.POINTER(GridFileInfo), ctypes.c_char_p, _i64]),
 }
 
 _library = None

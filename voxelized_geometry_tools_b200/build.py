@@ -35,6 +35,8 @@ TRANSLATION_UNITS = [
     ("sdf_queries.cu", ["-fmad=false"]),
     # the mesh rasterizer's "cell touched" test is a double comparison mirrored as written
     ("mesh_rasterizer.cu", ["-fmad=false"]),
+    # the reference's file formats (host code; zlib for the compressed forms)
+    ("grid_files.cu", []),
 ]
 
 
@@ -81,7 +83,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {source}")
         objects.append(str(obj))
     link = ([nvcc] + _host_compiler_flags() + ARCH_FLAGS + ["-shared", "-o", str(LIBRARY)]
-            + objects)
+            + objects + ["-lz"])
     result = subprocess.run(link, capture_output=True, text=True)
     if result.returncode != 0:
         sys.stderr.write(" ".join(link) + "\n" + result.stdout + result.stderr)

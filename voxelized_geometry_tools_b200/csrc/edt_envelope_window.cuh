@@ -48,10 +48,22 @@ namespace
 constexpr int kWindowWarpsPerBlock = 1;
 // Window radius and resident warps per SM (72 / 64 registers) for the packed (y) pass and the
 // finalizing (x) pass: the in-plane distances the y pass sees are larger than the final ones.
-constexpr int kWindowRadiusPacked = 12;
-constexpr int kWindowBlocksPacked = 28;
-constexpr int kWindowRadiusFinal = 8;
-constexpr int kWindowBlocksFinal = 32;
+#ifndef VGT_WINDOW_RADIUS_PACKED
+#define VGT_WINDOW_RADIUS_PACKED 12
+#endif
+#ifndef VGT_WINDOW_RADIUS_FINAL
+#define VGT_WINDOW_RADIUS_FINAL 8
+#endif
+constexpr int kWindowRadiusPacked = VGT_WINDOW_RADIUS_PACKED;
+#ifndef VGT_WINDOW_BLOCKS_PACKED
+#define VGT_WINDOW_BLOCKS_PACKED 28
+#endif
+constexpr int kWindowBlocksPacked = VGT_WINDOW_BLOCKS_PACKED;
+constexpr int kWindowRadiusFinal = VGT_WINDOW_RADIUS_FINAL;
+#ifndef VGT_WINDOW_BLOCKS_FINAL
+#define VGT_WINDOW_BLOCKS_FINAL 32
+#endif
+constexpr int kWindowBlocksFinal = VGT_WINDOW_BLOCKS_FINAL;
 // Hand-over buffer between the window kernel and the stack kernel ("redo list"), T = number of
 // tiles: word 0 = number of listed tiles, word 1 = mode (0: the stack kernel redoes the listed
 // tiles; 1: the pilot found the map deep, the stack kernel does every tile), word 2 = extended-
@@ -212,7 +224,10 @@ __device__ __forceinline__ uint32_t LeadingZeros(uint32_t word)
 
 // Accumulators per row of the window minimum (the R rows of a chunk are independent chains
 // already; more than one accumulator per row costs a merge per row).
-constexpr int kWindowChains = 1;
+#ifndef VGT_WINDOW_CHAINS
+#define VGT_WINDOW_CHAINS 1
+#endif
+constexpr int kWindowChains = VGT_WINDOW_CHAINS;
 
 // Calls f(std::integral_constant<int, 0>{}) ... f(std::integral_constant<int, kCount - 1>{}).
 template <int kCount, int kIndex = 0, typename F>

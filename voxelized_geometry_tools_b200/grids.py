@@ -192,6 +192,9 @@ class OccupancyMap:
         self._origin_transform = np.array(origin_transform, dtype=np.float64).reshape(4, 4)
         self._frame = frame
         self._sizes = sizes
+        # (the reference hands one cell to the grid as default and out-of-bounds value)
+        self._default_occupancy = float(default_occupancy)
+        self._oob_occupancy = float(default_occupancy)
         if data is None:
             self._data = np.full(sizes.shape, default_occupancy, dtype=np.float32)
         else:
