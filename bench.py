@@ -1003,7 +1003,7 @@ def main():
                         help="N = 8 only: skip the 2048^3 grid of BASELINE config 5")
     parser.add_argument("--skip-strong", action="store_true",
                         help="skip the 1024^3 strong-scaling leg (BASELINE config 4)")
-    parser.add_argument("--exchange", default="auto", choices=["auto", "peer_store", "nccl"])
+    parser.add_argument("--exchange", default="auto", choices=["auto", "peer_store", "peer_copy", "nccl"])
     parser.add_argument("--chunks", type=int, default=2,
                         help="x-chunks per slab for overlapping the all-to-all (N > 1)")
     args = parser.parse_args()

@@ -58,7 +58,9 @@ def main():
     for dims, border, chunks, exchange in (
             ((96, 80, 72), False, 1, "nccl"), ((61, 45, 130), True, 3, "nccl"),
             ((256, 256, 256), False, 4, "nccl"), ((96, 80, 72), False, 1, "peer_store"),
-            ((61, 45, 130), True, 1, "peer_store"), ((256, 256, 256), False, 1, "peer_store")):
+            ((61, 45, 130), True, 1, "peer_store"), ((256, 256, 256), False, 1, "peer_store"),
+            ((96, 80, 72), False, 2, "peer_copy"), ((61, 45, 130), True, 3, "peer_copy"),
+            ((256, 256, 256), False, 4, "peer_copy")):
         plan = ShardedSignedDistanceField(dims, chunks=chunks, exchange=exchange)
         slab = synthetic.clustered_spheres_occupancy_torch(dims, dev, x_range=plan.x_range)
         for _ in range(3):      # several steps: exercises the double-buffered receive side

@@ -13,10 +13,19 @@
 // Here one lane owns one line (a warp = 32 adjacent lines, every row access is one 128-byte
 // segment, as in the stack kernels) and keeps the 3 R rows around the current chunk of R rows in
 // registers, two rows per register as 16-bit halves, so T costs one VIADDMNMX.U16x2 per two
-// candidate rows (R + 1 per voxel, the squared offsets are immediates) and e comes from a
-// class-bit window with one BREV and one FLO. The rows ahead arrive by plain loads one chunk
-// ahead (y pass) or through shared memory with cp.async two chunks ahead (x pass). No scratch,
-// the input is read once and not modified: 4 B in + 4 B out per voxel.
+// candidate rows (R + 1 per voxel, the squared offsets are immediates). e comes from the
+// boundary bits of a class-bit window: per row and side one shift and one count of leading
+// zeros, then one three-way minimum and a look-up of the square across the warp (SHFL). The rows
+// ahead arrive by plain loads one chunk ahead. No scratch, the input is read once and not
+// modified: 4 B in + 4 B out per voxel.
+//
+// The kernel is bound by the integer alu pipe and by issue slots, not by HBM, so everything
+// around the add-mins is written for the OTHER pipes: row addresses, shifts by constants, bit
+// extraction and the doubling that drops the class bit are integer multiplies (fma pipe) whose
+// power-of-two factors come from constant memory - ptxas would turn a literal back into an alu
+// shift or LEA -, the bit scans run on the xu pipe, the table of squares is a warp shuffle, and
+// the finalizing pass reads magnitudes of certified chunks from a copy of the head of the table
+// in shared memory (one 32-bit address instead of a 64-bit one).
 //
 // Rows that do not certify (distance to the opposite class > R voxels) continue the same search
 // outwards, four row pairs per vote, until d^2 reaches the best value so far - exact for any
@@ -509,65 +518,101 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   char* send_origin = nullptr;
   int next_part_start = first_row;
 
-  // one row of the output; write_base = address of the chunk's first output row
-  const auto emit_row = [&](const int q, const int j, char* const write_base, const uint32_t word)
+  // Send layout (see LineFamily): row q of a line is at send_origin + q * out_stride_bytes; the
+  // origin jumps at part boundaries, which are the same for every lane. locate_part(q) finds
+  // the part that holds row q: its origin and the first row of the next part.
+  const auto locate_part = [&](const int q)
   {
-    char* write_at = OffsetRows(write_base, out_stride_bytes, kSmallNumbers[j]);
-    if constexpr (kSend)
+    // Part h covers rows [y0, y0 + rows); its block starts at inner * num_outer * y0.
+    const int wide = family.out_base + 1;
+    const int wide_rows = family.out_extra * wide;
+    int y0;
+    int rows;
+    if (q < wide_rows)
     {
-      // Send layout (see LineFamily): row q is at send_origin + q * out_stride_bytes; the origin
-      // jumps at part boundaries, which are the same for every lane (warp-uniform branch).
-      if (q == next_part_start)
-      {
-        // Part h covers rows [y0, y0 + rows); its block starts at inner * num_outer * y0.
-        const int wide = family.out_base + 1;
-        const int wide_rows = family.out_extra * wide;
-        int y0;
-        int rows;
-        if (q < wide_rows)
-        {
-          y0 = (q / wide) * wide;
-          rows = wide;
-        }
-        else
-        {
-          y0 = wide_rows + ((q - wide_rows) / family.out_base) * family.out_base;
-          rows = family.out_base;
-        }
-        next_part_start = y0 + rows;
-        Out* part_row;
-        if (family.scatter_base[0] != nullptr)
-        {
-          // this part goes straight to its owner's receive buffer over NVLink
-          const int part = (q < wide_rows)
-              ? (q / wide)
-              : (family.out_extra + (q - wide_rows) / family.out_base);
-          // (selected with compares: indexing the kernel-parameter array with a register
-          // would force a local-memory copy of the whole parameter struct)
-          uint32_t* target = family.scatter_base[0];
-#pragma unroll
-          for (int i = 1; i < 8; i++)
-          {
-            target = (part == i) ? family.scatter_base[i] : target;
-          }
-          part_row = reinterpret_cast<Out*>(target)
-              + family.inner_count * ((family.scatter_row_offset + outer) * rows + (q - y0))
-              + column;
-        }
-        else
-        {
-          part_row = out + family.inner_count * (family.num_outer * y0 + outer * rows + (q - y0))
-              + column;
-        }
-        send_origin = reinterpret_cast<char*>(part_row)
-            - static_cast<uint64_t>(static_cast<uint32_t>(q)) * out_stride_bytes;
-      }
-      write_at = send_origin + static_cast<uint64_t>(static_cast<uint32_t>(q)) * out_stride_bytes;
+      y0 = (q / wide) * wide;
+      rows = wide;
     }
-    // (the finalizing pass emits whole chunks: emit_finalized)
-    if constexpr (kMode == kEmitPacked)
+    else
     {
-      __stcs(reinterpret_cast<uint32_t*>(write_at), word);
+      y0 = wide_rows + ((q - wide_rows) / family.out_base) * family.out_base;
+      rows = family.out_base;
+    }
+    next_part_start = y0 + rows;
+    Out* part_row;
+    if (family.scatter_base[0] != nullptr)
+    {
+      // this part goes straight to its owner's receive buffer over NVLink
+      const int part = (q < wide_rows)
+          ? (q / wide)
+          : (family.out_extra + (q - wide_rows) / family.out_base);
+      // (selected with compares: indexing the kernel-parameter array with a register
+      // would force a local-memory copy of the whole parameter struct)
+      uint32_t* target = family.scatter_base[0];
+#pragma unroll
+      for (int i = 1; i < 8; i++)
+      {
+        target = (part == i) ? family.scatter_base[i] : target;
+      }
+      part_row = reinterpret_cast<Out*>(target)
+          + family.inner_count * ((family.scatter_row_offset + outer) * rows + (q - y0))
+          + column;
+    }
+    else
+    {
+      part_row = out + family.inner_count * (family.num_outer * y0 + outer * rows + (q - y0))
+          + column;
+    }
+    send_origin = reinterpret_cast<char*>(part_row)
+        - static_cast<uint64_t>(static_cast<uint32_t>(q)) * out_stride_bytes;
+  };
+
+  // The packed words of a chunk (words[j] = row base + j; `rows` of them are inside the line).
+  // Plain layout: row j at write_base + j * stride. Send layout: the rows are emitted group by
+  // group, a group = the rows of the chunk that lie in one part (nearly always the whole
+  // chunk), with ONE part look-up per group: the look-up (two divisions) exists once in the
+  // code, not once per unrolled row.
+  const auto emit_packed = [&](const int base, char* const write_base, const uint32_t* words,
+                               const int rows)
+  {
+    const auto store = [&](char* const at, const uint32_t word)
+    {
+      // (peer stores: .cs / .cg / .wt / default measured the same, profiles/r2_experiments.md)
+      __stcs(reinterpret_cast<uint32_t*>(at), word);
+    };
+    if constexpr (!kSend)
+    {
+#pragma unroll
+      for (int j = 0; j < kR; j++)
+      {
+        if (j < rows)  // warp-uniform (always true in interior chunks)
+        {
+          store(OffsetRows(write_base, out_stride_bytes, kSmallNumbers[j]), words[j]);
+        }
+      }
+    }
+    else
+    {
+      int row = 0;
+#pragma unroll 1
+      while (row < rows)
+      {
+        if (base + row >= next_part_start)  // warp-uniform
+        {
+          locate_part(base + row);
+        }
+        const int group_end = min(rows, next_part_start - base);
+        char* const group_base = OffsetRows(send_origin, out_stride_bytes, static_cast<uint32_t>(base));
+#pragma unroll
+        for (int j = 0; j < kR; j++)
+        {
+          if (j >= row && j < group_end)  // warp-uniform
+          {
+            store(OffsetRows(group_base, out_stride_bytes, kSmallNumbers[j]), words[j]);
+          }
+        }
+        row = group_end;
+      }
     }
   };
 
@@ -1038,22 +1083,19 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
       {
         // the class bits of this chunk's rows: row j at bit R - 1 - j
         const uint32_t chunk_only = static_cast<uint32_t>(classes >> kR) & kSideMask;
+        uint32_t words[kR];
 #pragma unroll
         for (int j = 0; j < kR; j++)
         {
-          const int q = base + j;
-          if (!kEdge || q <= last_row)  // warp-uniform
-          {
-            // the class of row j moved to bit 31 with zeros in the low half (a multiply); the
-            // squared distance of an odd row comes down by a multiply too, and ONE logic
-            // operation assembles the word (values stay below 0x8000: bit 15 is clear)
-            const uint32_t filled = chunk_only * kPowersOfTwo[32 - kR + j];
-            const uint32_t pair = best_pairs[j >> 1];
-            const uint32_t word = (j & 1) ? ((filled & 0x80000000u) | ShiftRightByMultiply<16>(pair))
-                                          : ((filled | pair) & 0x8000ffffu);
-            emit_row(q, j, write_base, word);
-          }
+          // the class of row j moved to bit 31 with zeros in the low half (a multiply); the
+          // squared distance of an odd row comes down by a multiply too, and ONE logic
+          // operation assembles the word (values stay below 0x8000: bit 15 is clear)
+          const uint32_t filled = chunk_only * kPowersOfTwo[32 - kR + j];
+          const uint32_t pair = best_pairs[j >> 1];
+          words[j] = (j & 1) ? ((filled & 0x80000000u) | ShiftRightByMultiply<16>(pair))
+                             : ((filled | pair) & 0x8000ffffu);
         }
+        emit_packed(base, write_base, words, kEdge ? min(kR, last_row + 1 - base) : kR);
       }
       else
       {

@@ -74,8 +74,10 @@ class ShardedSignedDistanceField:
         overlap the all-to-all of chunk c (NCCL runs on its own stream). profile=True records CUDA
         events around the stages (``last_stage_ms`` after a synchronise)."""
         # exchange: "peer_store" = the y pass stores straight into the peers' receive buffers over
-        # NVLink (symmetric memory, no collective call); "nccl" = all-to-all; "auto" = peer_store
-        # when the stages and the device support it, else nccl.
+        # NVLink (symmetric memory, no collective call); "peer_copy" = the y pass of x-chunk c
+        # writes the send layout locally and the copy engines move its parts into the peers'
+        # receive buffers while the passes of chunk c + 1 run (`chunks` chunks); "nccl" =
+        # all-to-all; "auto" = peer_store when the stages and the device support it, else nccl.
         self.dims = tuple(int(d) for d in dims)
         self.group = group
         self.exchange = exchange
@@ -140,11 +142,14 @@ class ShardedSignedDistanceField:
         if tuple(occupancy_slab.shape) != self.x_slab_shape():
             raise ValueError(f"expected an x-slab of shape {self.x_slab_shape()}")
         self._mark("start", occupancy_slab)
-        if (self.world_size > 1 and self.exchange in ("auto", "peer_store")
+        if (self.world_size > 1 and self.exchange in ("auto", "peer_store", "peer_copy")
                 and self.stages.local_passes_scatter is not None and occupancy_slab.is_cuda
                 and self._peer is None):
             self._setup_peer_store(occupancy_slab.device)
-        if self.world_size > 1 and self._peer:
+        if self.world_size > 1 and self._peer and self.exchange == "peer_copy":
+            y_slab = self._peer_copy_local_and_exchange(occupancy_slab, unknown_is_filled)
+            self.exchange_used = "peer_copy"
+        elif self.world_size > 1 and self._peer:
             y_slab = self._peer_store_local_and_exchange(occupancy_slab, unknown_is_filled)
             self.exchange_used = "peer_store"
         elif self.world_size == 1:
@@ -193,7 +198,7 @@ class ShardedSignedDistanceField:
                 buffers.append(buffer)
             self._peer = {"buffers": buffers, "handles": handles}
         except Exception as error:  # no symmetric memory on this system: use NCCL
-            if self.exchange == "peer_store":
+            if self.exchange in ("peer_store", "peer_copy"):
                 raise
             self._peer = False
             self._peer_error = repr(error)
@@ -209,6 +214,64 @@ class ShardedSignedDistanceField:
         self.stages.local_passes_scatter(occupancy_slab, self.rank, self.x_range[0], nx,
                                          [int(p) for p in handle.buffer_ptrs], buffer.numel(),
                                          unknown_is_filled)
+        self._mark("local", occupancy_slab)
+        handle.barrier(channel=0)
+        return buffer[:nx * nyl * nz].view(nx, nyl, nz)
+
+    # ------------------------------------------------------------------ peer copies (DMA)
+    def _peer_copy_local_and_exchange(self, occupancy_slab, unknown_is_filled):
+        """x-chunks of the slab: the z / y passes of chunk c write the send layout into local
+        memory; its world parts then travel to their owners' receive buffers (symmetric memory,
+        mapped into this process) as plain device-to-device copies on side streams - the copy
+        engines, not the SMs, drive NVLink - while the passes of chunk c + 1 run. The block a
+        chunk contributes to a peer's y-slab is rows x in [x0 + c0, x0 + c1): contiguous there.
+        One symmetric-memory barrier, ordered after this rank's copies, separates the exchange
+        from the x pass; receive buffers are double-buffered across steps."""
+        nx, ny, nz = self.dims
+        world = self.world_size
+        nyl = self.y_range[1] - self.y_range[0]
+        nxl = self.x_range[1] - self.x_range[0]
+        x0 = self.x_range[0]
+        index = self._step % 2
+        self._step += 1
+        buffer, handle = self._peer["buffers"][index], self._peer["handles"][index]
+        device = occupancy_slab.device
+        if "copy_streams" not in self._peer:
+            self._peer["copy_streams"] = [torch.cuda.Stream(device=device) for _ in range(2)]
+        copy_streams = self._peer["copy_streams"]
+        compute = torch.cuda.current_stream(device)
+        chunks = max(1, min(self.chunks, nxl))
+        keep = []
+        for c in range(chunks):
+            c0, c1 = split_range(nxl, chunks, c)
+            if c1 <= c0:
+                continue
+            send = self.stages.local_passes_send(occupancy_slab[c0:c1], unknown_is_filled, world)
+            keep.append(send)
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            offsets, offset = [], 0
+            for peer in range(world):
+                y0, y1 = split_range(ny, world, peer)
+                offsets.append((offset, (c1 - c0) * (y1 - y0) * nz))
+                offset += offsets[-1][1]
+            # peers in an order rotated by the rank: at any moment every rank copies to a
+            # different peer
+            for k in range(world):
+                peer = (self.rank + 1 + k) % world
+                start, count = offsets[peer]
+                if count == 0:
+                    continue
+                py0, py1 = split_range(ny, world, peer)
+                target = handle.get_buffer(peer, (count,), torch.int32,
+                                           (x0 + c0) * (py1 - py0) * nz)
+                stream = copy_streams[k % len(copy_streams)]
+                stream.wait_event(ready)
+                with torch.cuda.stream(stream):
+                    target.copy_(send[start:start + count], non_blocking=True)
+        for stream in copy_streams:
+            compute.wait_stream(stream)
+        self._peer["keep"] = keep  # (alive until the next step: the copies read them)
         self._mark("local", occupancy_slab)
         handle.barrier(channel=0)
         return buffer[:nx * nyl * nz].view(nx, nyl, nz)
