@@ -208,8 +208,11 @@ VGT_B200_API int vgt_b200_sdf_f32_dev(
     void* stream);
 
 /* Measurement aid for bench.py / profiles: the same three kernels as vgt_b200_sdf_f32_dev with
- * CUDA events between them on `stream`. Synchronises the stream. out_pass_ms[3] receives the
- * duration of the z scan, the y envelope pass and the x envelope pass + finalize. */
+ * CUDA events between them on `stream`. Synchronises the stream. out_pass_ms[5] receives the
+ * duration of the z scan, the y envelope pass and the x envelope pass + finalize (each pass =
+ * pilot probe + decision + window kernel + stack kernel over the hand-over list), then the
+ * duration of the y pass's and of the x pass's main window-kernel launch alone (0 when that
+ * kernel did not run). */
 VGT_B200_API int vgt_b200_sdf_f32_dev_profile(
     const float* d_occupancy, int64_t nx, int64_t ny, int64_t nz, double resolution,
     int unknown_is_filled, int add_virtual_border, int device, float* d_sdf_out, float* d_min_max,

@@ -272,6 +272,18 @@ inline const Tuning& CurrentTuning()
 // VGT_B200_MAX_AXIS stays below it: 2 * 8191^2 < 2^28.
 constexpr int64_t kLeanMaxInput = (int64_t{1} << 29) - 1;
 
+// Measurement aid (vgt_b200_sdf_f32_dev_profile): events right around the main window-kernel
+// launch of each strided pass, so that the kernel's own duration can be told apart from the
+// pass (pilot + decision + window kernel + stack kernel over the redo list). Thread-local: only
+// the calling thread's launches are marked.
+struct WindowKernelMarks
+{
+  cudaEvent_t begin[2];
+  cudaEvent_t end[2];
+  int launches = 0;
+};
+thread_local WindowKernelMarks* g_window_marks = nullptr;
+
 // The window kernel over every tile of the family; tiles it gives up on are appended to
 // d_redo_list (layout in edt_envelope_window.cuh; header and flags zeroed here). With enough tiles
 // a pilot launch goes first: it probes two chunks of rows out of every 256 of every 8th tile
@@ -357,11 +369,15 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
   const auto launch_with_pilot = [&](auto kernel, auto pilot_kernel)
   {
     const dim3 threads(kWindowWarpsPerBlock * kWarp);
+    WindowKernelMarks* const marks =
+        (g_window_marks != nullptr && g_window_marks->launches < 2) ? g_window_marks : nullptr;
     if (!pilot)
     {
+      if (marks != nullptr) { cudaEventRecord(marks->begin[marks->launches], stream); }
       kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)), threads, 0,
                stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list, step_rate,
                          segment_rows, segment_rows, kSelectAll); NoteKernelLaunch();
+      if (marks != nullptr) { cudaEventRecord(marks->end[marks->launches++], stream); }
       return;
     }
     const int64_t pilot_blocks = (blocks + kPilotStride - 1) / kPilotStride;
@@ -374,9 +390,11 @@ int LaunchEnvelopeWindow(const uint32_t* d_in, typename OutputOf<kMode>::Type* d
                                    std::min(step_rate, kPilotStepRate), 2 * radius, kPilotSpacing,
                                    kSelectPilot); NoteKernelLaunch();
     DecideWindowModeKernel<<<1, 1, 0, stream>>>(d_redo_list, static_cast<uint32_t>(pilot_probes)); NoteKernelLaunch();
+    if (marks != nullptr) { cudaEventRecord(marks->begin[marks->launches], stream); }
     kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(segments)), threads, 0,
              stream>>>(d_in, d_out, derived, finalize, d_keys, d_redo_list, step_rate,
                        segment_rows, segment_rows, kSelectAfterPilot); NoteKernelLaunch();
+    if (marks != nullptr) { cudaEventRecord(marks->end[marks->launches++], stream); }
   };
   const auto launch = [&](auto kernel) { launch_with_pilot(kernel, kernel); };
   if constexpr (kMode == kEmitPacked)
@@ -1770,20 +1788,42 @@ int vgt_b200_sdf_f32_dev_profile(
   {
     VGT_CUDA_TRY(cudaEventCreate(&mark), "cudaEventCreate");
   }
+  WindowKernelMarks window_marks;
+  for (int i = 0; i < 2; i++)
+  {
+    VGT_CUDA_TRY(cudaEventCreate(&window_marks.begin[i]), "cudaEventCreate");
+    VGT_CUDA_TRY(cudaEventCreate(&window_marks.end[i]), "cudaEventCreate");
+  }
+  g_window_marks = &window_marks;
   const int status =
       SdfOnDevice<float, kEmitFloat>(d_occupancy, nx, ny, nz, resolution, unknown_is_filled,
                                      add_virtual_border, d_sdf_out, d_min_max, s, marks);
+  g_window_marks = nullptr;
   const cudaError_t sync = cudaStreamSynchronize(s);
+  out_pass_ms[3] = 0.0f;
+  out_pass_ms[4] = 0.0f;
   if (status == VGT_B200_OK && sync == cudaSuccess)
   {
     for (int i = 0; i < 3; i++)
     {
       cudaEventElapsedTime(out_pass_ms + i, marks[i], marks[i + 1]);
     }
+    // (a grid with a one-voxel axis skips that pass: the launches are then fewer than two, and
+    // the first one belongs to whichever strided pass ran)
+    for (int i = 0; i < window_marks.launches; i++)
+    {
+      const int slot = (window_marks.launches == 2) ? 3 + i : (ny > 1 ? 3 : 4);
+      cudaEventElapsedTime(out_pass_ms + slot, window_marks.begin[i], window_marks.end[i]);
+    }
   }
   for (auto& mark : marks)
   {
     cudaEventDestroy(mark);
+  }
+  for (int i = 0; i < 2; i++)
+  {
+    cudaEventDestroy(window_marks.begin[i]);
+    cudaEventDestroy(window_marks.end[i]);
   }
   if (status != VGT_B200_OK)
   {

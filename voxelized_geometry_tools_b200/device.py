@@ -51,20 +51,23 @@ def signed_distance_field(occupancy: torch.Tensor, resolution: float,
 
 
 def signed_distance_field_profile(occupancy: torch.Tensor, resolution: float,
-                                  out: torch.Tensor, min_max: torch.Tensor | None = None):
+                                  out: torch.Tensor, min_max: torch.Tensor | None = None,
+                                  kernels: bool = False):
     """Same kernels as signed_distance_field with CUDA events between them; synchronises.
-    Returns [ms z-scan, ms y-pass, ms x-pass + finalize]."""
+    Returns [ms z-scan, ms y-pass, ms x-pass + finalize]; kernels=True appends the durations of
+    the y pass's and the x pass's main window-kernel launch alone (a pass also holds the pilot
+    probe, the decision and the stack kernel over the hand-over list)."""
     _require_cuda(occupancy, torch.float32, "occupancy")
     _require_cuda(out, torch.float32, "out")
     device = occupancy.device
     nx, ny, nz = occupancy.shape
-    pass_ms = (ctypes.c_float * 3)()
+    pass_ms = (ctypes.c_float * 5)()
     code = _capi.library().vgt_b200_sdf_f32_dev_profile(
         occupancy.data_ptr(), nx, ny, nz, float(resolution), 1, 0, device.index or 0,
         out.data_ptr(), None if min_max is None else min_max.data_ptr(), _stream_handle(device),
         pass_ms)
     _capi.check(code)
-    return [float(v) for v in pass_ms]
+    return [float(v) for v in pass_ms][:5 if kernels else 3]
 
 
 def signed_distance_field_f64(occupancy: torch.Tensor, resolution: float,
