@@ -229,6 +229,36 @@ def test_axes_longer_than_1024_and_large_distances(shared_library, oracle):
     assert_matches_oracle(oracle, sparse, 0.5)
 
 
+@pytest.mark.parametrize("nz", [1028, 1536, 2044, 2048])
+def test_register_z_scan_with_two_words_per_lane(shared_library, oracle, nz):
+    # z lines of 1025 .. 2048 voxels: the register scan keeps two words per lane ("halves");
+    # the last voxel of a class in the first half precedes every word of the second and the
+    # first one of the second half follows every word of the first. Lines whose only
+    # opposite-class voxel sits right at the boundary (voxels 1023 / 1024), at the ends, or
+    # nowhere; plus random lines.
+    rng = np.random.default_rng(nz)
+    occupancy = random_occupancy(rng, (3, 9, nz), 0.02, blobs=True)
+    occupancy[0, 0, :] = 0.0
+    occupancy[0, 0, 1023] = 1.0
+    occupancy[0, 1, :] = 0.0
+    occupancy[0, 1, 1024] = 1.0
+    occupancy[0, 2, :] = 1.0
+    occupancy[0, 2, 1024] = 0.0
+    occupancy[0, 3, :] = 0.0
+    occupancy[0, 3, 0] = 1.0
+    occupancy[0, 4, :] = 0.0
+    occupancy[0, 4, nz - 1] = 1.0
+    occupancy[0, 5, :] = 1.0
+    occupancy[0, 6, :] = 0.0
+    occupancy[0, 7, :1024] = 1.0
+    occupancy[0, 7, 1024:] = 0.0
+    got_filled, got_free = vgt.ComputeSquaredDistanceFields(occupancy, True)
+    want_filled, want_free = oracle.edt_squared(occupancy, True)
+    np.testing.assert_array_equal(got_filled, squared_to_int(want_filled))
+    np.testing.assert_array_equal(got_free, squared_to_int(want_free))
+    assert_matches_oracle(oracle, occupancy, 0.02)
+
+
 @pytest.mark.parametrize("shape", [(1, 1, 1), (1, 1, 40), (9, 1, 7), (1, 33, 5), (11, 14, 9),
                                    (40, 36, 70), (3, 130, 33), (64, 64, 64)])
 def test_transform_in_place_on_sampled_functions(shared_library, oracle, shape):

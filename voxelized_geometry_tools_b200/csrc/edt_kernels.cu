@@ -47,9 +47,9 @@ int LaunchScan(const In* d_in, uint32_t* d_out, int64_t num_lines, int32_t lengt
   const bool aligned = (length % 4 == 0)
       && (reinterpret_cast<uintptr_t>(d_in) % sizeof(typename Source::Vector) == 0)
       && (reinterpret_cast<uintptr_t>(d_out) % sizeof(uint4) == 0);
-  if (aligned && length <= 1024)
+  if (aligned && length <= 2048)
   {
-    // whole line in registers: 1, 2, 4 or 8 iterations of 128 voxels
+    // whole line in registers: 1, 2, 4, 8 or 16 iterations of 128 voxels
     const auto launch = [&](auto kernel)
     {
       kernel<<<static_cast<unsigned>(blocks), kScanWarpsPerBlock * kWarp, 0, stream>>>(
@@ -68,9 +68,13 @@ int LaunchScan(const In* d_in, uint32_t* d_out, int64_t num_lines, int32_t lengt
     {
       launch(ScanContiguousAxisRegistersKernel<Source, 4>);
     }
-    else
+    else if (length <= 1024)
     {
       launch(ScanContiguousAxisRegistersKernel<Source, 8>);
+    }
+    else
+    {
+      launch(ScanContiguousAxisRegistersKernel<Source, 16>);
     }
     VGT_CUDA_TRY(cudaGetLastError(), "ScanContiguousAxisRegistersKernel launch");
     return VGT_B200_OK;

@@ -1,4 +1,4 @@
-// Pass A (the contiguous z axis) for lines of at most 1024 voxels, entirely in registers (sm_100a).
+// Pass A (the contiguous z axis) for lines of at most 2048 voxels, entirely in registers (sm_100a).
 // Included by edt_kernels.cu after edt_device.cuh.
 //
 // Same algorithm as ScanContiguousAxisVec4Kernel (edt_device.cuh): one warp owns one line, a lane
@@ -27,9 +27,14 @@ namespace edt
 {
 namespace
 {
-// kIterations = ceil(length / 128) rounded up to 1, 2, 4 or 8 (so at most 32 words per line).
+// kIterations = ceil(length / 128) rounded up to 1, 2, 4, 8 or 16. Up to 8 iterations a line has
+// at most 32 words and lane w owns word w; with 16 iterations (lines of 1025 .. 2048 voxels) a
+// lane owns two words, w and w + 32 ("halves"): each half is scanned on its own and the totals
+// cross over (the last filled / free voxel of the first half precedes every word of the second,
+// the first one of the second half follows every word of the first).
 template <typename Source, int kIterations>
-__global__ void __launch_bounds__(kScanWarpsPerBlock* kWarp, 8) ScanContiguousAxisRegistersKernel(
+__global__ void __launch_bounds__(kScanWarpsPerBlock* kWarp, (kIterations > 8) ? 4 : 8)
+    ScanContiguousAxisRegistersKernel(
     const typename Source::Vector* __restrict__ in, uint4* __restrict__ out, int64_t num_lines,
     int32_t length, int unknown_is_filled)
 {
@@ -67,53 +72,84 @@ __global__ void __launch_bounds__(kScanWarpsPerBlock* kWarp, 8) ScanContiguousAx
     words[it] = word;
   }
 
-  // 2. lane w owns word w (= iteration w / 4, group w % 4): position of the last filled / free
-  //    voxel before the word and of the first one after it, by warp scans over the words.
-  uint32_t mine = 0;
+  // 2. lane w owns word w (= iteration w / 4, group w % 4) of every half: position of the last
+  //    filled / free voxel before the word and of the first one after it, by warp scans over the
+  //    words.
+  constexpr int kHalves = (kIterations + 7) / 8;
+  static_assert(kHalves <= 2, "at most 64 words per line");
+  uint32_t mine[kHalves];
+#pragma unroll
+  for (int h = 0; h < kHalves; h++)
+  {
+    mine[h] = 0;
+  }
 #pragma unroll
   for (int it = 0; it < kIterations; it++)
   {
     const uint32_t from_leader = __shfl_sync(kFull, words[it], (lane & 3) << 3);
-    mine = ((lane >> 2) == it) ? from_leader : mine;
+    mine[it >> 3] = ((lane >> 2) == (it & 7)) ? from_leader : mine[it >> 3];
   }
-  const uint32_t valid = (lane < num_words) ? ValidBits(lane, length) : 0u;
-  const uint32_t filled_bits = mine & valid;
-  const uint32_t free_bits = ~mine & valid;
-  int last_filled = filled_bits ? (lane << 5) + 31 - __clz(filled_bits) : -kFar;
-  int last_free = free_bits ? (lane << 5) + 31 - __clz(free_bits) : -kFar;
-  int first_filled = filled_bits ? (lane << 5) + __ffs(filled_bits) - 1 : kFar;
-  int first_free = free_bits ? (lane << 5) + __ffs(free_bits) - 1 : kFar;
+  int before_filled[kHalves], before_free[kHalves], after_filled[kHalves], after_free[kHalves];
+  int last_filled[kHalves], last_free[kHalves], first_filled[kHalves], first_free[kHalves];
 #pragma unroll
-  for (int offset = 1; offset < kWarp; offset <<= 1)
+  for (int h = 0; h < kHalves; h++)
   {
-    const int up_filled = __shfl_up_sync(kFull, last_filled, offset);
-    const int up_free = __shfl_up_sync(kFull, last_free, offset);
-    const int down_filled = __shfl_down_sync(kFull, first_filled, offset);
-    const int down_free = __shfl_down_sync(kFull, first_free, offset);
-    if (lane >= offset)
+    const int w = (h << 5) + lane;
+    const uint32_t valid = (w < num_words) ? ValidBits(w, length) : 0u;
+    const uint32_t filled_bits = mine[h] & valid;
+    const uint32_t free_bits = ~mine[h] & valid;
+    last_filled[h] = filled_bits ? (w << 5) + 31 - __clz(filled_bits) : -kFar;
+    last_free[h] = free_bits ? (w << 5) + 31 - __clz(free_bits) : -kFar;
+    first_filled[h] = filled_bits ? (w << 5) + __ffs(filled_bits) - 1 : kFar;
+    first_free[h] = free_bits ? (w << 5) + __ffs(free_bits) - 1 : kFar;
+#pragma unroll
+    for (int offset = 1; offset < kWarp; offset <<= 1)
     {
-      last_filled = max(last_filled, up_filled);
-      last_free = max(last_free, up_free);
-    }
-    if (lane + offset < kWarp)
-    {
-      first_filled = min(first_filled, down_filled);
-      first_free = min(first_free, down_free);
+      const int up_filled = __shfl_up_sync(kFull, last_filled[h], offset);
+      const int up_free = __shfl_up_sync(kFull, last_free[h], offset);
+      const int down_filled = __shfl_down_sync(kFull, first_filled[h], offset);
+      const int down_free = __shfl_down_sync(kFull, first_free[h], offset);
+      if (lane >= offset)
+      {
+        last_filled[h] = max(last_filled[h], up_filled);
+        last_free[h] = max(last_free[h], up_free);
+      }
+      if (lane + offset < kWarp)
+      {
+        first_filled[h] = min(first_filled[h], down_filled);
+        first_free[h] = min(first_free[h], down_free);
+      }
     }
   }
-  int before_filled = __shfl_up_sync(kFull, last_filled, 1);
-  int before_free = __shfl_up_sync(kFull, last_free, 1);
-  int after_filled = __shfl_down_sync(kFull, first_filled, 1);
-  int after_free = __shfl_down_sync(kFull, first_free, 1);
-  if (lane == 0)
+  // what precedes the first word of a half / follows its last word
+  int preceding_filled = -kFar, preceding_free = -kFar;
+#pragma unroll
+  for (int h = 0; h < kHalves; h++)
   {
-    before_filled = -kFar;
-    before_free = -kFar;
-  }
-  if (lane == kWarp - 1)
-  {
-    after_filled = kFar;
-    after_free = kFar;
+    int following_filled = kFar, following_free = kFar;
+    if (h + 1 < kHalves)
+    {
+      // (the suffix minimum at lane 0 of the next half covers that whole half)
+      following_filled = __shfl_sync(kFull, first_filled[h + 1], 0);
+      following_free = __shfl_sync(kFull, first_free[h + 1], 0);
+    }
+    before_filled[h] = __shfl_up_sync(kFull, max(last_filled[h], preceding_filled), 1);
+    before_free[h] = __shfl_up_sync(kFull, max(last_free[h], preceding_free), 1);
+    after_filled[h] = __shfl_down_sync(kFull, min(first_filled[h], following_filled), 1);
+    after_free[h] = __shfl_down_sync(kFull, min(first_free[h], following_free), 1);
+    if (lane == 0)
+    {
+      before_filled[h] = preceding_filled;
+      before_free[h] = preceding_free;
+    }
+    if (lane == kWarp - 1)
+    {
+      after_filled[h] = following_filled;
+      after_free[h] = following_free;
+    }
+    // (the prefix maximum at lane 31 covers this whole half)
+    preceding_filled = max(preceding_filled, __shfl_sync(kFull, last_filled[h], kWarp - 1));
+    preceding_free = max(preceding_free, __shfl_sync(kFull, last_free[h], kWarp - 1));
   }
 
   // 3. per voxel: nearest opposite-class voxel inside the word (bit scan) or outside (tables).
@@ -124,10 +160,11 @@ __global__ void __launch_bounds__(kScanWarpsPerBlock* kWarp, 8) ScanContiguousAx
     const int w = (it << 2) + group;
     const int word_start = w << 5;
     // positions relative to the start of the word (all lanes shuffle; stores are predicated)
-    const int left_of_filled = __shfl_sync(kFull, before_free, w) - word_start;
-    const int left_of_free = __shfl_sync(kFull, before_filled, w) - word_start;
-    const int right_of_filled = __shfl_sync(kFull, after_free, w) - word_start;
-    const int right_of_free = __shfl_sync(kFull, after_filled, w) - word_start;
+    // (the half, it >> 3, is known at compile time: the loop is unrolled)
+    const int left_of_filled = __shfl_sync(kFull, before_free[it >> 3], w & 31) - word_start;
+    const int left_of_free = __shfl_sync(kFull, before_filled[it >> 3], w & 31) - word_start;
+    const int right_of_filled = __shfl_sync(kFull, after_free[it >> 3], w & 31) - word_start;
+    const int right_of_free = __shfl_sync(kFull, after_filled[it >> 3], w & 31) - word_start;
     const uint32_t word = words[it];
     const uint32_t valid_here = ValidBits(w, length);
     const uint32_t opposite_of_filled = ~word & valid_here;
