@@ -215,6 +215,24 @@ __device__ __forceinline__ uint32_t ShiftRightByMultiply(uint32_t word)
   return __umulhi(word, kPowersOfTwo[32 - kBits]);
 }
 
+// A row word of the input. The addresses come out of 64-bit arithmetic the compiler no longer
+// knows the address space of; said explicitly, the load is an LDG instead of a generic LD.
+#ifndef VGT_WINDOW_GLOBAL_LOADS
+#define VGT_WINDOW_GLOBAL_LOADS 1
+#endif
+__device__ __forceinline__ uint32_t LoadRowWord(const void* address)
+{
+#if VGT_WINDOW_GLOBAL_LOADS == 1
+  uint32_t word;
+  asm("ld.global.u32 %0, [%1];" : "=r"(word) : "l"(address));
+  return word;
+#elif VGT_WINDOW_GLOBAL_LOADS == 2
+  return __ldg(static_cast<const uint32_t*>(address));
+#else
+  return *static_cast<const uint32_t*>(address);
+#endif
+}
+
 // Number of leading zero bits; 0xffffffff when the word is 0 (one FLO).
 __device__ __forceinline__ uint32_t LeadingZeros(uint32_t word)
 {
@@ -331,8 +349,7 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
   asm volatile("" : "+l"(line));
   const auto load_row = [&](int row)
   {
-    return *reinterpret_cast<const uint32_t*>(
-        line + static_cast<uint64_t>(static_cast<uint32_t>(row)) * stride_bytes);
+    return LoadRowWord(line + static_cast<uint64_t>(static_cast<uint32_t>(row)) * stride_bytes);
   };
   char* write_origin = reinterpret_cast<char*>(out + first);
   asm volatile("" : "+l"(write_origin));
@@ -788,7 +805,7 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
             ? OffsetRows(line, stride_bytes,
                          static_cast<uint32_t>(min(base + kAhead * kR + j, last_row)))
             : OffsetRows(read_next, stride_bytes, kSmallNumbers[j]);
-        raw[j] = *reinterpret_cast<const uint32_t*>(next_row);
+        raw[j] = LoadRowWord(next_row);
       }
     }
     // Every row's window minimum, and (kWithClasses) the nearest opposite-class row inside its
@@ -1038,10 +1055,10 @@ __global__ void __launch_bounds__(kWindowWarpsPerBlock* kWarp, kBlocksPerSm)
         {
           const int below = __viaddmax_s32(base - kR - 1 - u, -t, 0);
           const int above = __viaddmin_s32(base + 2 * kR + u, t, last_row);
-          words_below[u] = *reinterpret_cast<const uint32_t*>(
-              line + static_cast<uint64_t>(static_cast<uint32_t>(below)) * stride_bytes);
-          words_above[u] = *reinterpret_cast<const uint32_t*>(
-              line + static_cast<uint64_t>(static_cast<uint32_t>(above)) * stride_bytes);
+          words_below[u] =
+              LoadRowWord(line + static_cast<uint64_t>(static_cast<uint32_t>(below)) * stride_bytes);
+          words_above[u] =
+              LoadRowWord(line + static_cast<uint64_t>(static_cast<uint32_t>(above)) * stride_bytes);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; u++)
