@@ -249,7 +249,7 @@ public:
     return position - starting_offset;
   }
   const T& DefaultValue() const { return default_value_; }
-  const T& OobValue() const { return oob_value_; }
+  const T& OOBValue() const { return oob_value_; }
 
   bool IsInitialized() const { return initialized_; }
   bool HasUniformVoxelSize() const { return sizes_.UniformVoxelSize(); }

@@ -57,7 +57,7 @@ int Load(const char* path, Scalar* values, int64_t capacity, int64_t* dims, doub
   frame[frame_capacity - 1] = 0;
   *locked = field.IsLocked() ? 1 : 0;
   default_and_oob[0] = static_cast<double>(field.DefaultValue());
-  default_and_oob[1] = static_cast<double>(field.OobValue());
+  default_and_oob[1] = static_cast<double>(field.OOBValue());
   if (field.NumTotalVoxels() > capacity)
   {
     return 3;

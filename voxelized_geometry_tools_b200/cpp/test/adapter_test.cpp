@@ -30,6 +30,7 @@
 #include <voxelized_geometry_tools/tagged_object_occupancy_map.hpp>
 
 #include "b200_cell_map_signed_distance_fields.hpp"
+#include "b200_grid_files.hpp"
 #include "b200_mesh_rasterizer.hpp"
 #include "b200_pointcloud_voxelization.hpp"
 #include "b200_signed_distance_field_generation.hpp"
@@ -747,6 +748,78 @@ void MeshRasterizerTest()
   EXPECT_TRUE(threw);
 }
 
+// the SDF files. The reference's own SaveToFile / LoadFromFile (compiled here over
+// the stand-in serialization layer) against the library's writer / reader: same bytes, and
+// each side loads what the other wrote; a field computed on the device goes to a file
+// without a host copy of the caller's own.
+std::vector<char> FileBytes(const std::string& path)
+{
+  std::vector<char> bytes;
+  if (FILE* file = std::fopen(path.c_str(), "rb"))
+  {
+    char buffer[4096];
+    size_t got = 0;
+    while ((got = std::fread(buffer, 1, sizeof(buffer), file)) > 0)
+    {
+      bytes.insert(bytes.end(), buffer, buffer + got);
+    }
+    std::fclose(file);
+  }
+  return bytes;
+}
+
+template <typename ScalarType>
+void GridFileTest()
+{
+  namespace files = grid_files::b200;
+  OccupancyMap map = MakeMap(0.25, 2.0, 1.5, 1.0, 0.0f);
+  for (int64_t x = 2; x < 5; x++)
+  {
+    for (int64_t y = 1; y < 4; y++)
+    {
+      map.SetIndex(x, y, 2, OccupancyCell(1.0f));
+    }
+  }
+  const SignedDistanceField<ScalarType> sdf =
+      b200::ExtractSignedDistanceFieldFromOccupancyMap<OccupancyMap, ScalarType>(
+          map, SDFGenerationParams<ScalarType>());
+  const std::string base = std::string("/tmp/vgt_b200_adapter_") + (sizeof(ScalarType) == 4 ? "f" : "d");
+  for (const bool compress : {false, true})
+  {
+    const std::string theirs = base + (compress ? "_theirs.sdfz" : "_theirs.sdfr");
+    const std::string ours = base + (compress ? "_ours.sdfz" : "_ours.sdfr");
+    SignedDistanceField<ScalarType>::SaveToFile(sdf, theirs, compress);
+    files::SaveSignedDistanceFieldToFile(sdf, ours, compress);
+    const auto their_bytes = FileBytes(theirs);
+    EXPECT_TRUE(!their_bytes.empty());
+    EXPECT_TRUE(their_bytes == FileBytes(ours));
+    // the reference's reader on our file, our reader on the reference's file
+    const auto from_ours = SignedDistanceField<ScalarType>::LoadFromFile(ours);
+    const auto from_theirs = files::LoadSignedDistanceFieldFromFile<ScalarType>(theirs);
+    for (const auto* loaded : {&from_ours, &from_theirs})
+    {
+      EXPECT_TRUE(loaded->GetImmutableRawData() == sdf.GetImmutableRawData());
+      EXPECT_TRUE(loaded->Frame() == sdf.Frame());
+      EXPECT_TRUE(loaded->IsLocked() == sdf.IsLocked());
+      EXPECT_TRUE(loaded->NumXVoxels() == sdf.NumXVoxels() && loaded->NumZVoxels() == sdf.NumZVoxels());
+      EXPECT_TRUE(loaded->GetMinimumMaximum().Minimum() == sdf.GetMinimumMaximum().Minimum());
+      EXPECT_TRUE(loaded->GetMinimumMaximum().Maximum() == sdf.GetMinimumMaximum().Maximum());
+    }
+    std::remove(theirs.c_str());
+    std::remove(ours.c_str());
+  }
+  bool threw = false;
+  try
+  {
+    files::LoadSignedDistanceFieldFromFile<ScalarType>(base + "_missing.sdf");
+  }
+  catch (const std::invalid_argument& error)
+  {
+    threw = std::string(error.what()) == "File does not exist";
+  }
+  EXPECT_TRUE(threw);
+}
+
 int main(int argc, char** argv)
 {
   if (vgt_b200_device_count() < 1)
@@ -766,6 +839,8 @@ int main(int argc, char** argv)
   TransformTest();
   FactoryTest();
   MeshRasterizerTest();
+  GridFileTest<float>();
+  GridFileTest<double>();
   if (g_failures == 0)
   {
     std::printf("ADAPTER_TEST_OK\n");
