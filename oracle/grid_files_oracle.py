@@ -23,7 +23,8 @@ count followed by the items; an Isometry3d as its 4x4 matrix, column-major; the 
 initialized flag, origin transform, inverse origin transform, cells, voxel sizes, voxel counts,
 default value, out-of-bounds value. The reference's own tests never touch these members, so no
 golden file exists; tests/test_grid_files.py checks the product against this module and against
-the reference's members compiled over oracle/ref_shim (which restates the same third-party layer).
+the reference's own members - SignedDistanceField<T> and OccupancyMap, headers and sources
+unmodified - compiled over oracle/ref_shim (which restates the same third-party layer).
 """
 from __future__ import annotations
 

@@ -222,6 +222,64 @@ def test_reference_errors_match(tmp_path, reference_library):
     assert code == 1 and message == "File has invalid header [CMGR]"
 
 
+@pytest.fixture(scope="module")
+def reference_maps_library():
+    """oracle/_ref/libvgt_ref_maps.so: the reference's own OccupancyMap with its file members."""
+    path = reference_oracle._PATH.with_name("libvgt_ref_maps.so")
+    if not path.exists():
+        pytest.skip("oracle/_ref/libvgt_ref_maps.so is not built (needs /root/reference)")
+    return ctypes.CDLL(str(path))
+
+
+@pytest.mark.parametrize("compress", [False, True])
+def test_map_files_equal_the_references_own_members(tmp_path, reference_maps_library, compress):
+    rng = np.random.default_rng(23)
+    shape = (5, 7, 3)
+    sizes = grids.VoxelGridSizes.FromVoxelCounts(0.125, shape)
+    cells = rng.choice(np.array([0.0, 0.25, 0.5, 1.0], dtype=np.float32), size=shape)
+    occupancy_map = grids.OccupancyMap(origin_transform(rng), "map_frame", sizes,
+                                       default_occupancy=0.5, data=cells)
+    ours, theirs = tmp_path / "ours.cmg", tmp_path / "theirs.cmg"
+    grid_files.SaveOccupancyMapToFile(occupancy_map, ours, compress)
+    origin = np.ascontiguousarray(occupancy_map.OriginTransform().T.reshape(-1))
+    message = ctypes.create_string_buffer(256)
+    code = reference_maps_library.vgt_ref_map_save_to_file(
+        cells.ctypes.data_as(ctypes.c_void_p), *(ctypes.c_int64(v) for v in shape),
+        ctypes.c_double(0.125), origin.ctypes.data_as(ctypes.c_void_p), b"map_frame",
+        ctypes.c_float(0.5), ctypes.c_float(0.5), str(theirs).encode(), ctypes.c_int(compress),
+        message, ctypes.c_int64(256))
+    assert code == 0, message.value
+    assert ours.read_bytes() == theirs.read_bytes()
+    # the reference's LoadFromFile on our file
+    values = np.zeros(cells.size, dtype=np.float32)
+    dims = (ctypes.c_int64 * 3)()
+    resolution = ctypes.c_double()
+    got_origin = np.zeros(16)
+    frame = ctypes.create_string_buffer(64)
+    default_and_oob = (ctypes.c_float * 2)()
+    code = reference_maps_library.vgt_ref_map_load_from_file(
+        str(ours).encode(), values.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(values.size),
+        dims, ctypes.byref(resolution), got_origin.ctypes.data_as(ctypes.c_void_p), frame,
+        ctypes.c_int64(64), default_and_oob, message, ctypes.c_int64(256))
+    assert code == 0, message.value
+    assert tuple(dims) == shape and resolution.value == 0.125
+    assert frame.value == b"map_frame" and tuple(default_and_oob) == (0.5, 0.5)
+    assert np.array_equal(values.reshape(shape), cells)
+    assert np.array_equal(got_origin.reshape(4, 4).T, occupancy_map.OriginTransform())
+    # ours on the reference's file
+    loaded = grid_files.LoadOccupancyMapFromFile(theirs)
+    assert np.array_equal(loaded.GetImmutableRawData(), cells) and loaded.Frame() == "map_frame"
+    # and the reference's errors
+    code = reference_maps_library.vgt_ref_map_load_from_file(
+        str(tmp_path / "missing.cmg").encode(), values.ctypes.data_as(ctypes.c_void_p),
+        ctypes.c_int64(values.size), dims, ctypes.byref(resolution),
+        got_origin.ctypes.data_as(ctypes.c_void_p), frame, ctypes.c_int64(64), default_and_oob,
+        message, ctypes.c_int64(256))
+    assert code == 1 and message.value == b"File does not exist"
+    with pytest.raises(ValueError, match="File does not exist"):
+        grid_files.LoadOccupancyMapFromFile(tmp_path / "missing.cmg")
+
+
 @pytest.mark.gpu
 def test_device_resident_sdf_saved_straight_to_a_file(tmp_path):
     import torch
