@@ -58,6 +58,36 @@ def sdf(occupancy, resolution: float, unknown_is_filled: bool = True,
     return out, (min_max[0], min_max[1])
 
 
+# The reference's own OccupancyMap (occupancy_map.hpp / .cpp unmodified) lives in a library of
+# its own, see oracle/ref_shim/ref_map_files_entry.cpp.
+_MAPS_PATH = _PATH.with_name("libvgt_ref_maps.so")
+_maps_lib = None
+
+
+def maps_available() -> bool:
+    return _MAPS_PATH.exists()
+
+
+def occupancy_map_sdf(occupancy, resolution: float, unknown_is_filled: bool = True,
+                      add_virtual_border: bool = False, threads: int = 0, dtype=np.float32):
+    """OccupancyMap::ExtractSignedDistanceField<T> (occupancy_map.hpp:174-216) - the public entry
+    this backend drops in for - on the reference's own class."""
+    global _maps_lib
+    if _maps_lib is None:
+        _maps_lib = ctypes.CDLL(str(_MAPS_PATH))
+    occ = np.ascontiguousarray(occupancy, dtype=np.float32)
+    out = np.empty(occ.shape, dtype=dtype)
+    min_max = np.zeros(2, dtype=dtype)
+    code = _maps_lib.vgt_ref_map_extract_sdf(
+        ctypes.c_int(np.dtype(dtype).itemsize), occ.ctypes.data_as(ctypes.c_void_p),
+        *(ctypes.c_int64(v) for v in occ.shape), ctypes.c_double(resolution),
+        ctypes.c_int(unknown_is_filled), ctypes.c_int(add_virtual_border), ctypes.c_int(threads),
+        out.ctypes.data_as(ctypes.c_void_p), min_max.ctypes.data_as(ctypes.c_void_p))
+    if code != 0:
+        raise RuntimeError("reference OccupancyMap::ExtractSignedDistanceField failed")
+    return out, (min_max[0], min_max[1])
+
+
 def transform_inplace(field: np.ndarray, threads: int = 0) -> np.ndarray:
     assert field.dtype == np.float64 and field.flags.c_contiguous and field.ndim == 3
     if lib().vgt_ref_transform_inplace_f64(field.ctypes.data_as(_f64p), *field.shape, threads):

@@ -229,6 +229,27 @@ def test_axes_longer_than_1024_and_large_distances(shared_library, oracle):
     assert_matches_oracle(oracle, sparse, 0.5)
 
 
+def test_drop_in_equals_the_references_own_occupancy_map_member(shared_library):
+    # OccupancyMap::ExtractSignedDistanceField<T> on the reference's own class (its
+    # occupancy_map.hpp / .cpp compiled unmodified into oracle/_ref/libvgt_ref_maps.so) against
+    # the same call on the device: values, extrema, both scalar types, both predicates, border.
+    from oracle import reference_oracle
+    if not reference_oracle.maps_available():
+        pytest.skip("oracle/_ref/libvgt_ref_maps.so not built")
+    rng = np.random.default_rng(77)
+    for shape in ((40, 36, 70), (7, 130, 33)):
+        occupancy = random_occupancy(rng, shape, 0.08, unknown=0.1, blobs=True)
+        for unknown_is_filled, border, dtype in ((True, False, np.float32),
+                                                 (False, True, np.float32),
+                                                 (True, True, np.float64)):
+            want, (lo, hi) = reference_oracle.occupancy_map_sdf(
+                occupancy, 0.05, unknown_is_filled, border, dtype=dtype)
+            sdf = make_map(occupancy, 0.05).ExtractSignedDistanceField(
+                params(unknown_is_filled, border), dtype)
+            np.testing.assert_array_equal(sdf.GetImmutableRawData(), want)
+            assert sdf.GetMinimumMaximum() == (lo, hi)
+
+
 @pytest.mark.parametrize("nz", [1028, 1536, 2044, 2048])
 def test_register_z_scan_with_two_words_per_lane(shared_library, oracle, nz):
     # z lines of 1025 .. 2048 voxels: the register scan keeps two words per lane ("halves");

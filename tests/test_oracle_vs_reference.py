@@ -43,6 +43,24 @@ def test_restatement_equals_reference(oracle, shape):
             assert mine_extrema == their_extrema
 
 
+@pytest.mark.skipif(not reference_oracle.maps_available(),
+                    reason="oracle/_ref/libvgt_ref_maps.so not built")
+@pytest.mark.parametrize("shape", [(1, 1, 1), (4, 8, 12), (9, 1, 7), (13, 11, 17), (3, 40, 9)])
+def test_restatement_equals_the_references_own_occupancy_map_member(oracle, shape):
+    # OccupancyMap::ExtractSignedDistanceField<T> itself (occupancy_map.hpp:174-216): the public
+    # entry, with the reference's own predicate (:181-205) on its own OccupancyCell grid.
+    rng = np.random.default_rng(abs(hash(shape)) % 2 ** 32 + 5)
+    for fill, unknown_is_filled, border in itertools.product(
+            (0.0, 0.1, 0.6, 1.0), (True, False), (False, True)):
+        occupancy = random_occupancy(rng, shape, fill, unknown=0.2)
+        for dtype in (np.float32, np.float64):
+            mine, mine_extrema = oracle.sdf(occupancy, 0.3, unknown_is_filled, border, dtype=dtype)
+            theirs, their_extrema = reference_oracle.occupancy_map_sdf(
+                occupancy, 0.3, unknown_is_filled, border, dtype=dtype)
+            np.testing.assert_array_equal(mine, theirs)
+            assert mine_extrema == their_extrema
+
+
 def test_restatement_equals_reference_medium(oracle):
     rng = np.random.default_rng(101)
     occupancy = random_occupancy(rng, (64, 72, 80), 0.1, blobs=True)
