@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <stdexcept>
+#include <vector>
 
 namespace common_robotics_utilities
 {
@@ -17,6 +18,13 @@ inline T ClampValue(const T& value, const T& min, const T& max)
 {
   if (max < min) { throw std::invalid_argument("min > max"); }
   return std::min(max, std::max(min, value));
+}
+
+// (tagged_object_occupancy_map.hpp:286-288: the ids collected in a set, as a vector)
+template <typename Key, typename SetLike>
+inline std::vector<Key> GetKeysFromSetLike(const SetLike& set_like)
+{
+  return std::vector<Key>(set_like.begin(), set_like.end());
 }
 
 template <typename T, std::memory_order kOrder>

@@ -88,6 +88,33 @@ def occupancy_map_sdf(occupancy, resolution: float, unknown_is_filled: bool = Tr
     return out, (min_max[0], min_max[1])
 
 
+def tagged_map_sdf(cells, resolution: float, objects_to_use=(), unknown_is_filled: bool = True,
+                   add_virtual_border: bool = False, free_and_named: bool = False,
+                   dtype=np.float32):
+    """TaggedObjectOccupancyMap::ExtractSignedDistanceField<T>(objects_to_use, parameters)
+    (tagged_object_occupancy_map.hpp:199-247) or, free_and_named=True,
+    ::ExtractFreeAndNamedObjectsSignedDistanceField<T> (:293-378), on the reference's own class.
+    cells: structured array with 8-byte {occupancy float32, object_id uint32} items."""
+    global _maps_lib
+    if _maps_lib is None:
+        _maps_lib = ctypes.CDLL(str(_MAPS_PATH))
+    cells = np.ascontiguousarray(cells)
+    assert cells.dtype.itemsize == 8, "TaggedObjectOccupancyCell is {float32, uint32}"
+    ids = np.ascontiguousarray(np.asarray(list(objects_to_use), dtype=np.uint32))
+    out = np.empty(cells.shape, dtype=dtype)
+    min_max = np.zeros(2, dtype=dtype)
+    code = _maps_lib.vgt_ref_tagged_map_sdf(
+        ctypes.c_int(np.dtype(dtype).itemsize), cells.ctypes.data_as(ctypes.c_void_p),
+        *(ctypes.c_int64(v) for v in cells.shape), ctypes.c_double(resolution),
+        ids.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(ids.size),
+        ctypes.c_int(unknown_is_filled), ctypes.c_int(add_virtual_border),
+        ctypes.c_int(free_and_named), out.ctypes.data_as(ctypes.c_void_p),
+        min_max.ctypes.data_as(ctypes.c_void_p))
+    if code != 0:
+        raise RuntimeError("reference TaggedObjectOccupancyMap SDF failed")
+    return out, (min_max[0], min_max[1])
+
+
 def transform_inplace(field: np.ndarray, threads: int = 0) -> np.ndarray:
     assert field.dtype == np.float64 and field.flags.c_contiguous and field.ndim == 3
     if lib().vgt_ref_transform_inplace_f64(field.ctypes.data_as(_f64p), *field.shape, threads):

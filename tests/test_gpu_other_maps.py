@@ -114,6 +114,30 @@ def test_free_and_named_objects(shared_library, oracle, map_type):
         assert_same(got, want, extrema)
 
 
+def test_tagged_map_equals_the_references_own_members(shared_library):
+    # the device entries against the reference's own TaggedObjectOccupancyMap members
+    # (tagged_object_occupancy_map.hpp / .cpp compiled unmodified, oracle/_ref/libvgt_ref_maps.so)
+    from oracle import reference_oracle
+    if not reference_oracle.maps_available():
+        pytest.skip("oracle/_ref/libvgt_ref_maps.so not built")
+    rng = np.random.default_rng(54)
+    shape = (21, 26, 38)
+    cells = random_cells(rng, shape, grids.TAGGED_OBJECT_OCCUPANCY_CELL, num_objects=5)
+    tagged = vgt.TaggedObjectOccupancyMap(IDENTITY, "f", sizes_of(shape, 0.04), cells)
+    for objects, unknown, border, dtype in (
+            ([], True, False, np.float32), ([2, 4], False, True, np.float32),
+            ([3], True, True, np.float64)):
+        want, extrema = reference_oracle.tagged_map_sdf(cells, 0.04, objects, unknown, border,
+                                                        dtype=dtype)
+        assert_same(tagged.ExtractSignedDistanceField(objects, params(unknown, border), dtype),
+                    want, extrema)
+    for unknown, border, dtype in ((True, False, np.float32), (False, True, np.float64)):
+        want, extrema = reference_oracle.tagged_map_sdf(cells, 0.04, (), unknown, border,
+                                                        free_and_named=True, dtype=dtype)
+        assert_same(tagged.ExtractFreeAndNamedObjectsSignedDistanceField(params(unknown, border),
+                                                                         dtype), want, extrema)
+
+
 def test_cell_entry_rejects_bad_arguments(shared_library):
     lib = _capi.library()
     cells = np.zeros((2, 2, 2, 3), dtype=np.uint32)

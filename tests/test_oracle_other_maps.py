@@ -2,10 +2,12 @@
 rank 1) against the reference's own assertions: the four map types produce the same SDF for the
 same occupancy (test/sdf_generation_test.cpp:152-189), and hand-checked predicate / merge cases."""
 import numpy as np
+import pytest
 
+from oracle import reference_oracle
 from voxelized_geometry_tools_b200 import grids
 
-from .conftest import occupancy_from_golden_case
+from .conftest import occupancy_from_golden_case, random_occupancy
 
 
 def tagged_cells(occupancy, object_ids, dtype=grids.TAGGED_OBJECT_OCCUPANCY_CELL):
@@ -53,3 +55,33 @@ def test_free_and_named_merge(oracle):
     # not inside a named object, so it reads 0; the named cell reads its depth inside named space
     assert got.ravel().tolist() == [2.0, 1.0, 0.0, 0.0, 1.0, 1.0, -1.0]
     assert (lo, hi) == (-1.0, 2.0)
+
+
+@pytest.mark.skipif(not reference_oracle.maps_available(),
+                    reason="oracle/_ref/libvgt_ref_maps.so not built")
+def test_restatement_equals_the_references_own_tagged_map_members(oracle):
+    # TaggedObjectOccupancyMap::ExtractSignedDistanceField<T>(objects_to_use, ...) and
+    # ::ExtractFreeAndNamedObjectsSignedDistanceField<T> on the reference's own class (its
+    # tagged_object_occupancy_map.hpp / .cpp compiled unmodified): predicate with and without
+    # ids, ids that do not occur, repeated ids, both unknown rules, border, both scalar types.
+    rng = np.random.default_rng(61)
+    for shape in ((9, 7, 11), (14, 20, 6)):
+        occupancy = random_occupancy(rng, shape, 0.25, unknown=0.15)
+        ids = rng.integers(0, 5, size=shape).astype(np.uint32)
+        cells = tagged_cells(occupancy, ids)
+        for objects, unknown, border, dtype in (
+                ((), True, False, np.float32), ((3,), True, False, np.float32),
+                ((1, 4, 4), False, True, np.float32), ((77,), True, False, np.float64),
+                ((0, 2), False, True, np.float64)):
+            mine, mine_extrema = oracle.sdf_from_cells(cells, 0.2, unknown, border, objects,
+                                                       dtype=dtype)
+            theirs, their_extrema = reference_oracle.tagged_map_sdf(
+                cells, 0.2, objects, unknown, border, dtype=dtype)
+            np.testing.assert_array_equal(mine, theirs)
+            assert mine_extrema == their_extrema
+        for unknown, border, dtype in ((True, False, np.float32), (False, True, np.float64)):
+            mine, mine_extrema = oracle.sdf_free_and_named(cells, 0.2, unknown, border, dtype)
+            theirs, their_extrema = reference_oracle.tagged_map_sdf(
+                cells, 0.2, (), unknown, border, free_and_named=True, dtype=dtype)
+            np.testing.assert_array_equal(mine, theirs)
+            assert mine_extrema == their_extrema
