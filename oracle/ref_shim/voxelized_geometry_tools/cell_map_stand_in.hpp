@@ -1,8 +1,9 @@
-// TEST INFRASTRUCTURE ONLY -- shared body of the stand-ins for the reference's three cell-map
-// headers (occupancy_component_map.hpp, tagged_object_occupancy_map.hpp,
-// tagged_object_occupancy_component_map.hpp). The real headers need the serialization / maybe /
-// topology layers of common_robotics_utilities; the C++ adapter only needs the packed cell
-// layouts (which the reference pins with static_asserts) and the grid surface.
+// TEST INFRASTRUCTURE ONLY -- shared body of the stand-ins for the reference's two component-map
+// headers (occupancy_component_map.hpp, tagged_object_occupancy_component_map.hpp). The real
+// headers need the logging / topology layers of common_robotics_utilities; the C++ adapter only
+// needs the packed cell layouts (which the reference pins with static_asserts) and the grid
+// surface. (OccupancyMap and TaggedObjectOccupancyMap are the reference's own classes: their
+// headers compile over the shim as they are.)
 #pragma once
 
 #include <cstdint>
