@@ -5,7 +5,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace common_robotics_utilities
@@ -27,7 +29,10 @@ inline std::vector<Key> GetKeysFromSetLike(const SetLike& set_like)
   return std::vector<Key>(set_like.begin(), set_like.end());
 }
 
-template <typename T, std::memory_order kOrder>
+// (topology_computation.hpp:335, occupancy_component_map.hpp:267: an optional message sink)
+using LoggingFunction = std::function<void(const std::string&)>;
+
+template <typename T, std::memory_order kOrder = std::memory_order_seq_cst>
 class CopyableMoveableAtomic
 {
 public:

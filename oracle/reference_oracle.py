@@ -115,6 +115,37 @@ def tagged_map_sdf(cells, resolution: float, objects_to_use=(), unknown_is_fille
     return out, (min_max[0], min_max[1])
 
 
+def component_map_sdf(cells, resolution: float, objects_to_use=(), unknown_is_filled: bool = True,
+                      add_virtual_border: bool = False, free_and_named: bool = False,
+                      dtype=np.float32):
+    """The SDF members of the reference's own OccupancyComponentMap (8-byte cells:
+    occupancy_component_map.hpp:270-306) and TaggedObjectOccupancyComponentMap (16-byte cells:
+    tagged_object_occupancy_component_map.hpp:360-575), chosen by the cell size."""
+    global _maps_lib
+    if _maps_lib is None:
+        _maps_lib = ctypes.CDLL(str(_MAPS_PATH))
+    cells = np.ascontiguousarray(cells)
+    if cells.dtype.itemsize == 8:
+        kind = 1
+        assert not objects_to_use and not free_and_named
+    else:
+        assert cells.dtype.itemsize == 16
+        kind = 3 if free_and_named else 2
+    ids = np.ascontiguousarray(np.asarray(list(objects_to_use), dtype=np.uint32))
+    out = np.empty(cells.shape, dtype=dtype)
+    min_max = np.zeros(2, dtype=dtype)
+    code = _maps_lib.vgt_ref_component_map_sdf(
+        ctypes.c_int(kind), ctypes.c_int(np.dtype(dtype).itemsize),
+        cells.ctypes.data_as(ctypes.c_void_p), *(ctypes.c_int64(v) for v in cells.shape),
+        ctypes.c_double(resolution), ids.ctypes.data_as(ctypes.c_void_p),
+        ctypes.c_int64(ids.size), ctypes.c_int(unknown_is_filled),
+        ctypes.c_int(add_virtual_border), out.ctypes.data_as(ctypes.c_void_p),
+        min_max.ctypes.data_as(ctypes.c_void_p))
+    if code != 0:
+        raise RuntimeError("reference component map SDF failed")
+    return out, (min_max[0], min_max[1])
+
+
 def transform_inplace(field: np.ndarray, threads: int = 0) -> np.ndarray:
     assert field.dtype == np.float64 and field.flags.c_contiguous and field.ndim == 3
     if lib().vgt_ref_transform_inplace_f64(field.ctypes.data_as(_f64p), *field.shape, threads):

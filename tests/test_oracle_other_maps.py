@@ -85,3 +85,42 @@ def test_restatement_equals_the_references_own_tagged_map_members(oracle):
                 cells, 0.2, (), unknown, border, free_and_named=True, dtype=dtype)
             np.testing.assert_array_equal(mine, theirs)
             assert mine_extrema == their_extrema
+
+
+@pytest.mark.skipif(not reference_oracle.maps_available(),
+                    reason="oracle/_ref/libvgt_ref_maps.so not built")
+def test_restatement_equals_the_references_own_component_map_members(oracle):
+    # OccupancyComponentMap and TaggedObjectOccupancyComponentMap (headers and sources
+    # unmodified): their SDF members against the restatement, component / segment words filled
+    # with noise (they must not matter).
+    rng = np.random.default_rng(62)
+    shape = (10, 9, 13)
+    occupancy = random_occupancy(rng, shape, 0.3, unknown=0.15)
+    component = np.zeros(shape, dtype=grids.OCCUPANCY_COMPONENT_CELL)
+    component["occupancy"] = occupancy
+    component["component"] = rng.integers(0, 2 ** 32, size=shape, dtype=np.uint64).astype(np.uint32)
+    for unknown, border, dtype in ((True, False, np.float32), (False, True, np.float64)):
+        mine, mine_extrema = oracle.sdf_from_cells(component, 0.1, unknown, border, dtype=dtype)
+        theirs, their_extrema = reference_oracle.component_map_sdf(
+            component, 0.1, (), unknown, border, dtype=dtype)
+        np.testing.assert_array_equal(mine, theirs)
+        assert mine_extrema == their_extrema
+    tagged = tagged_cells(occupancy, rng.integers(0, 4, size=shape).astype(np.uint32),
+                          grids.TAGGED_OBJECT_OCCUPANCY_COMPONENT_CELL)
+    tagged["component"] = rng.integers(0, 1000, size=shape).astype(np.uint32)
+    tagged["spatial_segment"] = rng.integers(0, 1000, size=shape).astype(np.uint32)
+    for objects, unknown, border, dtype in (((), True, False, np.float32),
+                                            ((2, 3), False, True, np.float32),
+                                            ((1,), True, True, np.float64)):
+        mine, mine_extrema = oracle.sdf_from_cells(tagged, 0.1, unknown, border, objects,
+                                                   dtype=dtype)
+        theirs, their_extrema = reference_oracle.component_map_sdf(
+            tagged, 0.1, objects, unknown, border, dtype=dtype)
+        np.testing.assert_array_equal(mine, theirs)
+        assert mine_extrema == their_extrema
+    for unknown, border, dtype in ((True, False, np.float32), (False, True, np.float64)):
+        mine, mine_extrema = oracle.sdf_free_and_named(tagged, 0.1, unknown, border, dtype)
+        theirs, their_extrema = reference_oracle.component_map_sdf(
+            tagged, 0.1, (), unknown, border, free_and_named=True, dtype=dtype)
+        np.testing.assert_array_equal(mine, theirs)
+        assert mine_extrema == their_extrema
