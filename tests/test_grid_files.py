@@ -147,6 +147,57 @@ def test_empty_frame_and_single_cell(tmp_path):
     assert loaded.GetImmutableRawData().tolist() == [[[2.5]]] and loaded._oob_value == 0.0
 
 
+# ---- committed golden files written by the reference's own members --------------------------------
+def test_golden_files_written_by_the_reference(tmp_path):
+    # tests/golden/grid_files/*: written by SignedDistanceField<T>::SaveToFile and
+    # OccupancyMap::SaveToFile of the reference build (tests/golden/make_grid_file_goldens.py).
+    # The product must write the same bytes for the same inputs, and read them back.
+    import json
+    from pathlib import Path
+    golden = Path(__file__).resolve().parent / "golden" / "grid_files"
+    index = json.loads((golden / "index.json").read_text())
+    shape = tuple(index["shape"])
+    origin = np.array(index["origin_row_major"]).reshape(4, 4)
+    values = (np.arange(np.prod(shape), dtype=np.float64).reshape(shape) - 7.5) * 0.125
+    cells = np.array([0.0, 0.5, 1.0, 0.25], dtype=np.float32)[np.arange(np.prod(shape)) % 4]
+    cells = cells.reshape(shape)
+    sizes = grids.VoxelGridSizes.FromVoxelCounts(index["resolution"], shape)
+    assert len(index["files"]) == 10
+    for name, what in index["files"].items():
+        want = (golden / name).read_bytes()
+        out = tmp_path / name
+        if what["kind"] == "sdf":
+            dtype = np.float32 if what["dtype"] == "f32" else np.float64
+            sdf = grids.SignedDistanceField(origin, index["frame"], sizes, values.astype(dtype),
+                                            index["oob_value"])
+            if what["locked"]:
+                sdf.Lock()
+            grid_files.SaveSignedDistanceFieldToFile(sdf, out, what["compressed"])
+            assert out.read_bytes() == want, name
+            loaded = grid_files.LoadSignedDistanceFieldFromFile(golden / name, dtype)
+            assert np.array_equal(loaded.GetImmutableRawData(), values.astype(dtype))
+            assert loaded.IsLocked() == what["locked"] and loaded.Frame() == index["frame"]
+            assert loaded._oob_value == index["oob_value"]
+            assert np.array_equal(loaded.OriginTransform(), origin)
+            # the restated oracle agrees with the reference's bytes too
+            payload = gfo.load_from_file(golden / name, gfo.SDF_MAGIC)
+            assert payload == gfo.serialize_grid(values.astype(dtype), index["resolution"],
+                                                 origin.T.reshape(-1), index["oob_value"],
+                                                 index["oob_value"], index["frame"],
+                                                 locked=what["locked"])
+        else:
+            occupancy_map = grids.OccupancyMap(origin, index["frame"], sizes,
+                                               default_occupancy=what["default_occupancy"],
+                                               data=cells)
+            occupancy_map._oob_occupancy = what["oob_occupancy"]
+            grid_files.SaveOccupancyMapToFile(occupancy_map, out, what["compressed"])
+            assert out.read_bytes() == want, name
+            loaded = grid_files.LoadOccupancyMapFromFile(golden / name)
+            assert np.array_equal(loaded.GetImmutableRawData(), cells)
+            assert loaded._default_occupancy == what["default_occupancy"]
+            assert loaded._oob_occupancy == what["oob_occupancy"]
+
+
 # ---- against the reference's own members (oracle/_ref, built where /root/reference exists) ----
 def reference_save(reference_library, sdf, path, compress):
     data = np.ascontiguousarray(sdf.GetImmutableRawData())
