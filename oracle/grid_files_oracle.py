@@ -21,8 +21,9 @@ which is neither in the reference tree nor pinned by it (package.xml.ros2:12). T
 restated as published by that library: raw little-endian items; strings and vectors as a uint64
 count followed by the items; an Isometry3d as its 4x4 matrix, column-major; the grid as
 initialized flag, origin transform, inverse origin transform, cells, voxel sizes, voxel counts,
-default value, out-of-bounds value. The reference's own tests never touch these members, so no
-golden file exists; tests/test_grid_files.py checks the product against this module and against
+default value, out-of-bounds value. The reference's own tests never touch these members; the
+golden files under tests/golden/grid_files/ were written by the reference's members compiled
+over the same restated third-party layer. tests/test_grid_files.py checks the product against this module and against
 the reference's own members - SignedDistanceField<T> and OccupancyMap, headers and sources
 unmodified - compiled over oracle/ref_shim (which restates the same third-party layer).
 """
