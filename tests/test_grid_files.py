@@ -137,6 +137,22 @@ def test_errors_are_the_references(tmp_path):
         grid_files.LoadSignedDistanceFieldFromFile(double_path, np.float32)
 
 
+def test_members_named_like_the_references(tmp_path):
+    # SignedDistanceField<T>::SaveToFile(sdf, path, compress) / ::LoadFromFile(path) and the same
+    # pair on OccupancyMap, as static members of the mirror classes
+    rng = np.random.default_rng(13)
+    sdf = make_sdf(rng, np.float32)
+    path = tmp_path / "member.sdf"
+    grids.SignedDistanceField.SaveToFile(sdf, path, True)
+    loaded = grids.SignedDistanceField.LoadFromFile(path)
+    assert np.array_equal(loaded.GetImmutableRawData(), sdf.GetImmutableRawData())
+    sizes = grids.VoxelGridSizes.FromVoxelCounts(0.5, (2, 3, 4))
+    occupancy_map = grids.OccupancyMap(np.eye(4), "m", sizes, default_occupancy=0.5)
+    grids.OccupancyMap.SaveToFile(occupancy_map, tmp_path / "member.cmg", False)
+    again = grids.OccupancyMap.LoadFromFile(tmp_path / "member.cmg")
+    assert np.array_equal(again.GetImmutableRawData(), occupancy_map.GetImmutableRawData())
+
+
 def test_empty_frame_and_single_cell(tmp_path):
     sizes = grids.VoxelGridSizes.FromVoxelCounts(1.0, (1, 1, 1))
     sdf = grids.SignedDistanceField(np.eye(4), "", sizes, np.array([[[2.5]]], dtype=np.float32), 0.0)

@@ -182,6 +182,17 @@ class SignedDistanceField:
             raise RuntimeError("Cannot get min/max of an unlocked SDF")
         return self._minimum_maximum
 
+    # --- files (signed_distance_field.hpp:643-722), through csrc/grid_files.cu -----------------
+    @staticmethod
+    def SaveToFile(sdf: "SignedDistanceField", filepath, compress: bool) -> None:
+        from . import grid_files
+        grid_files.SaveSignedDistanceFieldToFile(sdf, filepath, compress)
+
+    @staticmethod
+    def LoadFromFile(filepath, dtype=np.float32) -> "SignedDistanceField":
+        from . import grid_files
+        return grid_files.LoadSignedDistanceFieldFromFile(filepath, dtype)
+
 
 class OccupancyMap:
     """Dense occupancy grid: one float per cell, <0.5 free, 0.5 unknown, >0.5 filled
@@ -252,6 +263,17 @@ class OccupancyMap:
     def copy(self) -> "OccupancyMap":
         return OccupancyMap(self._origin_transform, self._frame, self._sizes,
                             data=self._data.copy())
+
+    # --- files (occupancy_map.cpp:116-193), through csrc/grid_files.cu -------------------------
+    @staticmethod
+    def SaveToFile(occupancy_map: "OccupancyMap", filepath, compress: bool) -> None:
+        from . import grid_files
+        grid_files.SaveOccupancyMapToFile(occupancy_map, filepath, compress)
+
+    @staticmethod
+    def LoadFromFile(filepath) -> "OccupancyMap":
+        from . import grid_files
+        return grid_files.LoadOccupancyMapFromFile(filepath)
 
     # --- the path's entry points (occupancy_map.hpp:174-216, occupancy_map.cpp:250-260) ----
     def ExtractSignedDistanceField(self, parameters: SignedDistanceFieldGenerationParameters,
