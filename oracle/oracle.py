@@ -73,7 +73,8 @@ def build(force: bool = False) -> Path:
 
 def build_reference(force: bool = False) -> Path | None:
     """Compiles the reference's own EDT source (needs /root/reference). None if absent."""
-    if _REF_PATH.exists() and not force:
+    maps_path = _REF_PATH.with_name("libvgt_ref_maps.so")
+    if _REF_PATH.exists() and maps_path.exists() and not force:
         return _REF_PATH
     if not Path("/root/reference/src/voxelized_geometry_tools"
                 "/signed_distance_field_generation.cpp").exists():
