@@ -146,6 +146,16 @@ def test_members_named_like_the_references(tmp_path):
     grids.SignedDistanceField.SaveToFile(sdf, path, True)
     loaded = grids.SignedDistanceField.LoadFromFile(path)
     assert np.array_equal(loaded.GetImmutableRawData(), sdf.GetImmutableRawData())
+    # without a dtype the scalar type is found from the file
+    for dtype in (np.float32, np.float64):
+        typed = tmp_path / f"typed_{np.dtype(dtype).name}.sdf"
+        original = make_sdf(rng, dtype, shape=(3, 5, 2))
+        grids.SignedDistanceField.SaveToFile(original, typed, False)
+        found = grids.SignedDistanceField.LoadFromFile(typed)
+        assert found.GetImmutableRawData().dtype == np.dtype(dtype)
+        assert np.array_equal(found.GetImmutableRawData(), original.GetImmutableRawData())
+    with pytest.raises(ValueError, match="File does not exist"):
+        grids.SignedDistanceField.LoadFromFile(tmp_path / "nothing.sdf")
     sizes = grids.VoxelGridSizes.FromVoxelCounts(0.5, (2, 3, 4))
     occupancy_map = grids.OccupancyMap(np.eye(4), "m", sizes, default_occupancy=0.5)
     grids.OccupancyMap.SaveToFile(occupancy_map, tmp_path / "member.cmg", False)

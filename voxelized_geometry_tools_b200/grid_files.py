@@ -71,9 +71,19 @@ def SaveSignedDistanceFieldToFile(sdf: SignedDistanceField, filepath, compress: 
     _save(filepath, _sdf_kind(data.dtype), compress, data, info, sdf.Frame())
 
 
-def LoadSignedDistanceFieldFromFile(filepath, dtype=np.float32) -> SignedDistanceField:
+def LoadSignedDistanceFieldFromFile(filepath, dtype=None) -> SignedDistanceField:
     """SignedDistanceField<T>::LoadFromFile (signed_distance_field.hpp:670-722); a file saved
-    locked comes back locked, with its extrema recomputed like Lock() does (:579-592)."""
+    locked comes back locked, with its extrema recomputed like Lock() does (:579-592).
+    dtype plays the part of the reference's template argument; None = whichever of float32 /
+    float64 the file parses as (the format does not name its scalar type, but the cell count
+    and the voxel counts only agree for the right one)."""
+    if dtype is None:
+        try:
+            return LoadSignedDistanceFieldFromFile(filepath, np.float32)
+        except ValueError as first_error:
+            if str(first_error).startswith("File"):   # missing / too small / wrong magic
+                raise
+            return LoadSignedDistanceFieldFromFile(filepath, np.float64)
     cells, origin, sizes, frame, info = _load(filepath, _sdf_kind(dtype), np.dtype(dtype))
     sdf = SignedDistanceField(origin, frame, sizes, cells, info.oob_value)
     if info.locked:

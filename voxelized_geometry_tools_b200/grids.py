@@ -189,7 +189,7 @@ class SignedDistanceField:
         grid_files.SaveSignedDistanceFieldToFile(sdf, filepath, compress)
 
     @staticmethod
-    def LoadFromFile(filepath, dtype=np.float32) -> "SignedDistanceField":
+    def LoadFromFile(filepath, dtype=None) -> "SignedDistanceField":
         from . import grid_files
         return grid_files.LoadSignedDistanceFieldFromFile(filepath, dtype)
 
