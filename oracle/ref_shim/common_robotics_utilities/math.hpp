@@ -25,6 +25,12 @@ inline T Interpolate(const T& p1, const T& p2, const double ratio)
 {
   return (p1 * (1.0 - ratio)) + (p2 * ratio);
 }
+// (scalars by value, so that a constexpr local can be passed from a capture-less lambda:
+// test/voxel_raycasting_test.cpp:40-45)
+inline double Interpolate(const double p1, const double p2, const double ratio)
+{
+  return (p1 * (1.0 - ratio)) + (p2 * ratio);
+}
 
 template <typename T>
 inline T TrilinearInterpolate(

@@ -9,6 +9,8 @@
 #include <cstdint>
 #include <stdexcept>
 
+#include <common_robotics_utilities/openmp_helpers.hpp>
+
 #ifdef _OPENMP
 #include <omp.h>
 #endif

@@ -29,6 +29,9 @@ inline std::vector<Key> GetKeysFromSetLike(const SetLike& set_like)
   return std::vector<Key>(set_like.begin(), set_like.end());
 }
 
+// (test/voxel_raycasting_test.cpp:17, 88-92: a source of uniform draws from [0, 1))
+using UniformUnitRealFunction = std::function<double()>;
+
 // (topology_computation.hpp:335, occupancy_component_map.hpp:267: an optional message sink)
 using LoggingFunction = std::function<void(const std::string&)>;
 
