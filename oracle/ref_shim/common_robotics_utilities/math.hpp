@@ -7,12 +7,17 @@
 // stays parity-unpinned (tolerance 1e-12 relative, oracle/sdf_queries_oracle.py).
 #pragma once
 
+#include <vector>
+
 #include <Eigen/Geometry>
 
 namespace common_robotics_utilities
 {
 namespace math
 {
+// (test/pointcloud_voxelization_test.cpp:78: a cloud as a vector of points)
+using VectorVector3d = std::vector<Eigen::Vector3d>;
+
 inline double ClampedRatio(const double query, const double low, const double high)
 {
   const double ratio = (query - low) / (high - low);

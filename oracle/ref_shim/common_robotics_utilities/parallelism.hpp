@@ -86,6 +86,13 @@ void StaticParallelForRangeLoop(
     functor(ThreadWorkRange(begin, end, t));
   }
 }
+// (device_pointcloud_voxelization.cpp:147-149: one item per cloud; the order in which items are
+// handed out does not matter to the caller, a static split serves)
+template <typename Functor>
+void DynamicParallelForIndexLoop(
+    const DegreeOfParallelism& parallelism, int64_t range_start, int64_t range_end,
+    const Functor& functor, ParallelForBackend backend = ParallelForBackend::BEST_AVAILABLE);
+
 template <typename Functor>
 void StaticParallelForIndexLoop(
     const DegreeOfParallelism& parallelism, int64_t range_start, int64_t range_end,
@@ -101,6 +108,13 @@ void StaticParallelForIndexLoop(
         }
       },
       backend);
+}
+template <typename Functor>
+void DynamicParallelForIndexLoop(
+    const DegreeOfParallelism& parallelism, int64_t range_start, int64_t range_end,
+    const Functor& functor, ParallelForBackend backend)
+{
+  StaticParallelForIndexLoop(parallelism, range_start, range_end, functor, backend);
 }
 }  // namespace parallelism
 }  // namespace common_robotics_utilities

@@ -78,6 +78,7 @@ public:
   int64_t TotalVoxels() const { return counts_.x * counts_.y * counts_.z; }
   double VoxelXSize() const { return voxel_size_; }
   double InvVoxelXSize() const { return 1.0 / voxel_size_; }
+  double InverseVoxelXSize() const { return InvVoxelXSize(); }
   Eigen::Vector3d Sizes() const
   {
     return Eigen::Vector3d(static_cast<double>(counts_.x) * voxel_size_,
@@ -262,6 +263,9 @@ public:
   int64_t NumTotalVoxels() const { return sizes_.TotalVoxels(); }
   double VoxelXSize() const { return sizes_.VoxelXSize(); }
   Eigen::Vector3d GridSizes() const { return sizes_.Sizes(); }
+  double GridXSize() const { return sizes_.Sizes()(0); }
+  double GridYSize() const { return sizes_.Sizes()(1); }
+  double GridZSize() const { return sizes_.Sizes()(2); }
 
   bool CheckGridIndexInBounds(int64_t x, int64_t y, int64_t z) const
   {
